@@ -1,0 +1,102 @@
+/* vpfp_b200.h -- C ABI of the B200-native VPFP phase-space update (libvpfp_b200.so).
+ *
+ * Drop-in boundary for the per-timestep hot path of VlaPy (pure Python reference; paths below
+ * are relative to its source tree).  One entry point per reference operator; a maintainer binds
+ * them with ctypes from the reference's factory functions.
+ *
+ * Conventions
+ *  - every pointer is DEVICE memory owned by the caller (torch tensors: tensor.data_ptr());
+ *    f is fp64, row-major (batch*nx rows, nv contiguous) with row stride `ld` doubles (ld >= nv);
+ *  - kernels are enqueued on `stream` (a cudaStream_t passed as void*) and never synchronise;
+ *  - return 0 on success, non-zero on error (no exceptions cross the ABI); vpfp_last_error()
+ *    gives the message; VPFP_ERR_UNSUPPORTED maps to Python NotImplementedError;
+ *  - the library keeps only twiddle tables and reduction scratch (cached per device, freed by
+ *    vpfp_shutdown()); there is no CPU fallback anywhere.
+ */
+#ifndef VPFP_B200_H
+#define VPFP_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VPFP_ABI_VERSION 1
+
+#define VPFP_OK 0
+#define VPFP_ERR_ARG 1          /* bad argument                                   */
+#define VPFP_ERR_UNSUPPORTED 2  /* size/flavour not implemented (NotImplementedError) */
+#define VPFP_ERR_CUDA 3         /* a CUDA runtime call failed                      */
+
+/* flags for the advection operators */
+#define VPFP_PHASE_EXACT 0   /* per-bin sincos of theta = (k*dt)*c, the reference's own rounding */
+#define VPFP_PHASE_TABLE 1   /* geometric phase tables (needs a uniform fftfreq wavenumber grid) */
+
+/* collision operator ids (vlapy/core/collisions.py:292-317) */
+#define VPFP_FP_LB 0
+#define VPFP_FP_DG 1
+
+int vpfp_abi_version(void);
+const char *vpfp_last_error(void);
+int vpfp_shutdown(void);
+
+/* e df/dv, exponential integrator: f_out = Re ifft_v( exp(-i kv dt e[x]) fft_v f_in ).
+ * Replaces vlapy/core/vlasov.py:113-140 (step_edfdv_exponential).
+ * f_in/f_out: (rows, nv) with row strides ld_in/ld_out; e: (rows); kv: (nv) = 2*pi*fftfreq.
+ * rows = batch*nx (the operator is independent per row). nv must be a power of two >= 4. */
+int vpfp_edfdv_exp(const double *f_in, long ld_in, double *f_out, long ld_out, const double *e,
+                   const double *kv, double dt, int rows, int nv, int flags, void *stream);
+
+/* v df/dx, exponential integrator: f_out = Re ifft_x( exp(-i kx dt v) fft_x f_in ).
+ * Replaces vlapy/core/vlasov.py:83-110 (step_vdfdx_exponential).
+ * f: (batch, nx, ncols) row stride ld; kx: (batch, nx) per-simulation wavenumbers; v: (ncols).
+ * ncols may be a v-slice (multi-GPU v-sharded layout); it must be even, nx a power of two. */
+int vpfp_vdfdx_exp(const double *f_in, long ld_in, double *f_out, long ld_out, const double *kx,
+                   const double *v, double dt, int batch, int nx, int ncols, int flags,
+                   void *stream);
+
+/* e df/dv, 2nd-order centred differences: f_out = f - e * gradient_v(f) * dt (edge_order=2).
+ * Replaces vlapy/core/vlasov.py:143-165. */
+int vpfp_edfdv_cd2(const double *f_in, long ld_in, double *f_out, long ld_out, const double *e,
+                   double dt, double dv, int rows, int nv, void *stream);
+
+/* v-moments per row: out[k*out_ld + row], k = 0..nmom-1:
+ *   k<6: trapz_v(f v^k)   (n, j, T, q, fv4, vN; vlapy/core/step.py:164-171, field.py:27-36)
+ *   k=6: trapz_v(f^2), k=7: trapz_v(f ln f)   (step.py:216-224; NaN where f <= 0 like numpy)
+ * v0/v1 give trapz end weights: the first/last LOCAL column gets weight dv/2 only when it is the
+ * global first/last velocity cell (flags bit0 = has global first, bit1 = has global last). */
+int vpfp_moments(const double *f, long ld, const double *v, double dv, double *out, long out_ld,
+                 int nmom, int rows, int ncols, int edge_flags, void *stream);
+
+/* Spectral Poisson: e = driver + Re ifft( i one_over_kx fft(1 - n) ).
+ * Replaces vlapy/core/field.py:39-88.  n, driver, e: (batch, nx); one_over_kx: (batch, nx).
+ * driver may be NULL.  Any nx >= 2 (powers of two use the FFT path, others a direct DFT). */
+int vpfp_poisson(const double *n, const double *one_over_kx, const double *driver, double *e,
+                 int batch, int nx, void *stream);
+
+/* Implicit Fokker-Planck step, one tridiagonal system in v per row:
+ * moments of f_in -> LB or Dougherty diagonals -> solve (A f_out = f_in).
+ * Replaces vlapy/core/collisions.py:26-160 + 222-265 via step.py:70-113.
+ * v: (nv). moments_out (nullable): (8, rows) moments of f_out laid out like vpfp_moments. */
+int vpfp_fp_step(const double *f_in, long ld_in, double *f_out, long ld_out, const double *v,
+                 double nu, double dt, double dv, int op, double *moments_out, long mom_ld,
+                 int rows, int nv, void *stream);
+
+/* First nmodes x-Fourier modes of f per v: out[(b*nmodes + m)*ncols + j] = sum_x f[b,x,j] w^(m x)
+ * as interleaved (re, im) doubles.  Replaces vlapy/core/step.py:130-135 (get_f_to_store). */
+int vpfp_xmodes(const double *f, long ld, double *out, int nmodes, int batch, int nx, int ncols,
+                void *stream);
+
+/* Ponderomotive driver E_d(x, t) summed over npulse pulses (vlapy/field_driver.py:24-50).
+ * pulses: host array of 7 doubles per pulse {k0, w0, a0, t_L, t_R, t_wL, t_wR}. x, out: device. */
+int vpfp_driver(const double *x, double t, const double *pulses, int npulse, double *out, int nx,
+                void *stream);
+
+/* Series reductions of one stored step (vlapy/core/step.py:202-224): out[0..6] =
+ * mean_x of moments rows n, j, T, mean(e^2), mean(de^2), mean_x of rows f2, flogf. */
+int vpfp_series(const double *moments, long mom_ld, const double *e, const double *de,
+                double *out, int nx, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VPFP_B200_H */

@@ -1,0 +1,110 @@
+"""ctypes loader for the HOST EMULATION of the kernel programs (tests only; see vpfp_emul.cpp)."""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+SO = os.path.join(HERE, "libvpfp_emul.so")
+SRC = os.path.join(HERE, "vpfp_emul.cpp")
+CSRC = os.path.join(os.path.dirname(os.path.dirname(HERE)), "vlapy_b200", "csrc")
+
+
+def build(force=False):
+    deps = [SRC] + [os.path.join(CSRC, n) for n in ("advect.h", "rowops.h", "vpfp_common.h")]
+    if force or not os.path.exists(SO) or any(os.path.getmtime(d) > os.path.getmtime(SO) for d in deps):
+        subprocess.check_call(["g++", "-O2", "-ffp-contract=off", "-std=c++17", "-shared", "-fPIC",
+                               "-o", SO, SRC])
+    return SO
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        _lib = ctypes.CDLL(build())
+    return _lib
+
+
+def _p(a):
+    return a.ctypes.data_as(ctypes.c_void_p) if a is not None else None
+
+
+c_long, c_int, c_double = ctypes.c_long, ctypes.c_int, ctypes.c_double
+
+
+def edfdv_exp(f, e, kv, dt, max_single=8192):
+    f = np.ascontiguousarray(f); out = np.empty_like(f)
+    rows, nv = f.shape
+    lib().emul_edfdv_exp(_p(f), c_long(nv), _p(out), c_long(nv), _p(np.ascontiguousarray(e)),
+                         _p(np.ascontiguousarray(kv)), c_double(dt), c_int(rows), c_int(nv), c_int(max_single))
+    return out
+
+
+def vdfdx_exp(f, kx, v, dt, batch=1, max_single=2048):
+    f = np.ascontiguousarray(f); out = np.empty_like(f)
+    ncols = f.shape[-1]
+    nx = f.shape[-2]
+    lib().emul_vdfdx_exp(_p(f), c_long(ncols), _p(out), c_long(ncols), _p(np.ascontiguousarray(kx)),
+                         _p(np.ascontiguousarray(v)), c_double(dt), c_int(batch), c_int(nx), c_int(ncols),
+                         c_int(max_single))
+    return out
+
+
+def poisson(n, ook, driver, max_single=8192):
+    n = np.ascontiguousarray(np.atleast_2d(n)); batch, nx = n.shape
+    ook = np.ascontiguousarray(np.broadcast_to(ook, n.shape))
+    drv = None if driver is None else np.ascontiguousarray(np.broadcast_to(driver, n.shape))
+    e = np.empty_like(n)
+    lib().emul_poisson(_p(n), _p(ook), _p(drv), _p(e), c_int(batch), c_int(nx), c_int(max_single))
+    return e
+
+
+def edfdv_cd2(f, e, dt, dv):
+    f = np.ascontiguousarray(f); out = np.empty_like(f); rows, nv = f.shape
+    lib().emul_edfdv_cd2(_p(f), c_long(nv), _p(out), c_long(nv), _p(np.ascontiguousarray(e)), c_double(dt),
+                         c_double(dv), c_int(rows), c_int(nv))
+    return out
+
+
+def moments(f, v, dv, nmom=8, edge_flags=3):
+    f = np.ascontiguousarray(f); rows, ncols = f.shape
+    out = np.zeros((nmom, rows))
+    lib().emul_moments(_p(f), c_long(ncols), _p(np.ascontiguousarray(v)), c_double(dv), _p(out), c_long(rows),
+                       c_int(nmom), c_int(rows), c_int(ncols), c_int(edge_flags))
+    return out
+
+
+def fp_step(f, v, nu, dt, dv, op, want_moments=False, m=0):
+    f = np.ascontiguousarray(f); out = np.empty_like(f); rows, nv = f.shape
+    mom = np.zeros((8, rows)) if want_moments else None
+    lib().emul_fp_step(_p(f), c_long(nv), _p(out), c_long(nv), _p(np.ascontiguousarray(v)), c_double(nu),
+                       c_double(dt), c_double(dv), c_int(0 if op == "lb" else 1), _p(mom), c_long(rows),
+                       c_int(rows), c_int(nv), c_int(m))
+    return (out, mom) if want_moments else out
+
+
+def xmodes(f, nmodes=2):
+    f = np.ascontiguousarray(f); nx, ncols = f.shape
+    out = np.zeros((nmodes, ncols, 2))
+    lib().emul_xmodes(_p(f), c_long(ncols), _p(out), c_int(nmodes), c_int(1), c_int(nx), c_int(ncols))
+    return out[..., 0] + 1j * out[..., 1]
+
+
+def driver(x, t, pulses):
+    arr = np.array([[p["k0"], p["w0"], p["a0"], p["t_L"], p["t_R"], p["t_wL"], p["t_wR"]]
+                    for p in pulses.values()], dtype=np.float64)
+    out = np.empty_like(x)
+    lib().emul_driver(_p(np.ascontiguousarray(x)), c_double(t), _p(arr), c_int(arr.shape[0]), _p(out), c_int(x.size))
+    return out
+
+
+def series(mom, e, de):
+    out = np.zeros(7)
+    mom = np.ascontiguousarray(mom)
+    lib().emul_series(_p(mom), c_long(mom.shape[1]), _p(np.ascontiguousarray(e)), _p(np.ascontiguousarray(de)),
+                      _p(out), c_int(e.size))
+    return out

@@ -1,0 +1,172 @@
+// vpfp_emul.cpp -- HOST EMULATION of the CUDA phase programs, TEST INFRASTRUCTURE ONLY.
+//
+// Compiles the very same program sources as the GPU library (vlapy_b200/csrc/advect.h, rowops.h)
+// with g++ and runs every CTA's phases sequentially over its threads, so that the tile index
+// arithmetic and the numerics can be checked against the oracle on the CPU-only build box
+// (tests/test_emul_kernels.py).  It is never loaded by the product package, is not a fallback,
+// and is not built by __graft_entry__.build() as part of the product library.
+#include <cstdlib>
+#include <cstring>
+#include <cmath>
+#include <vector>
+
+#include "../../vlapy_b200/csrc/advect.h"
+#include "../../vlapy_b200/csrc/rowops.h"
+
+template <class Prog>
+static void run_prog(const Prog& prog, long nblocks, int threads, long smem_bytes, int nph) {
+  std::vector<unsigned char> smem((size_t)(smem_bytes > 0 ? smem_bytes : 16) + 64);
+  unsigned char* base = smem.data();
+  base += (16 - ((uintptr_t)base & 15)) & 15;
+  for (long blk = 0; blk < nblocks; ++blk)
+    for (int ph = 0; ph < nph; ++ph)
+      for (int tid = 0; tid < threads; ++tid) prog.phase(ph, blk, tid, threads, base);
+}
+
+static std::vector<cplx> make_tw(int N) {
+  std::vector<cplx> h((size_t)N);
+  const long double two_pi = 6.283185307179586476925286766559005768L;
+  for (int m = 0; m < N; ++m) {
+    long double a = two_pi * (long double)m / (long double)N;
+    h[m].x = (double)cosl(a);
+    h[m].y = (double)(-sinl(a));
+  }
+  h[0].x = 1.0; h[0].y = 0.0;
+  if (N % 4 == 0) { h[N / 4].x = 0.0; h[N / 4].y = -1.0; h[3 * N / 4].x = 0.0; h[3 * N / 4].y = 1.0; }
+  if (N % 2 == 0) { h[N / 2].x = -1.0; h[N / 2].y = 0.0; }
+  return h;
+}
+
+static void run_advect(AdvectProg a, int max_cols, int max_rows) {
+  const AdvectPlan pl = make_advect_plan(a.mode, a.N, max_cols, max_rows);
+  std::vector<cplx> tw = make_tw(a.N);
+  a.tw = tw.data();
+  if (pl.N1 == 1) {
+    advect_set_pass(a, pl, 0);
+    run_prog(a, a.ntiles(), pl.threads[0], a.smem_bytes(), a.nphases());
+    return;
+  }
+  std::vector<double> phantom((size_t)a.N, 0.0);
+  if (a.mode == ADV_ROWS && (a.nrows & 1)) a.phantom = phantom.data();
+  for (int pass = 1; pass <= 3; ++pass) {
+    advect_set_pass(a, pl, pass);
+    run_prog(a, a.ntiles(), pl.threads[pass], a.smem_bytes(), a.nphases());
+  }
+}
+
+extern "C" {
+
+// max_single_* let the tests force the three-pass decomposition at small sizes.
+int emul_edfdv_exp(const double* f_in, long ld_in, double* f_out, long ld_out, const double* e,
+                   const double* kv, double dt, int rows, int nv, int max_single) {
+  AdvectProg a;
+  memset(&a, 0, sizeof(a));
+  a.mode = ADV_ROWS; a.op = OP_PHASE; a.N = nv;
+  a.nsim = 1; a.nrows = rows; a.nseq = (rows + 1) / 2;
+  a.fin = f_in; a.ld_in = ld_in; a.fout = f_out; a.ld_out = ld_out;
+  a.kvec = kv; a.cvec = e; a.addv = nullptr; a.dt = dt;
+  run_advect(a, max_single, max_single);
+  return 0;
+}
+
+int emul_vdfdx_exp(const double* f_in, long ld_in, double* f_out, long ld_out, const double* kx,
+                   const double* v, double dt, int batch, int nx, int ncols, int max_single) {
+  AdvectProg a;
+  memset(&a, 0, sizeof(a));
+  a.mode = ADV_COLS; a.op = OP_PHASE; a.N = nx;
+  a.nsim = batch; a.nrows = nx; a.nseq = ncols / 2;
+  a.fin = f_in; a.ld_in = ld_in; a.fout = f_out; a.ld_out = ld_out;
+  a.kvec = kx; a.cvec = v; a.addv = nullptr; a.dt = dt;
+  run_advect(a, max_single, max_single);
+  return 0;
+}
+
+int emul_poisson(const double* n, const double* ook, const double* driver, double* e, int batch,
+                 int nx, int max_single) {
+  AdvectProg a;
+  memset(&a, 0, sizeof(a));
+  a.mode = ADV_ROWS; a.op = OP_POISSON; a.N = nx;
+  a.nsim = 1; a.nrows = batch; a.nseq = (batch + 1) / 2;
+  a.fin = n; a.ld_in = nx; a.fout = e; a.ld_out = nx;
+  a.kvec = ook; a.cvec = nullptr; a.addv = driver; a.dt = 0.0;
+  run_advect(a, max_single, max_single);
+  return 0;
+}
+
+int emul_edfdv_cd2(const double* f_in, long ld_in, double* f_out, long ld_out, const double* e,
+                   double dt, double dv, int rows, int nv) {
+  Cd2Prog p;
+  p.fin = f_in; p.ld_in = ld_in; p.fout = f_out; p.ld_out = ld_out; p.e = e;
+  p.dt = dt; p.dv = dv; p.rows = rows; p.nv = nv;
+  const int threads = 256;
+  p.cblocks = (nv + threads * 4 - 1) / (threads * 4);
+  run_prog(p, (long)rows * p.cblocks, threads, 0, 1);
+  return 0;
+}
+
+int emul_moments(const double* f, long ld, const double* v, double dv, double* out, long out_ld,
+                 int nmom, int rows, int ncols, int edge_flags) {
+  MomentsProg p;
+  p.f = f; p.ld = ld; p.v = v; p.dv = dv; p.out = out; p.out_ld = out_ld;
+  p.nmom = nmom; p.rows = rows; p.ncols = ncols; p.edge_flags = edge_flags;
+  int threads = 256;
+  while (threads > 32 && threads * 2 > ncols) threads >>= 1;
+  run_prog(p, rows, threads, p.smem_bytes(threads), p.nphases(threads));
+  return 0;
+}
+
+int emul_fp_step(const double* f_in, long ld_in, double* f_out, long ld_out, const double* v,
+                 double nu, double dt, double dv, int op, double* moments_out, long mom_ld,
+                 int rows, int nv, int m_override) {
+  FpProg p;
+  p.fin = f_in; p.ld_in = ld_in; p.fout = f_out; p.ld_out = ld_out; p.v = v;
+  p.nu = nu; p.dt = dt; p.dv = dv; p.op = op; p.mom_out = moments_out; p.mom_ld = mom_ld;
+  p.rows = rows; p.nv = nv;
+  int m = nv / 256;
+  if (m < 4) m = 4;
+  if (m > 16) m = 16;
+  if (m_override > 0) m = m_override;
+  p.m = m;
+  p.P = nv / m;
+  int threads = ((p.P + 31) / 32) * 32;
+  if (threads > 1024) threads = 1024;
+  run_prog(p, rows, threads, p.smem_bytes(threads), p.nphases(threads));
+  return 0;
+}
+
+int emul_xmodes(const double* f, long ld, double* out, int nmodes, int batch, int nx, int ncols) {
+  XmodesProg p;
+  p.f = f; p.ld = ld; p.nmodes = nmodes; p.batch = batch; p.nx = nx; p.ncols = ncols;
+  const int threads = 128;
+  p.cblocks = (ncols + threads - 1) / threads;
+  int xch = nx / 64;
+  if (xch < 1) xch = 1;
+  if (xch > 64) xch = 64;
+  p.xchunks = xch;
+  std::vector<double> partial((size_t)batch * xch * nmodes * ncols * 2);
+  p.partial = partial.data();
+  run_prog(p, (long)batch * xch * p.cblocks, threads, 0, 1);
+  XmodesReduceProg r;
+  r.partial = p.partial; r.out = out; r.nmodes = nmodes; r.batch = batch; r.ncols = ncols; r.xchunks = xch;
+  long total = (long)batch * nmodes * ncols * 2;
+  run_prog(r, (total + 255) / 256, 256, 0, 1);
+  return 0;
+}
+
+int emul_driver(const double* x, double t, const double* pulses, int npulse, double* out, int nx) {
+  DriverProg p;
+  p.x = x; p.out = out; p.t = t; p.nx = nx; p.npulse = npulse;
+  for (int i = 0; i < npulse * 7; ++i) p.pulses[i] = pulses[i];
+  run_prog(p, (nx + 255) / 256, 256, 0, 1);
+  return 0;
+}
+
+int emul_series(const double* moments, long mom_ld, const double* e, const double* de, double* out, int nx) {
+  SeriesProg p;
+  p.mom = moments; p.mom_ld = mom_ld; p.e = e; p.de = de; p.out = out; p.nx = nx;
+  int threads = 256;
+  while (threads > 32 && threads > nx) threads >>= 1;
+  run_prog(p, 1, threads, p.smem_bytes(threads), p.nphases(threads));
+  return 0;
+}
+}

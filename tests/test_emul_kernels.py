@@ -1,0 +1,160 @@
+"""CPU check of the kernel *programs* (vlapy_b200/csrc/advect.h, rowops.h): the same sources that
+nvcc compiles for sm_100a are compiled with g++ and run thread-by-thread (tests/emul/), then
+compared with the golden fixtures / oracle at the parity tolerance of BASELINE.json (1e-12).
+This validates index arithmetic and numerics where no GPU exists; the -m gpu tests repeat the
+comparison on the real kernels."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+from conftest import golden, rel_err
+from oracle import vpfp_oracle as O
+
+sys.path.insert(0, os.path.join(os.path.dirname(__file__), "emul"))
+import emul_lib as E  # noqa: E402
+
+TOL = 1e-12
+
+
+@pytest.mark.parametrize("name", ["ops_small", "ops_c1", "ops_white"])
+@pytest.mark.parametrize("max_single", [8192, 8])
+def test_advection_programs(name, max_single):
+    g = golden(name)
+    f, e, dt = g["f"], g["e"], float(g["dt"])
+    assert rel_err(E.vdfdx_exp(f, g["kx"], g["v"], dt, max_single=max_single), g["vdfdx"]) < TOL
+    assert rel_err(E.vdfdx_exp(f, g["kx"], g["v"], -0.066 * dt, max_single=max_single), g["vdfdx_neg"]) < TOL
+    assert rel_err(E.edfdv_exp(f, e, g["kv"], 0.5 * dt, max_single=max_single), g["edfdv"]) < TOL
+    assert rel_err(E.edfdv_exp(f, e, g["kv"], -0.21 * dt, max_single=max_single), g["edfdv_neg"]) < TOL
+
+
+@pytest.mark.parametrize("shape", [(2, 4), (4, 8), (6, 16), (3, 64), (64, 4), (7, 128), (1, 32), (5, 256)])
+@pytest.mark.parametrize("max_single", [8192, 4, 16])
+def test_edfdv_shapes(shape, max_single):
+    """rows: any count (odd counts leave the last packed channel empty); nv: powers of two."""
+    nx, nv = shape
+    rng = np.random.default_rng(nx * 1000 + nv)
+    f = rng.standard_normal((nx, nv))
+    e = rng.standard_normal(nx)
+    dv, v, kv = O.velocity_grid(6.4, nv)
+    assert rel_err(E.edfdv_exp(f, e, kv, 0.37, max_single=max_single), O.edfdv_exponential(f, e, 0.37, kv)) < TOL
+
+
+@pytest.mark.parametrize("shape", [(2, 4), (4, 2), (8, 6), (16, 18), (64, 2), (128, 6), (32, 34), (256, 4)])
+@pytest.mark.parametrize("max_single", [8192, 4, 16])
+def test_vdfdx_shapes(shape, max_single):
+    """nx: powers of two; column count: any even number (ragged last tile)."""
+    nx, nv = shape
+    rng = np.random.default_rng(nx * 1000 + nv)
+    f = rng.standard_normal((nx, nv))
+    v = np.linspace(-6.0, 6.0, nv)
+    dx, x, kx, ook = O.spatial_grid(0.0, 20.0, nx)
+    assert rel_err(E.vdfdx_exp(f, kx, v, 0.37, max_single=max_single), O.vdfdx_exponential(f, 0.37, kx, v)) < TOL
+
+
+def test_vdfdx_batched_sims_have_their_own_kx():
+    rng = np.random.default_rng(5)
+    batch, nx, nv = 3, 16, 8
+    f = rng.standard_normal((batch, nx, nv))
+    dv, v, kv = O.velocity_grid(6.4, nv)
+    kxs = np.stack([O.spatial_grid(0.0, 2 * np.pi / k0, nx)[2] for k0 in (0.25, 0.3, 0.45)])
+    out = E.vdfdx_exp(f, kxs, v, 0.2, batch=batch)
+    for b in range(batch):
+        assert rel_err(out[b], O.vdfdx_exponential(f[b], 0.2, kxs[b], v)) < TOL
+
+
+@pytest.mark.parametrize("max_single", [8192, 8])
+def test_poisson_program(max_single):
+    for name in ("ops_small", "ops_c1", "ops_white"):
+        g = golden(name)
+        e = E.poisson(g["charges"], g["one_over_kx"], g["drv"], max_single=max_single)[0]
+        assert rel_err(e, g["efield"]) < TOL
+    # several rows (odd count) with different one_over_kx rows
+    rng = np.random.default_rng(3)
+    n = 1.0 + 0.1 * rng.standard_normal((5, 64))
+    ooks = np.stack([O.spatial_grid(0.0, 2 * np.pi / k0, 64)[3] for k0 in (0.25, 0.3, 0.35, 0.4, 0.45)])
+    drv = 0.01 * rng.standard_normal((5, 64))
+    e = E.poisson(n, ooks, drv, max_single=max_single)
+    for i in range(5):
+        assert rel_err(e[i], drv[i] + O.solve_for_field(n[i], ooks[i])) < TOL
+
+
+def test_cd2_moments_modes_series_driver():
+    for name in ("ops_small", "ops_c1"):
+        g = golden(name)
+        dv, dt = float(g["dv"]), float(g["dt"])
+        assert rel_err(E.edfdv_cd2(g["f"], g["e"], 0.5 * dt, dv), g["cd2"]) < TOL
+        mom = E.moments(g["fpos"], g["v"], dv)
+        assert rel_err(mom[:6], g["moments"]) < TOL
+        assert rel_err(E.moments(g["f"], g["v"], dv, nmom=1)[0], g["charges"]) < TOL
+        ser = E.series(mom, g["e"], g["drv"])
+        np.testing.assert_allclose(ser, g["series"], rtol=1e-12)
+        assert rel_err(E.xmodes(g["fpos"]), g["modes"]) < 1e-12
+    cfg = O.landau_config()
+    for t in (0.0, 3.3, 7.7, 21.0):
+        np.testing.assert_allclose(E.driver(cfg["x"], t, cfg["pulses"]), cfg["driver_function"](t),
+                                   rtol=1e-13, atol=1e-22)
+
+
+def test_moments_nan_semantics_of_flogf():
+    g = golden("ops_small")
+    mom = E.moments(g["f"], g["v"], float(g["dv"]))     # f has negative cells -> log() is NaN
+    ref = O.series_moments(g["f"], g["e"], g["drv"], O.field_moments(g["f"], g["v"], float(g["dv"])), float(g["dv"]))
+    assert np.isnan(ref[6]) and np.isnan(mom[7]).any()
+
+
+@pytest.mark.parametrize("op", ["lb", "dg"])
+def test_fp_program_vs_reference(op):
+    for name in ("ops_small", "ops_c1", "ops_white"):
+        g = golden(name)
+        out, mom = E.fp_step(g["fpos"], g["v"], float(g["nu"]), float(g["dt"]), float(g["dv"]), op, want_moments=True)
+        assert rel_err(out, g[op + "_solve"]) < TOL
+        assert rel_err(mom[:6], O.field_moments(g[op + "_solve"], g["v"], float(g["dv"]))) < TOL
+
+
+def fp_longdouble(f, v, nu, dt, dv, op):
+    """The reference algorithm (moments, diagonals, Thomas) in extended precision: the yardstick
+    that separates algorithmic error from the conditioning of a stiff system."""
+    L = np.longdouble
+    f, v, nu, dt, dv = f.astype(L), v.astype(L), L(nu), L(dt), L(dv)
+    tr = lambda y: (dv * (y[..., 1:] + y[..., :-1]) / 2).sum(-1)  # noqa: E731
+    if op == "lb":
+        vbar, T = np.zeros(f.shape[0], L), tr(f * v ** 2)
+    else:
+        vbar = tr(f * v)
+        T = tr(f * (v[None, :] - vbar[:, None]) ** 2)
+    nx, nv = f.shape
+    a = nu * dt * (-T[:, None] / dv ** 2 + (v[None, :-1] - vbar[:, None]) / 2 / dv)
+    b = 1 + nu * dt * np.ones((nx, nv), L) * (2 * T[:, None] / dv ** 2)
+    c = nu * dt * (-T[:, None] / dv ** 2 - (v[None, 1:] - vbar[:, None]) / 2 / dv)
+    return O.thomas_batched(a, b, c, f).astype(np.float64)
+
+
+@pytest.mark.parametrize("op", ["lb", "dg"])
+@pytest.mark.parametrize("nu", [1e-2, 1.0, 30.0])
+@pytest.mark.parametrize("nv,m", [(8, 4), (24, 4), (100, 7), (1024, 0), (2048, 16), (4096, 0)])
+def test_fp_program_sizes_and_stiffness(op, nu, nv, m):
+    """Chunked elimination + cyclic reduction vs the reference's Thomas sweep.  For stiff systems
+    (nu*dt*T/dv^2 >> 1, condition number ~1e6) the reference itself is only good to ~1e-10, so the
+    bar is: within 1e-12 of the reference, or no further from the extended-precision solution
+    than a small multiple of the reference's own distance."""
+    dv, v, kv = O.velocity_grid(6.0, nv)
+    f = O.shifted_maxwellian(3, v, 1.0, 0.7) * np.array([1.0, 0.7, 1.3])[:, None]
+    ref = O.collision_step(f, v, nu, 0.1, dv, op)
+    out = E.fp_step(f, v, nu, 0.1, dv, op, m=m)
+    if rel_err(out, ref) < TOL:
+        return
+    truth = fp_longdouble(f, v, nu, 0.1, dv, op)
+    assert rel_err(out, truth) < 4 * rel_err(ref, truth) + TOL
+
+
+def test_fp_collision_unit_cases_16_steps():
+    g = golden("collisions_unit")
+    v, dv, nu, dt = g["v"], float(g["dv"]), float(g["nu"]), float(g["dt"])
+    for vshift in (0.0, 0.5, 1.5):
+        for op in ("lb", "dg"):
+            f = g["f_%g" % vshift].copy()
+            for _ in range(16):
+                f = E.fp_step(f, v, nu, dt, dv, op)
+            assert rel_err(f, g["out_%s_%g" % (op, vshift)]) < TOL

@@ -1,0 +1,329 @@
+"""GPU parity tests (-m gpu): the CUDA path, called through the operator mirrors / C ABI, against
+the golden fixtures (outputs of the reference itself) and the CPU oracle on seeded inputs.
+
+Tolerance: BASELINE.json asks for 1e-12 relative per operator in fp64, with the norm
+max|a-b| / max|b|.  Sizes here are ones the oracle finishes in seconds; full-size
+(16384^2) behaviour is covered by size-independent properties in test_gpu_fullsize.py."""
+import numpy as np
+import pytest
+
+from conftest import golden, rel_err
+from oracle import vpfp_oracle as O
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-12
+
+
+@pytest.fixture(scope="module")
+def dev():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from vlapy_b200 import _lib
+    _lib.lib()      # fail loudly if the extension is missing
+    return torch.device("cuda:0")
+
+
+def stuff_from(g_or_cfg, **extra):
+    keys = ("kx", "kv", "v", "x", "one_over_kx")
+    d = {k: np.asarray(g_or_cfg[k]) for k in keys}
+    d["dv"] = float(g_or_cfg["dv"])
+    d.update(extra)
+    return d
+
+
+@pytest.mark.parametrize("name", ["ops_small", "ops_c1", "ops_white"])
+def test_operators_vs_reference_outputs(dev, name):
+    from vlapy_b200.core import vlasov, field, step
+    g = golden(name)
+    f, e, dt, dv = g["f"], g["e"], float(g["dt"]), float(g["dv"])
+    nx, nv = f.shape
+    stuff = stuff_from(g, nx=nx, nv=nv)
+    vdfdx = vlasov.get_vdfdx(stuff, "exponential")
+    edfdv = vlasov.get_edfdv(stuff, "exponential")
+    cd2 = vlasov.get_edfdv(stuff, "cd2")
+    f_keep = f.copy()
+    assert rel_err(vdfdx(f, dt), g["vdfdx"]) < TOL
+    assert rel_err(vdfdx(f=f, dt=-0.066 * dt), g["vdfdx_neg"]) < TOL
+    assert rel_err(edfdv(f, e, 0.5 * dt), g["edfdv"]) < TOL
+    assert rel_err(edfdv(f=f, e=e, dt=-0.21 * dt), g["edfdv_neg"]) < TOL
+    assert rel_err(cd2(f, e, 0.5 * dt), g["cd2"]) < TOL
+    np.testing.assert_array_equal(f, f_keep)                      # operators are functional
+    assert rel_err(field.compute_charges(f, dv), g["charges"]) < TOL
+    fs = field.get_field_solver(stuff, "spectral")
+    assert rel_err(fs(g["drv"], f), g["efield"]) < TOL
+    assert rel_err(fs(driver_field=g["drv"], f=f), g["efield"]) < TOL
+    # device tensors in -> device tensors out
+    fd = torch.from_numpy(f).to(dev)
+    out = vdfdx(fd, dt)
+    assert isinstance(out, torch.Tensor) and out.is_cuda and out.data_ptr() != fd.data_ptr()
+    assert rel_err(out.cpu().numpy(), g["vdfdx"]) < TOL
+    # collisions through the reference's entry point (tests/test_collisions.py:205-211)
+    for op in ("lb", "dg"):
+        fp = step.get_collision_step(
+            stuff_for_time_loop=dict(f=g["fpos"], v=g["v"], nv=nv, nx=nx, nu=float(g["nu"]), dt=dt, dv=dv),
+            all_params={"fokker-planck": {"type": op, "solver": "batched_tridiagonal"}, "nu": float(g["nu"])})
+        assert rel_err(fp(g["fpos"]), g[op + "_solve"]) < TOL
+        assert rel_err(fp(f=g["fpos"]), g[op + "_solve"]) < TOL
+
+
+def test_stored_quantities_vs_reference_outputs(dev):
+    from vlapy_b200 import ops
+    for name in ("ops_small", "ops_c1", "ops_white"):
+        g = golden(name)
+        dv = float(g["dv"])
+        f = torch.from_numpy(g["fpos"]).to(dev)
+        v = torch.from_numpy(g["v"]).to(dev)
+        mom = ops.moments(f, v, dv)
+        assert rel_err(mom[:6].cpu().numpy(), g["moments"]) < TOL
+        ser = ops.series(mom, torch.from_numpy(g["e"]).to(dev), torch.from_numpy(g["drv"]).to(dev))
+        np.testing.assert_allclose(ser.cpu().numpy(), g["series"], rtol=1e-12)
+        modes = ops.xmodes(f, 2)[0].cpu().numpy()
+        assert rel_err(modes, g["modes"]) < TOL
+    # f ln f is NaN where f <= 0, as in numpy (vlapy/core/step.py:222-224)
+    g = golden("ops_small")
+    mom = ops.moments(torch.from_numpy(g["f"]).to(dev), torch.from_numpy(g["v"]).to(dev), float(g["dv"]))
+    assert torch.isnan(mom[7]).any()
+
+
+@pytest.mark.parametrize("shape", [(2, 4), (3, 64), (64, 512), (7, 2048), (6, 8192), (5, 16384), (34, 32768)])
+def test_edfdv_sizes_vs_oracle(dev, shape):
+    """every nv regime: one CTA per row pair (<= 8192) and the three-pass decomposition above,
+    odd row counts included."""
+    from vlapy_b200.core import vlasov
+    nx, nv = shape
+    rng = np.random.default_rng(nx + nv)
+    dv, v, kv = O.velocity_grid(6.4, nv)
+    f = O.maxwellian(nx, nv, 6.4) * (1 + 0.1 * rng.standard_normal((nx, 1))) + 1e-3 * rng.standard_normal((nx, nv))
+    e = 0.05 * rng.standard_normal(nx)
+    out = vlasov.get_edfdv_exponential(kv)(f, e, 0.125)
+    assert rel_err(out, O.edfdv_exponential(f, e, 0.125, kv)) < TOL
+
+
+@pytest.mark.parametrize("shape", [(2, 4), (32, 512), (256, 130), (2048, 34), (4096, 32), (16384, 18), (65536, 4)])
+def test_vdfdx_sizes_vs_oracle(dev, shape):
+    """every nx regime: whole columns in one CTA (<= 2048) and the three-pass decomposition,
+    ragged column tiles included."""
+    from vlapy_b200.core import vlasov
+    nx, nv = shape
+    rng = np.random.default_rng(nx + nv)
+    v = np.linspace(-6.4, 6.4, nv)
+    dx, x, kx, ook = O.spatial_grid(0.0, 2 * np.pi / 0.35, nx)
+    f = np.exp(-v ** 2 / 2)[None, :] * (1 + 0.1 * np.sin(0.35 * x))[:, None] + 1e-3 * rng.standard_normal((nx, nv))
+    out = vlasov.get_vdfdx_exponential(kx, v)(f, 0.25)
+    assert rel_err(out, O.vdfdx_exponential(f, 0.25, kx, v)) < TOL
+
+
+def test_vdfdx_ensemble_with_per_simulation_kx(dev):
+    from vlapy_b200.core import vlasov
+    rng = np.random.default_rng(11)
+    batch, nx, nv = 5, 64, 128
+    dv, v, kv = O.velocity_grid(6.4, nv)
+    k0s = np.linspace(0.25, 0.45, batch)
+    kxs = np.stack([O.spatial_grid(0.0, 2 * np.pi / k0, nx)[2] for k0 in k0s])
+    f = rng.standard_normal((batch, nx, nv))
+    out = vlasov.get_vdfdx_exponential(kxs, v)(f, 0.2)
+    for b in range(batch):
+        assert rel_err(out[b], O.vdfdx_exponential(f[b], 0.2, kxs[b], v)) < TOL
+
+
+def test_row_pitch_larger_than_row(dev):
+    """v-sharded / padded layouts: operators take a row pitch (ld) different from the row length."""
+    from vlapy_b200 import ops
+    rng = np.random.default_rng(2)
+    nx, nv = 64, 96
+    big = torch.from_numpy(rng.standard_normal((nx, 2 * nv))).to(dev)
+    f = big[:, 16:16 + nv]                       # pitch 192, 16-byte aligned offset
+    v = torch.linspace(-3, 3, nv, dtype=torch.float64, device=dev)
+    dx, x, kx, ook = O.spatial_grid(0.0, 20.0, nx)
+    out = ops.vdfdx_exp(f, torch.from_numpy(kx).to(dev), v, 0.3)
+    ref = O.vdfdx_exponential(f.cpu().numpy(), 0.3, kx, v.cpu().numpy())
+    assert rel_err(out.cpu().numpy(), ref) < TOL
+    mom = ops.moments(f, v, 0.1, nmom=6, edge_flags=1)   # local slice owning only the first global cell
+    w = np.full(nv, 0.1); w[0] = 0.05
+    np.testing.assert_allclose(mom[0].cpu().numpy(), (f.cpu().numpy() * w).sum(1), rtol=1e-13)
+
+
+def test_field_solver_unit_cases(dev):
+    """tests/test_fieldsolver.py of the reference (nx = 96, direct DFT path) + powers of two."""
+    from vlapy_b200.core import field
+    g = golden("fieldsolver_unit")
+    x, kp = g["x"], 0.25
+    analytic = [np.cos(kp * x) / kp, -np.sin(2 * kp * x) / 2.0 / kp,
+                np.cos(2 * kp * x) / 2.0 / kp - np.sin(8 * kp * x) / 8.0 / kp]
+    for i in range(3):
+        e = field.solve_for_field(charge_density=g["rho_%d" % i], one_over_kx=g["one_over_kx"])
+        assert rel_err(e, g["e_%d" % i]) < TOL
+        np.testing.assert_almost_equal(e, analytic[i], decimal=4)
+    rng = np.random.default_rng(4)
+    for nx in (2, 8, 1024, 8192, 16384, 65536):
+        dx, xx, kx, ook = O.spatial_grid(0.0, 17.0, nx)
+        n = 1.0 + 0.1 * rng.standard_normal(nx)
+        assert rel_err(field.solve_for_field(n, ook), O.solve_for_field(n, ook)) < TOL
+
+
+def test_collision_unit_cases(dev):
+    """tests/test_collisions.py of the reference: 16 steps at nx=2, nv=1024, nu=1e-2, dt=0.1."""
+    from vlapy_b200.core import step
+    g = golden("collisions_unit")
+    v, dv, nu, dt = g["v"], float(g["dv"]), float(g["nu"]), float(g["dt"])
+    for vshift in (0.0, 0.5, 1.5):
+        f0 = g["f_%g" % vshift]
+        for op in ("lb", "dg"):
+            fp = step.get_collision_step(
+                stuff_for_time_loop=dict(f=f0, v=v, nv=1024, nx=2, nu=nu, dt=dt, dv=dv),
+                all_params={"fokker-planck": {"type": op, "solver": "batched_tridiagonal"}, "nu": nu})
+            f = f0.copy()
+            for _ in range(16):
+                f = fp(f)
+            assert rel_err(f, g["out_%s_%g" % (op, vshift)]) < TOL
+            if vshift == 0.0:
+                np.testing.assert_almost_equal(f, f0, decimal=4)
+                np.testing.assert_almost_equal(O.trapz_last(f * v, dv), O.trapz_last(f0 * v, dv), decimal=4)
+            if vshift == 0.5:
+                np.testing.assert_almost_equal(O.trapz_last(f, dv), O.trapz_last(f0, dv), decimal=4)
+                np.testing.assert_almost_equal(O.trapz_last(f * v ** 2, dv), O.trapz_last(f0 * v ** 2, dv), decimal=4)
+            if vshift == 1.5 and op == "lb":
+                assert np.all(O.trapz_last(f * v, dv) < O.trapz_last(f0 * v, dv))
+            if vshift == 1.5 and op == "dg":
+                np.testing.assert_almost_equal(O.trapz_last(f * v, dv), O.trapz_last(f0 * v, dv), decimal=4)
+
+
+@pytest.mark.parametrize("op", ["lb", "dg"])
+@pytest.mark.parametrize("nv", [8, 64, 512, 2048, 4096, 16384])
+def test_fp_sizes_vs_oracle(dev, op, nv):
+    from vlapy_b200 import ops
+    dv, v, kv = O.velocity_grid(6.4, nv)
+    nu = 3.4e-6 if nv >= 4096 else 1e-3
+    f = O.shifted_maxwellian(5, v, 1.0, 0.3) * np.array([1.0, 0.7, 1.3, 0.2, 2.0])[:, None]
+    ref = O.collision_step(f, v, nu, 0.25, dv, op)
+    mom = torch.zeros((8, 5), dtype=torch.float64, device=dev)
+    out = ops.fp_step(torch.from_numpy(f).to(dev), torch.from_numpy(v).to(dev), nu, 0.25, dv, op, moments_out=mom)
+    assert rel_err(out.cpu().numpy(), ref) < TOL
+    assert rel_err(mom[:6].cpu().numpy(), O.field_moments(ref, v, dv)) < TOL
+
+
+def make_stuff(cfg, rules, with_pulses=True):
+    stuff = {k: cfg[k] for k in ("kx", "x", "one_over_kx", "v", "kv", "nv", "nx", "dv", "dt", "nu",
+                                 "driver_function")}
+    stuff.update(e=cfg["e0"], f=cfg["f0"], rules_to_store_f=rules)
+    if with_pulses:
+        stuff["pulse_dictionary"] = cfg["pulses"]
+    return stuff
+
+
+def make_params(cfg, integ="leapfrog", op="lb", edfdv="exponential"):
+    return {"backend": {"core": "b200"}, "nu": cfg["nu"],
+            "vlasov-poisson": {"time": integ, "vdfdx": "exponential", "edfdv": edfdv, "poisson": "spectral"},
+            "fokker-planck": {"type": op, "solver": "batched_tridiagonal"}}
+
+
+RULES = {"time": "first-last", "space": ["k0", "k1"]}
+
+
+@pytest.mark.parametrize("integ", ["leapfrog", "pefrl", "h-sixth"])
+@pytest.mark.parametrize("device_driver", [True, False])
+def test_vp50_schedules_vs_reference(dev, integ, device_driver):
+    """50 Vlasov-Poisson steps at C1 for each splitting schedule."""
+    from vlapy_b200.core import step
+    g = golden("vp50_c1")
+    cfg = O.landau_config()
+    vp = step.get_vlasov_poisson_step(make_params(cfg, integ), make_stuff(cfg, RULES, device_driver))
+    e = torch.from_numpy(cfg["e0"]).to(dev)
+    f = torch.from_numpy(cfg["f0"]).to(dev)
+    for i in range(50):
+        e, f = vp(e=e, f=f, t=cfg["dt"] * i)
+    assert rel_err(f.cpu().numpy(), g["f_" + integ]) < TOL
+    assert np.max(np.abs(e.cpu().numpy() - g["e_" + integ])) < 5e-14
+
+
+def run_inner_loops(cfg, params, steps_in_loop, n_loops):
+    from vlapy_b200 import outer_loop
+    stuff = make_stuff(cfg, RULES)
+    sim, inner = outer_loop.get_sim_config_and_inner_loop_step(params, stuff, steps_in_loop, RULES)
+    outs = []
+    for li in range(n_loops):
+        t = cfg["dt"] * np.arange(li * steps_in_loop, (li + 1) * steps_in_loop)
+        drv = np.stack([cfg["driver_function"](ti) for ti in t])
+        sim = inner(time_array=t, driver_array=drv, temp_storage=sim)
+        outs.append({"fields": {k: v.copy() for k, v in sim["fields"].items()},
+                     "series": {k: np.array(v).copy() for k, v in sim["series"].items()},
+                     "stored_f": sim["stored_f"].copy(), "f": sim["f"].copy(), "e": sim["e"].copy(),
+                     "time": sim["time_batch"].copy()})
+    return outs
+
+
+def test_landau_damping_integrated(dev):
+    """tests/test_landau_damping.py of the reference re-expressed on the b200 backend: 800 steps
+    (2 inner loops of 400, vlapy/manager.py:61-83), damping rate of E_k1 vs the dispersion root."""
+    g = golden("landau_c1")
+    cfg = O.landau_config()
+    steps, loops = O.steps_in_loop_like_manager(32, 512, 500)
+    assert (steps, loops) == (400, 2)
+    for integ in ("leapfrog", "pefrl", "h-sixth"):
+        outs = run_inner_loops(cfg, make_params(cfg, integ), steps, loops)
+        e_hist = np.concatenate([o["fields"]["e"] for o in outs])
+        tax = np.concatenate([o["time"] for o in outs])
+        rate = O.damping_rate(e_hist, tax)
+        assert abs(rate - float(g["nu_ld"])) < 1.5e-4                       # the reference's own bar
+        assert abs(rate - float(g["rate_%s_exponential" % integ])) < 1e-7   # and its own number
+        assert np.max(np.abs(outs[-1]["e"] - g["e_final_" + integ])) < 1e-13
+        assert abs(outs[-1]["series"]["mean_n"][-1] - 1.0) < 1e-13
+        if integ == "leapfrog":
+            o = outs[0]
+            for k in ("e", "driver", "n", "j", "T", "q", "fv4", "vN"):
+                assert np.max(np.abs(o["fields"][k][:12] - g["fields_" + k])) < 1e-12 * max(1.0, np.abs(g["fields_" + k]).max())
+            for k in O.SERIES_KEYS + ("mean_cum_de2",):
+                np.testing.assert_allclose(o["series"][k][:12], g["series_" + k], rtol=1e-9, atol=1e-20)
+            assert o["stored_f"].dtype == np.complex64
+            assert rel_err(o["stored_f"][:12], g["stored_f"]) < 1e-6          # complex64 storage
+            assert rel_err(outs[-1]["f"], g["f_final_leapfrog"]) < TOL
+            assert np.max(np.abs(e_hist - g["e_hist_leapfrog"])) < 1e-13
+
+
+def test_landau_damping_cd2(dev):
+    g = golden("landau_c1")
+    cfg = O.landau_config()
+    outs = run_inner_loops(cfg, make_params(cfg, "leapfrog", edfdv="cd2"), 400, 2)
+    e_hist = np.concatenate([o["fields"]["e"] for o in outs])
+    tax = np.concatenate([o["time"] for o in outs])
+    rate = O.damping_rate(e_hist, tax)
+    assert abs(rate - float(g["nu_ld"])) < 1.5e-4
+    assert abs(rate - float(g["rate_leapfrog_cd2"])) < 1e-7
+
+
+@pytest.mark.parametrize("op", ["lb", "dg"])
+def test_nlepw_c2_40_steps_vs_reference(dev, op):
+    """C2 (256 x 2048, run_nlepw.py, k0 = 0.35): 40 collisional leapfrog steps."""
+    g = golden("nlepw_c2")
+    cfg = O.nlepw_config()
+    outs = run_inner_loops(cfg, make_params(cfg, "leapfrog", op), 40, 1)
+    f, e = outs[0]["f"], outs[0]["e"]
+    assert rel_err(e, g["e_" + op]) < 1e-11
+    assert rel_err(f[::8, ::16], g["f_sub_" + op]) < TOL
+    assert abs(f.sum() / float(g["f_sum_" + op]) - 1) < 1e-13
+    assert abs(f[100, 1300] / float(g["f_100_1300_" + op]) - 1) < 1e-12
+
+
+def test_small_collisional_run_through_inner_loop(dev):
+    """16 x 128 collisional run through two inner loops of the reference (everything the storage
+    layer receives: fields, series, stored modes, final state)."""
+    g = golden("nlepw_c2")
+    cfg = O.nlepw_config(nx=16, nv=128, k0=0.35, log_nu=-2)
+    assert abs(cfg["nu"] / float(g["small_nu"]) - 1) < 1e-14
+    outs = run_inner_loops(cfg, make_params(cfg, "leapfrog", "lb"), 24, 2)
+    for li, o in enumerate(outs):
+        for k in ("e", "driver", "n", "j", "T", "q", "fv4", "vN"):
+            ref = g["small_fields_%s_%d" % (k, li)]
+            assert np.max(np.abs(o["fields"][k] - ref)) < 1e-12 * max(1.0, np.abs(ref).max())
+        for k in O.SERIES_KEYS + ("mean_cum_de2", "mean_t_plus_e2_minus_cum_de2", "mean_t_plus_e2_plus_cum_de2"):
+            np.testing.assert_allclose(o["series"][k], g["small_series_%s_%d" % (k, li)], rtol=1e-9, atol=1e-18)
+        assert rel_err(o["stored_f"], g["small_stored_f_%d" % li]) < 1e-6
+        assert rel_err(o["f"], g["small_f_%d" % li]) < TOL
+        assert rel_err(o["e"], g["small_e_%d" % li]) < 1e-11
+
+
+def test_smoke_entry(dev):
+    import __graft_entry__ as ge
+    assert ge.smoke()

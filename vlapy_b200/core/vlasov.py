@@ -1,0 +1,83 @@
+"""Mirror of vlapy/core/vlasov.py for the b200 backend: x- and v-advection operator factories.
+
+Same factory names, closure signatures and string dispatch as the reference
+(vlapy/core/vlasov.py:83-140, 143-165, 213-260).  Closures are functional (a new array is
+returned, the argument is never modified) and accept numpy arrays or CUDA tensors, returning the
+same kind.
+"""
+import numpy as np
+
+from .. import ops
+from .._util import back, const, to_dev
+
+
+def _check_wavenumbers(k, what):
+    """The kernels evaluate the phase for bins 0..N/2 and use exp(-i k[N-m] c) = conj(exp(-i k[m] c)),
+    which holds for any np.fft.fftfreq-style grid (k[N-m] == -k[m], as the reference builds it in
+    vlapy/initializers.py:67,85)."""
+    k = np.asarray(k, dtype=np.float64)
+    n = k.shape[-1]
+    if n > 2 and not np.array_equal(k[..., 1:(n + 1) // 2], -k[..., :n // 2:-1]):
+        raise NotImplementedError(
+            what + ": wavenumber grids that are not antisymmetric (np.fft.fftfreq layout) "
+            "have not yet been implemented on the b200 backend")
+    return k
+
+
+def get_vdfdx_exponential(kx, v):
+    """vlapy/core/vlasov.py:83-110 -- v df/dx exponential integrator.
+
+    kx may be (nx,) or (batch, nx) for ensembles of simulations with their own box length."""
+    kx_d = const(_check_wavenumbers(kx, "v df/dx"))
+    v_d = const(v)
+
+    def step_vdfdx_exponential(f, dt):
+        f_d, host = to_dev(f)
+        return back(ops.vdfdx_exp(f_d.contiguous(), kx_d, v_d, dt), host)
+
+    return step_vdfdx_exponential
+
+
+def get_edfdv_exponential(kv):
+    """vlapy/core/vlasov.py:113-140 -- e df/dv exponential integrator."""
+    kv_d = const(_check_wavenumbers(kv, "e df/dv"))
+
+    def step_edfdv_exponential(f, e, dt):
+        f_d, host = to_dev(f)
+        e_d, _ = to_dev(e)
+        return back(ops.edfdv_exp(f_d.contiguous(), e_d.contiguous(), kv_d, dt), host)
+
+    return step_edfdv_exponential
+
+
+def get_edfdv_center_differenced(dv):
+    """vlapy/core/vlasov.py:143-165 -- f - e * gradient_v(f) * dt, 2nd-order edges."""
+
+    def step_edfdv_center_difference(f, e, dt):
+        f_d, host = to_dev(f)
+        e_d, _ = to_dev(e)
+        return back(ops.edfdv_cd2(f_d.contiguous(), e_d.contiguous(), dt, dv), host)
+
+    return step_edfdv_center_difference
+
+
+def get_vdfdx(stuff_for_time_loop, vdfdx_implementation="exponential"):
+    """vlapy/core/vlasov.py:213-235."""
+    if vdfdx_implementation == "exponential":
+        vdfdx = get_vdfdx_exponential(kx=stuff_for_time_loop["kx"], v=stuff_for_time_loop["v"])
+    else:
+        raise NotImplementedError(
+            "v df/dx: <" + vdfdx_implementation + "> has not yet been implemented on the b200 backend")
+    return vdfdx
+
+
+def get_edfdv(stuff_for_time_loop, edfdv_implementation="exponential"):
+    """vlapy/core/vlasov.py:238-260."""
+    if edfdv_implementation == "exponential":
+        edfdv = get_edfdv_exponential(kv=stuff_for_time_loop["kv"])
+    elif edfdv_implementation == "cd2":
+        edfdv = get_edfdv_center_differenced(dv=stuff_for_time_loop["dv"])
+    else:
+        raise NotImplementedError(
+            "e df/dv: <" + edfdv_implementation + "> has not yet been implemented on the b200 backend")
+    return edfdv

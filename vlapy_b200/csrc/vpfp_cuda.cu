@@ -1,0 +1,366 @@
+// vpfp_cuda.cu -- sm_100a kernels, launchers and the C ABI of libvpfp_b200.so (include/vpfp_b200.h).
+//
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -shared -Xcompiler -fPIC
+// There is no CPU path in this file: every entry point enqueues CUDA kernels on the caller's
+// stream and returns; failures are reported through the return code + vpfp_last_error().
+#include <cuda_runtime.h>
+
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/vpfp_b200.h"
+#include "advect.h"
+#include "rowops.h"
+
+// ------------------------------------------------------------------------------------------
+// error plumbing
+// ------------------------------------------------------------------------------------------
+static thread_local std::string g_err;
+static int fail(int code, const std::string& msg) {
+  g_err = msg;
+  return code;
+}
+#define CUDA_TRY(expr)                                                                          \
+  do {                                                                                          \
+    cudaError_t _e = (expr);                                                                    \
+    if (_e != cudaSuccess)                                                                      \
+      return fail(VPFP_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e));           \
+  } while (0)
+
+static bool is_pow2(long n) { return n > 0 && (n & (n - 1)) == 0; }
+
+// ------------------------------------------------------------------------------------------
+// generic phase-program driver: phases separated by CTA barriers (see vpfp_common.h)
+// ------------------------------------------------------------------------------------------
+template <class Prog>
+__global__ void __launch_bounds__(1024) prog_kernel(const Prog prog, const int nph) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  for (int ph = 0; ph < nph; ++ph) {
+    prog.phase(ph, (long)blockIdx.x, (int)threadIdx.x, (int)blockDim.x, smem);
+    __syncthreads();
+  }
+}
+
+template <class Prog>
+static int launch_prog(const Prog& prog, long nblocks, int threads, long smem, int nph,
+                       cudaStream_t st) {
+  if (nblocks <= 0) return VPFP_OK;
+  if (nblocks > 2147483647L) return fail(VPFP_ERR_UNSUPPORTED, "grid too large");
+  if (smem > 227 * 1024) return fail(VPFP_ERR_UNSUPPORTED, "tile does not fit shared memory");
+  static std::map<int, long> configured;  // per device: largest smem opted in for this Prog
+  if (smem > 48 * 1024) {
+    int dev = 0;
+    CUDA_TRY(cudaGetDevice(&dev));
+    static std::mutex mu;
+    std::lock_guard<std::mutex> lk(mu);
+    if (configured[dev] < smem) {
+      CUDA_TRY(cudaFuncSetAttribute(prog_kernel<Prog>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    227 * 1024));
+      configured[dev] = 227 * 1024;
+    }
+  }
+  prog_kernel<Prog><<<(unsigned)nblocks, threads, smem, st>>>(prog, nph);
+  CUDA_TRY(cudaGetLastError());
+  return VPFP_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// per-device caches: twiddle tables exp(-2 pi i m / N) and a grow-only scratch buffer
+// ------------------------------------------------------------------------------------------
+struct DeviceCache {
+  std::map<int, cplx*> tw;
+  void* scratch[4] = {nullptr, nullptr, nullptr, nullptr};   // grow-only, one per purpose
+  size_t scratch_bytes[4] = {0, 0, 0, 0};
+};
+enum { SCR_XMODES = 0, SCR_PHANTOM = 1 };
+static std::map<int, DeviceCache> g_cache;
+static std::mutex g_cache_mu;
+
+static int get_twiddles(int N, const cplx** out) {
+  int dev = 0;
+  CUDA_TRY(cudaGetDevice(&dev));
+  std::lock_guard<std::mutex> lk(g_cache_mu);
+  DeviceCache& c = g_cache[dev];
+  auto it = c.tw.find(N);
+  if (it != c.tw.end()) {
+    *out = it->second;
+    return VPFP_OK;
+  }
+  std::vector<cplx> h((size_t)N);
+  const long double two_pi = 6.283185307179586476925286766559005768L;
+  for (int m = 0; m < N; ++m) {
+    long double a = two_pi * (long double)m / (long double)N;
+    h[m].x = (double)cosl(a);
+    h[m].y = (double)(-sinl(a));
+  }
+  // exact values on the axes and diagonals
+  h[0].x = 1.0; h[0].y = 0.0;
+  if (N % 4 == 0) { h[N / 4].x = 0.0; h[N / 4].y = -1.0; h[3 * N / 4].x = 0.0; h[3 * N / 4].y = 1.0; }
+  if (N % 2 == 0) { h[N / 2].x = -1.0; h[N / 2].y = 0.0; }
+  cplx* d = nullptr;
+  CUDA_TRY(cudaMalloc(&d, sizeof(cplx) * (size_t)N));
+  CUDA_TRY(cudaMemcpy(d, h.data(), sizeof(cplx) * (size_t)N, cudaMemcpyHostToDevice));
+  c.tw[N] = d;
+  *out = d;
+  return VPFP_OK;
+}
+
+static int get_scratch(int slot, size_t bytes, void** out) {
+  int dev = 0;
+  CUDA_TRY(cudaGetDevice(&dev));
+  std::lock_guard<std::mutex> lk(g_cache_mu);
+  DeviceCache& c = g_cache[dev];
+  if (c.scratch_bytes[slot] < bytes) {
+    if (c.scratch[slot]) CUDA_TRY(cudaFree(c.scratch[slot]));   // implicit device sync: safe
+    c.scratch[slot] = nullptr;
+    c.scratch_bytes[slot] = 0;
+    CUDA_TRY(cudaMalloc(&c.scratch[slot], bytes));
+    c.scratch_bytes[slot] = bytes;
+  }
+  *out = c.scratch[slot];
+  return VPFP_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// advection / Poisson launcher
+// ------------------------------------------------------------------------------------------
+static int run_advect(AdvectProg a, cudaStream_t st) {
+  const AdvectPlan pl = make_advect_plan(a.mode, a.N);
+  int rc = get_twiddles(a.N, &a.tw);
+  if (rc) return rc;
+  if (pl.N1 == 1) {
+    advect_set_pass(a, pl, 0);
+    return launch_prog(a, a.ntiles(), pl.threads[0], a.smem_bytes(), a.nphases(), st);
+  }
+  if (a.mode == ADV_ROWS && (a.nrows & 1)) {
+    void* ph = nullptr;
+    rc = get_scratch(SCR_PHANTOM, sizeof(double) * (size_t)a.N, &ph);
+    if (rc) return rc;
+    a.phantom = (double*)ph;
+  }
+  for (int pass = 1; pass <= 3; ++pass) {
+    advect_set_pass(a, pl, pass);
+    rc = launch_prog(a, a.ntiles(), pl.threads[pass], a.smem_bytes(), a.nphases(), st);
+    if (rc) return rc;
+  }
+  return VPFP_OK;
+}
+
+// Direct O(N^2) DFT Poisson solve for lengths that are not powers of two (the reference's own
+// field-solver test uses nx = 96).  One CTA per density row.
+struct PoissonDftProg {
+  const double* n;
+  const double* ook;
+  const double* driver;
+  double* e;
+  int N;
+  __host__ __device__ long smem_bytes() const { return (long)3 * N * sizeof(double); }
+  __device__ void phase(int ph, long blk, int tid, int nthr, unsigned char* smem) const {
+    double* rho = reinterpret_cast<double*>(smem);
+    double* re = rho + N;
+    double* im = re + N;
+    const double w = -6.283185307179586476925286766559 / (double)N;
+    if (ph == 0) {
+      for (int x = tid; x < N; x += nthr) rho[x] = 1.0 - n[blk * N + x];
+    } else if (ph == 1) {
+      for (int k = tid; k < N; k += nthr) {
+        double sr = 0.0, si = 0.0;
+        for (int x = 0; x < N; ++x) {
+          long kx = ((long)k * x) % N;
+          double s, c;
+          sincos(w * (double)kx, &s, &c);
+          sr += rho[x] * c;
+          si += rho[x] * s;
+        }
+        // multiply by i * one_over_kx[k]
+        double o = ook[blk * N + k];
+        re[k] = -o * si;
+        im[k] = o * sr;
+      }
+    } else {
+      for (int x = tid; x < N; x += nthr) {
+        double acc = 0.0;
+        for (int k = 0; k < N; ++k) {
+          long kx = ((long)k * x) % N;
+          double s, c;
+          sincos(-w * (double)kx, &s, &c);
+          acc += re[k] * c - im[k] * s;
+        }
+        double val = acc / (double)N;
+        if (driver) val += driver[blk * N + x];
+        e[blk * N + x] = val;
+      }
+    }
+  }
+};
+
+// ------------------------------------------------------------------------------------------
+// C ABI
+// ------------------------------------------------------------------------------------------
+extern "C" {
+
+int vpfp_abi_version(void) { return VPFP_ABI_VERSION; }
+const char* vpfp_last_error(void) { return g_err.c_str(); }
+
+int vpfp_shutdown(void) {
+  std::lock_guard<std::mutex> lk(g_cache_mu);
+  for (auto& kv : g_cache) {
+    cudaSetDevice(kv.first);
+    for (auto& t : kv.second.tw) cudaFree(t.second);
+    for (int i = 0; i < 4; ++i)
+      if (kv.second.scratch[i]) cudaFree(kv.second.scratch[i]);
+  }
+  g_cache.clear();
+  return VPFP_OK;
+}
+
+int vpfp_edfdv_exp(const double* f_in, long ld_in, double* f_out, long ld_out, const double* e,
+                   const double* kv, double dt, int rows, int nv, int flags, void* stream) {
+  if (!f_in || !f_out || !e || !kv || rows <= 0 || nv <= 0 || ld_in < nv || ld_out < nv)
+    return fail(VPFP_ERR_ARG, "vpfp_edfdv_exp: bad argument");
+  if (!is_pow2(nv) || nv < 4 || nv > (1 << 24))
+    return fail(VPFP_ERR_UNSUPPORTED, "e df/dv: <exponential> needs nv = 2^k >= 4 on the b200 backend");
+  (void)flags;
+  AdvectProg a;
+  memset(&a, 0, sizeof(a));
+  a.mode = ADV_ROWS; a.op = OP_PHASE; a.N = nv;
+  a.nsim = 1; a.nrows = rows; a.nseq = (rows + 1) / 2;
+  a.fin = f_in; a.ld_in = ld_in; a.fout = f_out; a.ld_out = ld_out;
+  a.kvec = kv; a.cvec = e; a.addv = nullptr; a.dt = dt;
+  return run_advect(a, (cudaStream_t)stream);
+}
+
+int vpfp_vdfdx_exp(const double* f_in, long ld_in, double* f_out, long ld_out, const double* kx,
+                   const double* v, double dt, int batch, int nx, int ncols, int flags,
+                   void* stream) {
+  if (!f_in || !f_out || !kx || !v || batch <= 0 || nx <= 0 || ncols <= 0 || ld_in < ncols ||
+      ld_out < ncols)
+    return fail(VPFP_ERR_ARG, "vpfp_vdfdx_exp: bad argument");
+  if (!is_pow2(nx) || nx < 2 || nx > (1 << 24))
+    return fail(VPFP_ERR_UNSUPPORTED, "v df/dx: <exponential> needs nx = 2^k >= 2 on the b200 backend");
+  if ((ncols & 1) || (ld_in & 1) || (ld_out & 1) || ((uintptr_t)f_in & 15) || ((uintptr_t)f_out & 15))
+    return fail(VPFP_ERR_UNSUPPORTED, "v df/dx: column count and row pitch must be even, f 16-byte aligned");
+  (void)flags;
+  AdvectProg a;
+  memset(&a, 0, sizeof(a));
+  a.mode = ADV_COLS; a.op = OP_PHASE; a.N = nx;
+  a.nsim = batch; a.nrows = nx; a.nseq = ncols / 2;
+  a.fin = f_in; a.ld_in = ld_in; a.fout = f_out; a.ld_out = ld_out;
+  a.kvec = kx; a.cvec = v; a.addv = nullptr; a.dt = dt;
+  return run_advect(a, (cudaStream_t)stream);
+}
+
+int vpfp_edfdv_cd2(const double* f_in, long ld_in, double* f_out, long ld_out, const double* e,
+                   double dt, double dv, int rows, int nv, void* stream) {
+  if (!f_in || !f_out || !e || rows <= 0 || nv < 3) return fail(VPFP_ERR_ARG, "vpfp_edfdv_cd2: bad argument");
+  Cd2Prog p;
+  p.fin = f_in; p.ld_in = ld_in; p.fout = f_out; p.ld_out = ld_out; p.e = e;
+  p.dt = dt; p.dv = dv; p.rows = rows; p.nv = nv;
+  const int threads = 256;
+  p.cblocks = (nv + threads * 4 - 1) / (threads * 4);
+  return launch_prog(p, (long)rows * p.cblocks, threads, 0, 1, (cudaStream_t)stream);
+}
+
+int vpfp_moments(const double* f, long ld, const double* v, double dv, double* out, long out_ld,
+                 int nmom, int rows, int ncols, int edge_flags, void* stream) {
+  if (!f || !v || !out || rows <= 0 || ncols < 2 || nmom < 1 || nmom > 8)
+    return fail(VPFP_ERR_ARG, "vpfp_moments: bad argument");
+  MomentsProg p;
+  p.f = f; p.ld = ld; p.v = v; p.dv = dv; p.out = out; p.out_ld = out_ld;
+  p.nmom = nmom; p.rows = rows; p.ncols = ncols; p.edge_flags = edge_flags;
+  int threads = 256;
+  while (threads > 32 && threads * 2 > ncols) threads >>= 1;
+  return launch_prog(p, rows, threads, p.smem_bytes(threads), p.nphases(threads), (cudaStream_t)stream);
+}
+
+int vpfp_poisson(const double* n, const double* one_over_kx, const double* driver, double* e,
+                 int batch, int nx, void* stream) {
+  if (!n || !one_over_kx || !e || batch <= 0 || nx < 2) return fail(VPFP_ERR_ARG, "vpfp_poisson: bad argument");
+  if (!is_pow2(nx)) {
+    if (nx > 4096) return fail(VPFP_ERR_UNSUPPORTED, "spectral Poisson: non power-of-two nx > 4096");
+    PoissonDftProg p;
+    p.n = n; p.ook = one_over_kx; p.driver = driver; p.e = e; p.N = nx;
+    return launch_prog(p, batch, 256, p.smem_bytes(), 3, (cudaStream_t)stream);
+  }
+  AdvectProg a;
+  memset(&a, 0, sizeof(a));
+  a.mode = ADV_ROWS; a.op = OP_POISSON; a.N = nx;
+  a.nsim = 1; a.nrows = batch; a.nseq = (batch + 1) / 2;
+  a.fin = n; a.ld_in = nx; a.fout = e; a.ld_out = nx;
+  a.kvec = one_over_kx; a.cvec = nullptr; a.addv = driver; a.dt = 0.0;
+  return run_advect(a, (cudaStream_t)stream);
+}
+
+int vpfp_fp_step(const double* f_in, long ld_in, double* f_out, long ld_out, const double* v,
+                 double nu, double dt, double dv, int op, double* moments_out, long mom_ld,
+                 int rows, int nv, void* stream) {
+  if (!f_in || !f_out || !v || rows <= 0 || nv <= 0) return fail(VPFP_ERR_ARG, "vpfp_fp_step: bad argument");
+  if (op != VPFP_FP_LB && op != VPFP_FP_DG)
+    return fail(VPFP_ERR_UNSUPPORTED, "Collision Operator: unknown operator id");
+  if (nv < 8 || nv > 16384)
+    return fail(VPFP_ERR_UNSUPPORTED, "Fokker-Planck step needs 8 <= nv <= 16384 on the b200 backend");
+  FpProg p;
+  p.fin = f_in; p.ld_in = ld_in; p.fout = f_out; p.ld_out = ld_out; p.v = v;
+  p.nu = nu; p.dt = dt; p.dv = dv; p.op = op; p.mom_out = moments_out; p.mom_ld = mom_ld;
+  p.rows = rows; p.nv = nv;
+  int m = nv / 256;
+  if (m < 4) m = 4;
+  if (m > 16) m = 16;
+  p.m = m;
+  p.P = nv / m;
+  int threads = ((p.P + 31) / 32) * 32;
+  if (threads > 1024) threads = 1024;
+  return launch_prog(p, rows, threads, p.smem_bytes(threads), p.nphases(threads), (cudaStream_t)stream);
+}
+
+int vpfp_xmodes(const double* f, long ld, double* out, int nmodes, int batch, int nx, int ncols,
+                void* stream) {
+  if (!f || !out || nmodes < 1 || batch <= 0 || nx <= 0 || ncols <= 0)
+    return fail(VPFP_ERR_ARG, "vpfp_xmodes: bad argument");
+  XmodesProg p;
+  p.f = f; p.ld = ld; p.nmodes = nmodes; p.batch = batch; p.nx = nx; p.ncols = ncols;
+  const int threads = 128;
+  p.cblocks = (ncols + threads - 1) / threads;
+  int xch = nx / 64;
+  if (xch < 1) xch = 1;
+  if (xch > 64) xch = 64;
+  p.xchunks = xch;
+  void* scratch = nullptr;
+  size_t bytes = (size_t)batch * xch * nmodes * ncols * 2 * sizeof(double);
+  int rc = get_scratch(SCR_XMODES, bytes, &scratch);
+  if (rc) return rc;
+  p.partial = (double*)scratch;
+  rc = launch_prog(p, (long)batch * xch * p.cblocks, threads, 0, 1, (cudaStream_t)stream);
+  if (rc) return rc;
+  XmodesReduceProg r;
+  r.partial = p.partial; r.out = out; r.nmodes = nmodes; r.batch = batch; r.ncols = ncols; r.xchunks = xch;
+  long total = (long)batch * nmodes * ncols * 2;
+  return launch_prog(r, (total + 255) / 256, 256, 0, 1, (cudaStream_t)stream);
+}
+
+int vpfp_driver(const double* x, double t, const double* pulses, int npulse, double* out, int nx,
+                void* stream) {
+  if (!x || !out || nx <= 0 || npulse < 0 || (npulse > 0 && !pulses))
+    return fail(VPFP_ERR_ARG, "vpfp_driver: bad argument");
+  if (npulse > DRIVER_MAX_PULSES) return fail(VPFP_ERR_UNSUPPORTED, "vpfp_driver: too many pulses");
+  DriverProg p;
+  p.x = x; p.out = out; p.t = t; p.nx = nx; p.npulse = npulse;
+  for (int i = 0; i < npulse * 7; ++i) p.pulses[i] = pulses[i];
+  return launch_prog(p, (nx + 255) / 256, 256, 0, 1, (cudaStream_t)stream);
+}
+
+int vpfp_series(const double* moments, long mom_ld, const double* e, const double* de, double* out,
+                int nx, void* stream) {
+  if (!moments || !e || !out || nx <= 0) return fail(VPFP_ERR_ARG, "vpfp_series: bad argument");
+  SeriesProg p;
+  p.mom = moments; p.mom_ld = mom_ld; p.e = e; p.de = de; p.out = out; p.nx = nx;
+  int threads = 256;
+  while (threads > 32 && threads > nx) threads >>= 1;
+  return launch_prog(p, 1, threads, p.smem_bytes(threads), p.nphases(threads), (cudaStream_t)stream);
+}
+
+}  // extern "C"

@@ -1,0 +1,188 @@
+"""Device-tensor level operators: one function per C-ABI entry point.
+
+Inputs are CUDA fp64 torch tensors (torch is used for device memory and streams only); every call
+enqueues hand-written sm_100a kernels on torch's current stream and returns without synchronising.
+"""
+import ctypes
+
+import numpy as np
+import torch
+
+from . import _lib
+
+FP_OPS = {"lb": 0, "dg": 1}
+PHASE_EXACT, PHASE_TABLE = 0, 1
+
+# number of kernels of this library launched since the last reset (bench.py's gpu_launches claim)
+launch_count = 0
+
+
+def _count(n):
+    global launch_count
+    launch_count += n
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _chk_f(f, name="f"):
+    if not (isinstance(f, torch.Tensor) and f.is_cuda and f.dtype == torch.float64):
+        raise TypeError("%s must be a CUDA float64 tensor" % name)
+    if f.dim() < 2 or f.stride(-1) != 1:
+        raise ValueError("%s must have a contiguous last (v) axis" % name)
+    rows = int(np.prod(f.shape[:-1]))
+    ld = f.stride(-2)
+    # leading dims must be collapsible to a uniform row pitch
+    exp = ld
+    for d in range(f.dim() - 2, -1, -1):
+        if f.shape[d] != 1 and f.stride(d) != exp:
+            raise ValueError("%s must have a uniform row pitch" % name)
+        exp *= f.shape[d]
+    return rows, ld
+
+
+def _vec(x, n, name):
+    if not (isinstance(x, torch.Tensor) and x.is_cuda and x.dtype == torch.float64 and x.is_contiguous()):
+        raise TypeError("%s must be a contiguous CUDA float64 tensor" % name)
+    if x.numel() != n:
+        raise ValueError("%s has %d elements, expected %d" % (name, x.numel(), n))
+    return x
+
+
+def _is_pow2(n):
+    return n > 0 and (n & (n - 1)) == 0
+
+
+def adv_launches(mode, n):
+    """kernels per advection call: one when the sequence fits a CTA, else the three passes"""
+    return 1 if n <= (2048 if mode == "cols" else 8192) else 3
+
+
+def edfdv_exp(f, e, kv, dt, out=None, flags=PHASE_EXACT):
+    """vlapy/core/vlasov.py:123-138 on device. f: (..., nx, nv); e: (..., nx); kv: (nv)."""
+    rows, ld = _chk_f(f)
+    nv = f.shape[-1]
+    if out is None:
+        out = torch.empty(f.shape, dtype=f.dtype, device=f.device)
+    _, ldo = _chk_f(out, "out")
+    _vec(e, rows, "e"); _vec(kv, nv, "kv")
+    _lib.check(_lib.lib().vpfp_edfdv_exp(f.data_ptr(), ld, out.data_ptr(), ldo, e.data_ptr(), kv.data_ptr(),
+                                         float(dt), rows, nv, flags, _stream()))
+    _count(adv_launches("rows", nv))
+    return out
+
+
+def vdfdx_exp(f, kx, v, dt, out=None, flags=PHASE_EXACT):
+    """vlapy/core/vlasov.py:94-108 on device. f: (batch, nx, ncols) or (nx, ncols); kx: (batch, nx)."""
+    _, ld = _chk_f(f)
+    nx, ncols = f.shape[-2], f.shape[-1]
+    batch = int(np.prod(f.shape[:-2])) if f.dim() > 2 else 1
+    if out is None:
+        out = torch.empty(f.shape, dtype=f.dtype, device=f.device)
+    _, ldo = _chk_f(out, "out")
+    _vec(kx, batch * nx, "kx"); _vec(v, ncols, "v")
+    _lib.check(_lib.lib().vpfp_vdfdx_exp(f.data_ptr(), ld, out.data_ptr(), ldo, kx.data_ptr(), v.data_ptr(),
+                                         float(dt), batch, nx, ncols, flags, _stream()))
+    _count(adv_launches("cols", nx))
+    return out
+
+
+def edfdv_cd2(f, e, dt, dv, out=None):
+    """vlapy/core/vlasov.py:153-163 on device."""
+    rows, ld = _chk_f(f)
+    nv = f.shape[-1]
+    if out is None:
+        out = torch.empty(f.shape, dtype=f.dtype, device=f.device)
+    _, ldo = _chk_f(out, "out")
+    _vec(e, rows, "e")
+    _lib.check(_lib.lib().vpfp_edfdv_cd2(f.data_ptr(), ld, out.data_ptr(), ldo, e.data_ptr(), float(dt),
+                                         float(dv), rows, nv, _stream()))
+    _count(1)
+    return out
+
+
+def moments(f, v, dv, nmom=8, out=None, edge_flags=3):
+    """Rows of v-moments (nmom, rows): n, j, T, q, fv4, vN, int f^2, int f ln f."""
+    rows, ld = _chk_f(f)
+    ncols = f.shape[-1]
+    _vec(v, ncols, "v")
+    if out is None:
+        out = torch.empty((nmom, rows), dtype=f.dtype, device=f.device)
+    _lib.check(_lib.lib().vpfp_moments(f.data_ptr(), ld, v.data_ptr(), float(dv), out.data_ptr(),
+                                       out.stride(0), nmom, rows, ncols, edge_flags, _stream()))
+    _count(1)
+    return out
+
+
+def poisson(n, one_over_kx, driver=None, out=None):
+    """vlapy/core/field.py:39-88 on device: e = driver + Re ifft(i one_over_kx fft(1 - n))."""
+    nx = n.shape[-1]
+    batch = n.numel() // nx
+    _vec(n, batch * nx, "n"); _vec(one_over_kx, batch * nx, "one_over_kx")
+    if driver is not None:
+        _vec(driver, batch * nx, "driver")
+    if out is None:
+        out = torch.empty_like(n)
+    _lib.check(_lib.lib().vpfp_poisson(n.data_ptr(), one_over_kx.data_ptr(),
+                                       driver.data_ptr() if driver is not None else None,
+                                       out.data_ptr(), batch, nx, _stream()))
+    _count(adv_launches("rows", nx) if _is_pow2(nx) else 1)
+    return out
+
+
+def fp_step(f, v, nu, dt, dv, op="lb", out=None, moments_out=None):
+    """Implicit LB / Dougherty step (vlapy/core/collisions.py via step.py:102-108) on device."""
+    rows, ld = _chk_f(f)
+    nv = f.shape[-1]
+    if op not in FP_OPS:
+        raise NotImplementedError("Collision Operator: <" + str(op) + "> has not yet been implemented on the b200 backend")
+    _vec(v, nv, "v")
+    if out is None:
+        out = torch.empty(f.shape, dtype=f.dtype, device=f.device)
+    _, ldo = _chk_f(out, "out")
+    mp, mld = (None, 0) if moments_out is None else (moments_out.data_ptr(), moments_out.stride(0))
+    _lib.check(_lib.lib().vpfp_fp_step(f.data_ptr(), ld, out.data_ptr(), ldo, v.data_ptr(), float(nu), float(dt),
+                                       float(dv), FP_OPS[op], mp, mld, rows, nv, _stream()))
+    _count(1)
+    return out
+
+
+def xmodes(f, nmodes=2, out=None):
+    """fft_x(f)[:nmodes] per v as (batch, nmodes, ncols) complex128 (vlapy/core/step.py:130-135)."""
+    _, ld = _chk_f(f)
+    nx, ncols = f.shape[-2], f.shape[-1]
+    batch = int(np.prod(f.shape[:-2])) if f.dim() > 2 else 1
+    if out is None:
+        out = torch.empty((batch, nmodes, ncols, 2), dtype=f.dtype, device=f.device)
+    _lib.check(_lib.lib().vpfp_xmodes(f.data_ptr(), ld, out.data_ptr(), nmodes, batch, nx, ncols, _stream()))
+    _count(2)
+    return torch.view_as_complex(out)
+
+
+def driver(x, t, pulses, out=None):
+    """vlapy/field_driver.py:24-50 on device. pulses: host float64 array (npulse, 7)."""
+    pulses = np.ascontiguousarray(pulses, dtype=np.float64).reshape(-1, 7)
+    if out is None:
+        out = torch.empty_like(x)
+    _lib.check(_lib.lib().vpfp_driver(x.data_ptr(), float(t), pulses.ctypes.data_as(ctypes.c_void_p),
+                                      pulses.shape[0], out.data_ptr(), x.numel(), _stream()))
+    _count(1)
+    return out
+
+
+def series(mom, e, de, out=None):
+    """vlapy/core/step.py:202-224 on device: 7 x-means of one stored step."""
+    if out is None:
+        out = torch.empty(7, dtype=mom.dtype, device=mom.device)
+    _lib.check(_lib.lib().vpfp_series(mom.data_ptr(), mom.stride(0), e.data_ptr(),
+                                      de.data_ptr() if de is not None else None, out.data_ptr(),
+                                      e.numel(), _stream()))
+    _count(1)
+    return out
+
+
+def pulses_to_array(pulse_dictionary):
+    """{name: {k0, w0, a0, t_L, t_R, t_wL, t_wR, ...}} -> (npulse, 7) float64 in ABI order."""
+    return np.array([[p["k0"], p["w0"], p["a0"], p["t_L"], p["t_R"], p["t_wL"], p["t_wR"]]
+                     for p in pulse_dictionary.values()], dtype=np.float64).reshape(-1, 7)
