@@ -12,7 +12,7 @@ CSRC = os.path.join(os.path.dirname(os.path.dirname(HERE)), "vlapy_b200", "csrc"
 
 
 def build(force=False):
-    deps = [SRC] + [os.path.join(CSRC, n) for n in ("advect.h", "rowops.h", "vpfp_common.h")]
+    deps = [SRC] + [os.path.join(CSRC, n) for n in ("advect.h", "rowops.h", "vpfp_common.h", "butterflies.h")]
     if force or not os.path.exists(SO) or any(os.path.getmtime(d) > os.path.getmtime(SO) for d in deps):
         subprocess.check_call(["g++", "-O2", "-ffp-contract=off", "-std=c++17", "-shared", "-fPIC",
                                "-o", SO, SRC])
@@ -108,3 +108,11 @@ def series(mom, e, de):
     lib().emul_series(_p(mom), c_long(mom.shape[1]), _p(np.ascontiguousarray(e)), _p(np.ascontiguousarray(de)),
                       _p(out), c_int(e.size))
     return out
+
+
+def butterfly(x, radix, direction):
+    """register butterflies of the fast kernels: natural order in/out, direction -1 fwd / +1 inv"""
+    xy = np.ascontiguousarray(np.stack([x.real, x.imag], axis=1).astype(np.float64))
+    rc = lib().emul_butterfly(_p(xy), c_int(radix), c_int(direction))
+    assert rc == 0
+    return xy[:, 0] + 1j * xy[:, 1]

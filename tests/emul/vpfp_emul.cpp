@@ -170,3 +170,16 @@ int emul_series(const double* moments, long mom_ld, const double* e, const doubl
   return 0;
 }
 }
+
+// ---- register butterflies of the fast kernels (vlapy_b200/csrc/butterflies.h)
+#include "../../vlapy_b200/csrc/butterflies.h"
+extern "C" int emul_butterfly(double* xy, int radix, int dir) {
+  cplx x[16];
+  for (int i = 0; i < radix; ++i) { x[i].x = xy[2 * i]; x[i].y = xy[2 * i + 1]; }
+  if (radix == 4) { if (dir < 0) fast::fft4<-1>(x[0], x[1], x[2], x[3]); else fast::fft4<1>(x[0], x[1], x[2], x[3]); }
+  else if (radix == 8) { if (dir < 0) fast::fft8<-1>(x); else fast::fft8<1>(x); }
+  else if (radix == 16) { if (dir < 0) fast::fft16<-1>(x); else fast::fft16<1>(x); }
+  else return 1;
+  for (int i = 0; i < radix; ++i) { xy[2 * i] = x[i].x; xy[2 * i + 1] = x[i].y; }
+  return 0;
+}

@@ -158,3 +158,11 @@ def test_fp_collision_unit_cases_16_steps():
             for _ in range(16):
                 f = E.fp_step(f, v, nu, dt, dv, op)
             assert rel_err(f, g["out_%s_%g" % (op, vshift)]) < TOL
+
+
+@pytest.mark.parametrize("radix", [4, 8, 16])
+def test_register_butterflies(radix):
+    rng = np.random.default_rng(radix)
+    x = rng.standard_normal(radix) + 1j * rng.standard_normal(radix)
+    np.testing.assert_allclose(E.butterfly(x, radix, -1), np.fft.fft(x), rtol=0, atol=1e-14)
+    np.testing.assert_allclose(E.butterfly(x, radix, +1), np.fft.ifft(x) * radix, rtol=0, atol=1e-14)

@@ -115,6 +115,30 @@ def test_vdfdx_sizes_vs_oracle(dev, shape):
     assert rel_err(out, O.vdfdx_exponential(f, 0.25, kx, v)) < TOL
 
 
+@pytest.mark.parametrize("flags", [0, 1, 2])
+@pytest.mark.parametrize("n", [4096, 8192, 16384])
+def test_fast_and_generic_kernels_agree_with_oracle(dev, n, flags):
+    """register-resident kernels with exact phases (0) and geometric tables (1), and the generic
+    phase program (2), on white-noise-dominated input at the sizes the fast path serves."""
+    from vlapy_b200 import ops
+    rng = np.random.default_rng(n + flags)
+    # e df/dv: 5 rows (odd: phantom partner) of length n
+    dv, v, kv = O.velocity_grid(6.4, n)
+    f = rng.standard_normal((5, n))
+    e = 0.3 * rng.standard_normal(5)
+    out = ops.edfdv_exp(torch.from_numpy(f).to(dev), torch.from_numpy(e).to(dev), torch.from_numpy(kv).to(dev),
+                        0.125, flags=flags)
+    assert rel_err(out.cpu().numpy(), O.edfdv_exponential(f, e, 0.125, kv)) < TOL
+    # v df/dx: n rows, 36 columns (ragged tile), two simulations with their own kx
+    vv = np.linspace(-6.4, 6.4, 36)
+    kxs = np.stack([O.spatial_grid(0.0, 2 * np.pi / k0, n)[2] for k0 in (0.3, 0.41)])
+    g = rng.standard_normal((2, n, 36))
+    out = ops.vdfdx_exp(torch.from_numpy(g).to(dev), torch.from_numpy(kxs).to(dev), torch.from_numpy(vv).to(dev),
+                        0.25, flags=flags)
+    for b in range(2):
+        assert rel_err(out[b].cpu().numpy(), O.vdfdx_exponential(g[b], 0.25, kxs[b], vv)) < TOL
+
+
 def test_vdfdx_ensemble_with_per_simulation_kx(dev):
     from vlapy_b200.core import vlasov
     rng = np.random.default_rng(11)
@@ -160,7 +184,9 @@ def test_field_solver_unit_cases(dev):
     for nx in (2, 8, 1024, 8192, 16384, 65536):
         dx, xx, kx, ook = O.spatial_grid(0.0, 17.0, nx)
         n = 1.0 + 0.1 * rng.standard_normal(nx)
-        assert rel_err(field.solve_for_field(n, ook), O.solve_for_field(n, ook)) < TOL
+        ref = O.solve_for_field(n, ook)
+        err = np.max(np.abs(field.solve_for_field(n, ook) - ref))
+        assert err < TOL * max(np.abs(ref).max(), 1e-3), (nx, err)     # nx = 2 has only DC + Nyquist: E = 0
 
 
 def test_collision_unit_cases(dev):
@@ -202,6 +228,19 @@ def test_fp_sizes_vs_oracle(dev, op, nv):
     out = ops.fp_step(torch.from_numpy(f).to(dev), torch.from_numpy(v).to(dev), nu, 0.25, dv, op, moments_out=mom)
     assert rel_err(out.cpu().numpy(), ref) < TOL
     assert rel_err(mom[:6].cpu().numpy(), O.field_moments(ref, v, dv)) < TOL
+
+
+def field_tolerances(cfg, fmax):
+    """Per-field absolute tolerance that follows from 1e-12 relative parity on f (norm max|f|):
+    a v-moment of order p is a linear functional of f with L1 weight int |v|^p dv, and E is the
+    Poisson solve of the p = 0 moment (gain <= 1/k0 per mode, summed over a few modes)."""
+    vmax = float(np.abs(cfg["v"]).max())
+    tol = {}
+    for p, name in enumerate(("n", "j", "T", "q", "fv4", "vN")):
+        tol[name] = 1e-12 * fmax * 2.0 * vmax ** (p + 1) / (p + 1)
+    tol["e"] = 10.0 * tol["n"] / cfg["k0"]
+    tol["driver"] = 1e-15 * max(p_["a0"] * p_["k0"] for p_ in cfg["pulses"].values()) * 10
+    return tol
 
 
 def make_stuff(cfg, rules, with_pulses=True):
@@ -272,10 +311,12 @@ def test_landau_damping_integrated(dev):
         assert abs(outs[-1]["series"]["mean_n"][-1] - 1.0) < 1e-13
         if integ == "leapfrog":
             o = outs[0]
+            tol = field_tolerances(cfg, 0.4)
             for k in ("e", "driver", "n", "j", "T", "q", "fv4", "vN"):
-                assert np.max(np.abs(o["fields"][k][:12] - g["fields_" + k])) < 1e-12 * max(1.0, np.abs(g["fields_" + k]).max())
+                err = np.max(np.abs(o["fields"][k][:12] - g["fields_" + k]))
+                assert err < tol[k], (k, err, tol[k])
             for k in O.SERIES_KEYS + ("mean_cum_de2",):
-                np.testing.assert_allclose(o["series"][k][:12], g["series_" + k], rtol=1e-9, atol=1e-20)
+                np.testing.assert_allclose(o["series"][k][:12], g["series_" + k], rtol=1e-9, atol=1e-14, err_msg=k)
             assert o["stored_f"].dtype == np.complex64
             assert rel_err(o["stored_f"][:12], g["stored_f"]) < 1e-6          # complex64 storage
             assert rel_err(outs[-1]["f"], g["f_final_leapfrog"]) < TOL
@@ -313,12 +354,15 @@ def test_small_collisional_run_through_inner_loop(dev):
     cfg = O.nlepw_config(nx=16, nv=128, k0=0.35, log_nu=-2)
     assert abs(cfg["nu"] / float(g["small_nu"]) - 1) < 1e-14
     outs = run_inner_loops(cfg, make_params(cfg, "leapfrog", "lb"), 24, 2)
+    tol = field_tolerances(cfg, 0.4)
     for li, o in enumerate(outs):
         for k in ("e", "driver", "n", "j", "T", "q", "fv4", "vN"):
             ref = g["small_fields_%s_%d" % (k, li)]
-            assert np.max(np.abs(o["fields"][k] - ref)) < 1e-12 * max(1.0, np.abs(ref).max())
+            err = np.max(np.abs(o["fields"][k] - ref))
+            assert err < tol[k], (k, li, err, tol[k])
         for k in O.SERIES_KEYS + ("mean_cum_de2", "mean_t_plus_e2_minus_cum_de2", "mean_t_plus_e2_plus_cum_de2"):
-            np.testing.assert_allclose(o["series"][k], g["small_series_%s_%d" % (k, li)], rtol=1e-9, atol=1e-18)
+            np.testing.assert_allclose(o["series"][k], g["small_series_%s_%d" % (k, li)], rtol=1e-9, atol=1e-13,
+                                       err_msg=k)
         assert rel_err(o["stored_f"], g["small_stored_f_%d" % li]) < 1e-6
         assert rel_err(o["f"], g["small_f_%d" % li]) < TOL
         assert rel_err(o["e"], g["small_e_%d" % li]) < 1e-11

@@ -5,6 +5,8 @@ Same factory names, closure signatures and string dispatch as the reference
 returned, the argument is never modified) and accept numpy arrays or CUDA tensors, returning the
 same kind.
 """
+import os
+
 import numpy as np
 
 from .. import ops
@@ -24,16 +26,32 @@ def _check_wavenumbers(k, what):
     return k
 
 
+def _phase_flags(k):
+    """Geometric phase tables need a uniform grid k[m] = m k[1] (np.fft.fftfreq); anything else, or
+    VLAPY_B200_PHASE=exact, selects the per-bin sincos of theta = (k dt) c."""
+    mode = os.environ.get("VLAPY_B200_PHASE", "table")
+    if mode == "exact":
+        return ops.PHASE_EXACT
+    k = np.asarray(k, dtype=np.float64)
+    n = k.shape[-1]
+    m = np.arange(n // 2 + 1)
+    lin = m * k[..., 1:2]
+    if n >= 4 and np.all(np.abs(np.abs(k[..., : n // 2 + 1]) - np.abs(lin)) <= 8 * np.finfo(float).eps * np.abs(lin)):
+        return ops.PHASE_TABLE
+    return ops.PHASE_EXACT
+
+
 def get_vdfdx_exponential(kx, v):
     """vlapy/core/vlasov.py:83-110 -- v df/dx exponential integrator.
 
     kx may be (nx,) or (batch, nx) for ensembles of simulations with their own box length."""
     kx_d = const(_check_wavenumbers(kx, "v df/dx"))
     v_d = const(v)
+    flags = _phase_flags(kx)
 
     def step_vdfdx_exponential(f, dt):
         f_d, host = to_dev(f)
-        return back(ops.vdfdx_exp(f_d.contiguous(), kx_d, v_d, dt), host)
+        return back(ops.vdfdx_exp(f_d.contiguous(), kx_d, v_d, dt, flags=flags), host)
 
     return step_vdfdx_exponential
 
@@ -41,11 +59,12 @@ def get_vdfdx_exponential(kx, v):
 def get_edfdv_exponential(kv):
     """vlapy/core/vlasov.py:113-140 -- e df/dv exponential integrator."""
     kv_d = const(_check_wavenumbers(kv, "e df/dv"))
+    flags = _phase_flags(kv)
 
     def step_edfdv_exponential(f, e, dt):
         f_d, host = to_dev(f)
         e_d, _ = to_dev(e)
-        return back(ops.edfdv_exp(f_d.contiguous(), e_d.contiguous(), kv_d, dt), host)
+        return back(ops.edfdv_exp(f_d.contiguous(), e_d.contiguous(), kv_d, dt, flags=flags), host)
 
     return step_edfdv_exponential
 

@@ -1,0 +1,432 @@
+// advect_fast.cuh -- register-resident versions of the three advection passes (see advect.h for
+// the algorithm and the meaning of N = N1*N2, COLS/ROWS packing and the pointwise un-mixing).
+//
+// Differences from the generic phase program in advect.h:
+//  * every thread owns 16 complex values in registers; a length-L transform (L = 64 or 128) is
+//    two register butterflies (radix L/8, then radix 8) with ONE shared-memory exchange between;
+//  * the inverse runs the same two steps backwards (radix 8, exchange, radix L/8), so between the
+//    forward and the inverse transform of pass 2 the data never leaves registers;
+//  * in pass 2 a thread owns sub-transform m of one group AND sub-transform R1-1-m of the partner
+//    group (or R1-m inside a self-paired group): both members of every conjugate pair (k, N-k)
+//    sit in the same thread, so un-mixing the two packed real channels costs two complex
+//    multiplies per PAIR:  U = Z + conj(Zp), V = Z - conj(Zp), X1 = Pa U, X2 = Pb V,
+//    Y[k] = (X1 + X2)/2, Y[N-k] = conj(X1 - X2)/2;
+//  * phase factors come from geometric tables (VPFP_PHASE_TABLE): P(k) = base(k1) * G^(k2) with
+//    G = exp(-i N1 phi), phi = (K[1] dt) c, built once per column tile from 17 sincos per
+//    sequence and reused for all group-pair tiles the CTA walks through; VPFP_PHASE_EXACT keeps the
+//    per-bin sincos of theta = (K[k] dt) c (the reference's own rounding);
+//  * intermediates are stored in NATURAL k1 order (row k1*N2 + n2): every thread knows the bins
+//    it holds, so no bit reversal is needed anywhere.
+#pragma once
+#include "advect.h"
+#include "butterflies.h"
+
+namespace fast {
+
+// ------------------------------------------------------------------------------------------
+// geometry of a length-L transform held as 16 values per thread
+// ------------------------------------------------------------------------------------------
+template <int L>
+struct Geo {
+  static constexpr int R1 = L / 8;    // first radix (8 or 16)
+  static constexpr int TPC = L / 16;  // threads per sequence
+  static constexpr int NA = 16 / R1;  // radix-R1 butterflies per thread in step A
+};
+
+struct FastArgs {
+  int mode, exact;
+  int N, N1, N2;
+  int nsim, nseq, nrows;
+  const double* fin; long ld_in;
+  double* fout; long ld_out;
+  const double* kvec;  // [nsim][N] (COLS) or [N] (ROWS)
+  const double* cvec;  // v[ncols] (COLS) or e[nrows] (ROWS)
+  double dt;
+  double* phantom;
+  const cplx* twN;  // exp(-2 pi i m/N)
+  const cplx* twL1; // exp(-2 pi i m/N1), N1 entries
+  const cplx* twL2; // exp(-2 pi i m/N2), N2 entries
+};
+
+__device__ __forceinline__ cplx ldg_c(const cplx* p) {
+  const double2 v = __ldg(reinterpret_cast<const double2*>(p));
+  return cmake(v.x, v.y);
+}
+
+// global access of element n of packed sequence `seq` (COLS: column pair; ROWS: row pair)
+template <int MODE>
+__device__ __forceinline__ cplx gload(const FastArgs& a, const double* base, long ld, int sim, int seq, long n,
+                                      bool first_pass) {
+  if (MODE == ADV_COLS) {
+    const double2 v = *reinterpret_cast<const double2*>(base + ((long)sim * a.N + n) * ld + 2 * (long)seq);
+    return cmake(v.x, v.y);
+  }
+  const long ra = 2 * (long)seq, rb = ra + 1;
+  double re = base[ra * ld + n];
+  double im = (rb < a.nrows) ? base[rb * ld + n] : ((!first_pass && a.phantom) ? a.phantom[n] : 0.0);
+  return cmake(re, im);
+}
+
+template <int MODE>
+__device__ __forceinline__ void gstore(const FastArgs& a, int sim, int seq, long n, cplx val, bool last_pass) {
+  if (MODE == ADV_COLS) {
+    *reinterpret_cast<double2*>(a.fout + ((long)sim * a.N + n) * a.ld_out + 2 * (long)seq) = make_double2(val.x, val.y);
+    return;
+  }
+  const long ra = 2 * (long)seq, rb = ra + 1;
+  a.fout[ra * a.ld_out + n] = val.x;
+  if (rb < a.nrows) a.fout[rb * a.ld_out + n] = val.y;
+  else if (!last_pass && a.phantom) a.phantom[n] = val.y;
+}
+
+// ------------------------------------------------------------------------------------------
+// pass 1 (INV = 0): forward length-L transform over n1 for fixed n2, times W_N^(n2 k1)
+// pass 3 (INV = 1): inverse length-L transform over k1 for fixed n2
+// Tile: CB batch lanes (COLS: packed columns of one n2; ROWS: consecutive n2 of one row pair).
+// Block: CB * TPC threads, lanes run along the batch.
+// ------------------------------------------------------------------------------------------
+template <int L, int MODE, int INV, int CB>
+__global__ void __launch_bounds__(CB* Geo<L>::TPC) pass13_kernel(const FastArgs a) {
+  using G = Geo<L>;
+  constexpr int R1 = G::R1, TPC = G::TPC, NA = G::NA;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  cplx* S = reinterpret_cast<cplx*>(smem_raw);  // [L][CB]
+  const int b = threadIdx.x % CB;
+  const int t = threadIdx.x / CB;  // 0..TPC-1
+  // tile decode
+  int sim = 0, seq, n2;
+  bool valid;
+  if (MODE == ADV_COLS) {
+    const int tiles_b = (a.nseq + CB - 1) / CB;
+    const int bt = blockIdx.x % tiles_b;
+    const long r = blockIdx.x / tiles_b;
+    n2 = (int)(r % a.N2);
+    sim = (int)(r / a.N2);
+    seq = bt * CB + b;
+    valid = seq < a.nseq;
+  } else {
+    const int tiles_b = a.N2 / CB;
+    const int bt = blockIdx.x % tiles_b;
+    seq = blockIdx.x / tiles_b;
+    n2 = bt * CB + b;
+    valid = true;
+  }
+  const long N2 = a.N2;
+  cplx x[16];
+  if (!INV) {
+    // ---- step A: radix-R1 over l = r + 8 j
+    const double* src = a.fin;
+#pragma unroll
+    for (int q = 0; q < NA; ++q) {
+      const int r = t + TPC * q;
+#pragma unroll
+      for (int j = 0; j < R1; ++j)
+        x[q * R1 + j] = valid ? gload<MODE>(a, src, a.ld_in, sim, seq, (long)(r + 8 * j) * N2 + n2, true)
+                              : cmake(0.0, 0.0);
+    }
+#pragma unroll
+    for (int q = 0; q < NA; ++q) {
+      const int r = t + TPC * q;
+      fftR<R1, -1>(x + q * R1);
+#pragma unroll
+      for (int m = 1; m < R1; ++m) x[q * R1 + m] = cmul(x[q * R1 + m], ldg_c(a.twL1 + r * m));
+#pragma unroll
+      for (int m = 0; m < R1; ++m) S[(m * 8 + r) * CB + b] = x[q * R1 + m];
+    }
+    __syncthreads();
+    // ---- step B: two radix-8 sub-transforms m = t, t + TPC
+#pragma unroll
+    for (int s = 0; s < 2; ++s) {
+      const int m = t + TPC * s;
+#pragma unroll
+      for (int r = 0; r < 8; ++r) x[s * 8 + r] = S[(m * 8 + r) * CB + b];
+      fft8<-1>(x + s * 8);
+#pragma unroll
+      for (int kp = 0; kp < 8; ++kp) {
+        const int k1 = m + R1 * kp;
+        cplx val = x[s * 8 + kp];
+        const long tw = (long)n2 * k1;  // < N
+        if (tw != 0) val = cmul(val, ldg_c(a.twN + tw));
+        if (valid) gstore<MODE>(a, sim, seq, (long)k1 * N2 + n2, val, false);
+      }
+    }
+  } else {
+    // ---- step B': inverse radix-8 over k' for sub-transforms m = t, t + TPC
+#pragma unroll
+    for (int s = 0; s < 2; ++s) {
+      const int m = t + TPC * s;
+#pragma unroll
+      for (int kp = 0; kp < 8; ++kp)
+        x[s * 8 + kp] = valid ? gload<MODE>(a, a.fout, a.ld_out, sim, seq, (long)(m + R1 * kp) * N2 + n2, false)
+                              : cmake(0.0, 0.0);
+      fft8<1>(x + s * 8);
+#pragma unroll
+      for (int r = 0; r < 8; ++r) {
+        cplx val = x[s * 8 + r];
+        if (r * m != 0) val = cmulc(val, ldg_c(a.twL1 + r * m));
+        S[(m * 8 + r) * CB + b] = val;
+      }
+    }
+    __syncthreads();
+    // ---- step A': inverse radix-R1 over m for r = t (+ TPC)
+#pragma unroll
+    for (int q = 0; q < NA; ++q) {
+      const int r = t + TPC * q;
+#pragma unroll
+      for (int m = 0; m < R1; ++m) x[q * R1 + m] = S[(m * 8 + r) * CB + b];
+      fftR<R1, 1>(x + q * R1);
+#pragma unroll
+      for (int j = 0; j < R1; ++j)
+        if (valid) gstore<MODE>(a, sim, seq, (long)(r + 8 * j) * N2 + n2, x[q * R1 + j], true);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// pass 2: for the group pair {k1, N1-k1}: forward length-L transform over n2, pointwise phase
+// multiply with un-mixing, inverse transform, times conj W_N^(n2 k1).  L = N2.
+// Block: CB * 2*TPC threads; the CTA keeps its CB packed sequences and walks over T1CHUNK
+// consecutive group-pair tiles so the phase tables are built once.
+// ------------------------------------------------------------------------------------------
+template <int L, int MODE, int CB>
+__global__ void __launch_bounds__(CB * 2 * Geo<L>::TPC) pass2_kernel(const FastArgs a, const int t1_chunk) {
+  using G = Geo<L>;
+  constexpr int R1 = G::R1, TPC = G::TPC, NA = G::NA;
+  constexpr int NT = CB * 2 * TPC;
+  constexpr int PITCH = (MODE == ADV_ROWS) ? CB + 1 : CB;  // odd pitch: conflict-free transposing access
+  constexpr int HALF = L / 2;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  cplx* S = reinterpret_cast<cplx*>(smem_raw);        // [2][L][PITCH] exchange / staging
+  cplx* PT = S + 2 * L * PITCH;                       // [2 chan][CB][HALF+1]  G^j
+  cplx* BASE = PT + 2 * CB * (HALF + 1);              // [2 groups][2 chan][CB]
+  double* PHI = reinterpret_cast<double*>(BASE + 4 * CB);  // [2 chan][CB]
+
+  const int b = threadIdx.x % CB;
+  const int u = threadIdx.x / CB;  // 0..2*TPC-1 = 0..R1-1
+  const int T1 = a.N1 / 2;
+  const int nchunks = (T1 + t1_chunk - 1) / t1_chunk;
+  const int tiles_b = (a.nseq + CB - 1) / CB;
+  int sim = 0;
+  const int chunk = blockIdx.x % nchunks;
+  long rest = blockIdx.x / nchunks;
+  const int bt = (int)(rest % tiles_b);
+  if (MODE == ADV_COLS) sim = (int)(rest / tiles_b);
+  const int seq = bt * CB + b;
+  const bool valid = seq < a.nseq;
+  const long N = a.N, N1 = a.N1;
+  const double inv_n = 1.0 / (double)N;
+
+  // advection constants of the two packed channels
+  double ca = 0.0, cb = 0.0;
+  if (valid) {
+    const long ra = 2 * (long)seq, rb = ra + 1;
+    ca = a.cvec[ra];
+    cb = (MODE == ADV_COLS || rb < a.nrows) ? a.cvec[rb] : 0.0;
+  }
+  const double* K = a.kvec + (MODE == ADV_COLS ? (long)sim * N : 0);
+
+  if (!a.exact) {
+    // phi = (K[1] dt) c ; G = exp(-i N1 phi); PT[j] = G^j = H[j>>3] * Lo[j&7], scaled by 1/(2N)
+    if (u == 0) {
+      const double k1dt = mul_rn(K[1], a.dt);
+      PHI[b] = mul_rn(k1dt, ca);
+      PHI[CB + b] = mul_rn(k1dt, cb);
+    }
+    __syncthreads();
+    // Lo[j] j = 0..7 -> PT[..][j], H[j] j = 1..HALF/8 -> PT[..][8 j]
+    for (int w = threadIdx.x; w < 2 * CB * (8 + HALF / 8); w += NT) {
+      const int sq = w / (8 + HALF / 8), i = w % (8 + HALF / 8);
+      const int j = (i < 8) ? i : 8 * (i - 7);
+      const double th = (double)N1 * PHI[sq] * (double)j;
+      double s, c;
+      sincos(th, &s, &c);
+      PT[sq * (HALF + 1) + j] = cmake(c, -s);
+    }
+    __syncthreads();
+    for (int w = threadIdx.x; w < 2 * CB * (HALF + 1); w += NT) {
+      const int sq = w / (HALF + 1), j = w % (HALF + 1);
+      if (j >= 8 && (j & 7)) PT[sq * (HALF + 1) + j] = cmul(PT[sq * (HALF + 1) + (j & ~7)], PT[sq * (HALF + 1) + (j & 7)]);
+    }
+    __syncthreads();
+  }
+
+  for (int t1 = chunk * t1_chunk; t1 < min(T1, (chunk + 1) * t1_chunk); ++t1) {
+    const bool self = (t1 == 0);
+    const int k1g0 = self ? 0 : t1, k1g1 = self ? (int)(N1 / 2) : (int)(N1 - t1);
+#define K1G(g) ((g) ? k1g1 : k1g0)
+    if (!a.exact) {
+      // base(k1) per group/channel
+      if (u < 4) {
+        const int g = u >> 1, ch = u & 1;
+        double s, c;
+        sincos((double)K1G(g) * PHI[ch * CB + b], &s, &c);
+        BASE[(g * 2 + ch) * CB + b] = cmake(c * 0.5 * inv_n, -s * 0.5 * inv_n);
+      }
+    }
+    cplx x[16];
+    // ---------------- load + step A (group gA = u / TPC, r = (u % TPC) + TPC q)
+    {
+      const int g = u / TPC, ta = u % TPC;
+      if (MODE == ADV_ROWS) {
+        // stage the tile through shared memory with lanes along the contiguous n2 axis
+        __syncthreads();
+        for (int w = threadIdx.x; w < 2 * L * CB; w += NT) {
+          const int l = w % L, bb = (w / L) % CB, gg = w / (L * CB);
+          const int sq = bt * CB + bb;
+          cplx val = cmake(0.0, 0.0);
+          if (sq < a.nseq) val = gload<MODE>(a, a.fout, a.ld_out, sim, sq, (long)K1G(gg) * L + l, false);
+          S[(gg * L + l) * PITCH + bb] = val;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int q = 0; q < NA; ++q)
+#pragma unroll
+          for (int j = 0; j < R1; ++j) x[q * R1 + j] = S[(g * L + (ta + TPC * q) + 8 * j) * PITCH + b];
+        __syncthreads();
+      } else {
+#pragma unroll
+        for (int q = 0; q < NA; ++q)
+#pragma unroll
+          for (int j = 0; j < R1; ++j)
+            x[q * R1 + j] = valid ? gload<MODE>(a, a.fout, a.ld_out, sim, seq,
+                                                (long)K1G(g) * L + (ta + TPC * q) + 8 * j, false)
+                                  : cmake(0.0, 0.0);
+        __syncthreads();  // previous iteration's readers of S are done
+      }
+#pragma unroll
+      for (int q = 0; q < NA; ++q) {
+        const int r = ta + TPC * q;
+        fftR<R1, -1>(x + q * R1);
+#pragma unroll
+        for (int m = 1; m < R1; ++m) x[q * R1 + m] = cmul(x[q * R1 + m], ldg_c(a.twL2 + r * m));
+#pragma unroll
+        for (int m = 0; m < R1; ++m) S[(g * L + m * 8 + r) * PITCH + b] = x[q * R1 + m];
+      }
+    }
+    __syncthreads();
+    // ---------------- step B: sub-transforms (gA, mA) in x[0..7], (gB, mB) in x[8..15]
+    int gA, mA, gB, mB;
+    bool special = false;  // the thread holding m = 0 and m = R1/2 of the k1 = 0 group
+    if (!self) {
+      gA = 0; mA = u; gB = 1; mB = R1 - 1 - u;
+    } else if (u < R1 / 2) {
+      gA = gB = 0;
+      if (u == 0) { mA = 0; mB = R1 / 2; special = true; }
+      else { mA = u; mB = R1 - u; }
+    } else {
+      gA = gB = 1; mA = u - R1 / 2; mB = R1 - 1 - mA;
+    }
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+      x[r] = S[(gA * L + mA * 8 + r) * PITCH + b];
+      x[8 + r] = S[(gB * L + mB * 8 + r) * PITCH + b];
+    }
+    fft8<-1>(x);
+    fft8<-1>(x + 8);
+    // ---------------- pointwise: pairs (Z at bin k, Zp at bin N - k), both in this thread
+    {
+      const long k1A = self ? (gA ? N1 / 2 : 0) : (gA ? N1 - t1 : t1);
+      auto pair_op = [&](cplx& Zr, cplx& Zpr, const long kbin, const long k1, const int gsel, const bool selfpair) {
+        const bool neg = (2 * kbin > N);
+        const bool nyq = (2 * kbin == N);
+        cplx Pa, Pb;  // scaled by 1/(2N)
+        if (a.exact) {
+          const long kr = neg ? N - kbin : kbin;
+          const double kdt = mul_rn(K[kr], a.dt);
+          double s, c;
+          sincos(mul_rn(kdt, ca), &s, &c);
+          Pa = cmake(c * 0.5 * inv_n, (nyq ? 0.0 : (neg ? s : -s)) * 0.5 * inv_n);
+          sincos(mul_rn(kdt, cb), &s, &c);
+          Pb = cmake(c * 0.5 * inv_n, (nyq ? 0.0 : (neg ? s : -s)) * 0.5 * inv_n);
+        } else {
+          const int k2 = (int)((kbin - k1) / N1);           // 0..L-1
+          const int j = neg ? (L - k2) : k2;                // |signed k2| in 0..HALF
+          cplx ta_ = PT[b * (HALF + 1) + j], tb_ = PT[(CB + b) * (HALF + 1) + j];
+          if (neg) { ta_ = cconj(ta_); tb_ = cconj(tb_); }
+          Pa = cmul(BASE[(gsel * 2 + 0) * CB + b], ta_);
+          Pb = cmul(BASE[(gsel * 2 + 1) * CB + b], tb_);
+          if (nyq) { Pa.y = 0.0; Pb.y = 0.0; }
+        }
+        const cplx Z = Zr, Zp = Zpr;
+        const cplx U = cadd(Z, cconj(Zp)), V = csub(Z, cconj(Zp));
+        const cplx X1 = cmul(Pa, U), X2 = cmul(Pb, V);
+        Zr = cadd(X1, X2);
+        if (!selfpair) Zpr = cconj(csub(X1, X2));
+      };
+      if (!special) {
+        // cross pattern: A[k'] (bin k1A + N1 (mA + R1 k')) pairs with B[7 - k']
+#pragma unroll
+        for (int pr = 0; pr < 8; ++pr) pair_op(x[pr], x[15 - pr], k1A + N1 * (mA + R1 * pr), k1A, gA, false);
+      } else {
+        // k1 = 0 group, sub-transforms m = 0 (x[0..7]) and m = R1/2 (x[8..15]), paired inside themselves
+        pair_op(x[0], x[0], 0, 0, 0, true);                              // DC
+        pair_op(x[4], x[4], N1 * (long)(R1 * 4), 0, 0, true);            // Nyquist
+#pragma unroll
+        for (int pr = 1; pr < 4; ++pr) pair_op(x[pr], x[8 - pr], N1 * (long)(R1 * pr), 0, 0, false);
+#pragma unroll
+        for (int pr = 0; pr < 4; ++pr) pair_op(x[8 + pr], x[15 - pr], N1 * (long)(R1 / 2 + R1 * pr), 0, 0, false);
+      }
+    }
+    // ---------------- step B': inverse radix-8, conj twiddle, exchange
+    fft8<1>(x);
+    fft8<1>(x + 8);
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+      cplx va = x[r], vb = x[8 + r];
+      if (r * mA != 0) va = cmulc(va, ldg_c(a.twL2 + r * mA));
+      if (r * mB != 0) vb = cmulc(vb, ldg_c(a.twL2 + r * mB));
+      S[(gA * L + mA * 8 + r) * PITCH + b] = va;
+      S[(gB * L + mB * 8 + r) * PITCH + b] = vb;
+    }
+    __syncthreads();
+    // ---------------- step A': inverse radix-R1, conj four-step twiddle, store
+    {
+      const int g = u / TPC, ta = u % TPC;
+#pragma unroll
+      for (int q = 0; q < NA; ++q) {
+        const int r = ta + TPC * q;
+#pragma unroll
+        for (int m = 0; m < R1; ++m) x[q * R1 + m] = S[(g * L + m * 8 + r) * PITCH + b];
+        fftR<R1, 1>(x + q * R1);
+#pragma unroll
+        for (int j = 0; j < R1; ++j) {
+          const int n2 = r + 8 * j;
+          cplx val = x[q * R1 + j];
+          const long tw = (long)n2 * K1G(g);
+          if (tw != 0) val = cmulc(val, ldg_c(a.twN + tw));
+          x[q * R1 + j] = val;
+        }
+      }
+      if (MODE == ADV_ROWS) {
+        __syncthreads();
+#pragma unroll
+        for (int q = 0; q < NA; ++q)
+#pragma unroll
+          for (int j = 0; j < R1; ++j) S[(g * L + (ta + TPC * q) + 8 * j) * PITCH + b] = x[q * R1 + j];
+        __syncthreads();
+        for (int w = threadIdx.x; w < 2 * L * CB; w += NT) {
+          const int l = w % L, bb = (w / L) % CB, gg = w / (L * CB);
+          const int sq = bt * CB + bb;
+          if (sq < a.nseq) gstore<MODE>(a, sim, sq, (long)K1G(gg) * L + l, S[(gg * L + l) * PITCH + bb], false);
+        }
+      } else if (valid) {
+#pragma unroll
+        for (int q = 0; q < NA; ++q)
+#pragma unroll
+          for (int j = 0; j < R1; ++j)
+            gstore<MODE>(a, sim, seq, (long)K1G(g) * L + (ta + TPC * q) + 8 * j, x[q * R1 + j], false);
+      }
+    }
+  }
+}
+
+#undef K1G
+
+template <int L, int CB>
+constexpr size_t pass2_smem(int mode) {
+  return sizeof(cplx) * (size_t)(2 * L * ((mode == ADV_ROWS) ? CB + 1 : CB) + 2 * CB * (L / 2 + 1) + 4 * CB) +
+         sizeof(double) * 2 * CB;
+}
+
+}  // namespace fast

@@ -14,6 +14,7 @@
 
 #include "../../include/vpfp_b200.h"
 #include "advect.h"
+#include "advect_fast.cuh"
 #include "rowops.h"
 
 // ------------------------------------------------------------------------------------------
@@ -128,8 +129,67 @@ static int get_scratch(int slot, size_t bytes, void** out) {
 // ------------------------------------------------------------------------------------------
 // advection / Poisson launcher
 // ------------------------------------------------------------------------------------------
-static int run_advect(AdvectProg a, cudaStream_t st) {
-  const AdvectPlan pl = make_advect_plan(a.mode, a.N);
+// ---- fast register-resident path (advect_fast.cuh): N1, N2 in {64, 128}
+template <class Kern>
+static int opt_in_smem(Kern kern, size_t smem) {
+  if (smem > 48 * 1024) CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  return VPFP_OK;
+}
+
+template <int L, int MODE, int INV>
+static int launch_pass13(const fast::FastArgs& fa, cudaStream_t st) {
+  constexpr int CB = (L == 128) ? 16 : 32;
+  constexpr int threads = CB * fast::Geo<L>::TPC;
+  const size_t smem = sizeof(cplx) * L * CB;
+  long grid;
+  if (MODE == ADV_COLS) grid = (long)fa.nsim * fa.N2 * ((fa.nseq + CB - 1) / CB);
+  else grid = (long)fa.nseq * (fa.N2 / CB);
+  if (grid > 2147483647L) return fail(VPFP_ERR_UNSUPPORTED, "grid too large");
+  fast::pass13_kernel<L, MODE, INV, CB><<<(unsigned)grid, threads, smem, st>>>(fa);
+  CUDA_TRY(cudaGetLastError());
+  return VPFP_OK;
+}
+
+template <int L, int MODE>
+static int launch_pass2(const fast::FastArgs& fa, cudaStream_t st) {
+  constexpr int CB = (L == 128) ? 8 : 16;
+  constexpr int threads = CB * 2 * fast::Geo<L>::TPC;
+  const size_t smem = fast::pass2_smem<L, CB>(MODE);
+  static bool configured = false;
+  if (!configured) {
+    int rc = opt_in_smem(fast::pass2_kernel<L, MODE, CB>, smem);
+    if (rc) return rc;
+    configured = true;
+  }
+  const int T1 = fa.N1 / 2;
+  const int t1_chunk = 8;
+  const int nchunks = (T1 + t1_chunk - 1) / t1_chunk;
+  const long grid = (long)(MODE == ADV_COLS ? fa.nsim : 1) * ((fa.nseq + CB - 1) / CB) * nchunks;
+  if (grid > 2147483647L) return fail(VPFP_ERR_UNSUPPORTED, "grid too large");
+  fast::pass2_kernel<L, MODE, CB><<<(unsigned)grid, threads, smem, st>>>(fa, t1_chunk);
+  CUDA_TRY(cudaGetLastError());
+  return VPFP_OK;
+}
+
+template <int MODE>
+static int run_fast_mode(const fast::FastArgs& fa, cudaStream_t st) {
+  int rc;
+  if (fa.N1 == 64) rc = launch_pass13<64, MODE, 0>(fa, st); else rc = launch_pass13<128, MODE, 0>(fa, st);
+  if (rc) return rc;
+  if (fa.N2 == 64) rc = launch_pass2<64, MODE>(fa, st); else rc = launch_pass2<128, MODE>(fa, st);
+  if (rc) return rc;
+  if (fa.N1 == 64) rc = launch_pass13<64, MODE, 1>(fa, st); else rc = launch_pass13<128, MODE, 1>(fa, st);
+  return rc;
+}
+
+static bool fast_eligible(const AdvectProg& a, const AdvectPlan& pl) {
+  if (a.op != OP_PHASE || pl.N1 == 1) return false;
+  if (!((pl.N1 == 64 || pl.N1 == 128) && (pl.N2 == 64 || pl.N2 == 128))) return false;
+  return true;
+}
+
+static int run_advect(AdvectProg a, cudaStream_t st, int flags = VPFP_PHASE_EXACT) {
+  const AdvectPlan pl = make_advect_plan(a.mode, a.N, 2048, 2048);
   int rc = get_twiddles(a.N, &a.tw);
   if (rc) return rc;
   if (pl.N1 == 1) {
@@ -141,6 +201,20 @@ static int run_advect(AdvectProg a, cudaStream_t st) {
     rc = get_scratch(SCR_PHANTOM, sizeof(double) * (size_t)a.N, &ph);
     if (rc) return rc;
     a.phantom = (double*)ph;
+  }
+  if (fast_eligible(a, pl) && !(flags & VPFP_FORCE_GENERIC)) {
+    fast::FastArgs fa;
+    fa.mode = a.mode; fa.exact = (flags & VPFP_PHASE_TABLE) ? 0 : 1;
+    fa.N = a.N; fa.N1 = pl.N1; fa.N2 = pl.N2;
+    fa.nsim = a.nsim; fa.nseq = a.nseq; fa.nrows = a.nrows;
+    fa.fin = a.fin; fa.ld_in = a.ld_in; fa.fout = a.fout; fa.ld_out = a.ld_out;
+    fa.kvec = a.kvec; fa.cvec = a.cvec; fa.dt = a.dt; fa.phantom = a.phantom;
+    fa.twN = a.tw;
+    rc = get_twiddles(pl.N1, &fa.twL1);
+    if (rc) return rc;
+    rc = get_twiddles(pl.N2, &fa.twL2);
+    if (rc) return rc;
+    return (a.mode == ADV_COLS) ? run_fast_mode<ADV_COLS>(fa, st) : run_fast_mode<ADV_ROWS>(fa, st);
   }
   for (int pass = 1; pass <= 3; ++pass) {
     advect_set_pass(a, pl, pass);
@@ -224,14 +298,13 @@ int vpfp_edfdv_exp(const double* f_in, long ld_in, double* f_out, long ld_out, c
     return fail(VPFP_ERR_ARG, "vpfp_edfdv_exp: bad argument");
   if (!is_pow2(nv) || nv < 4 || nv > (1 << 24))
     return fail(VPFP_ERR_UNSUPPORTED, "e df/dv: <exponential> needs nv = 2^k >= 4 on the b200 backend");
-  (void)flags;
   AdvectProg a;
   memset(&a, 0, sizeof(a));
   a.mode = ADV_ROWS; a.op = OP_PHASE; a.N = nv;
   a.nsim = 1; a.nrows = rows; a.nseq = (rows + 1) / 2;
   a.fin = f_in; a.ld_in = ld_in; a.fout = f_out; a.ld_out = ld_out;
   a.kvec = kv; a.cvec = e; a.addv = nullptr; a.dt = dt;
-  return run_advect(a, (cudaStream_t)stream);
+  return run_advect(a, (cudaStream_t)stream, flags);
 }
 
 int vpfp_vdfdx_exp(const double* f_in, long ld_in, double* f_out, long ld_out, const double* kx,
@@ -244,14 +317,13 @@ int vpfp_vdfdx_exp(const double* f_in, long ld_in, double* f_out, long ld_out, c
     return fail(VPFP_ERR_UNSUPPORTED, "v df/dx: <exponential> needs nx = 2^k >= 2 on the b200 backend");
   if ((ncols & 1) || (ld_in & 1) || (ld_out & 1) || ((uintptr_t)f_in & 15) || ((uintptr_t)f_out & 15))
     return fail(VPFP_ERR_UNSUPPORTED, "v df/dx: column count and row pitch must be even, f 16-byte aligned");
-  (void)flags;
   AdvectProg a;
   memset(&a, 0, sizeof(a));
   a.mode = ADV_COLS; a.op = OP_PHASE; a.N = nx;
   a.nsim = batch; a.nrows = nx; a.nseq = ncols / 2;
   a.fin = f_in; a.ld_in = ld_in; a.fout = f_out; a.ld_out = ld_out;
   a.kvec = kx; a.cvec = v; a.addv = nullptr; a.dt = dt;
-  return run_advect(a, (cudaStream_t)stream);
+  return run_advect(a, (cudaStream_t)stream, flags);
 }
 
 int vpfp_edfdv_cd2(const double* f_in, long ld_in, double* f_out, long ld_out, const double* e,

@@ -11,7 +11,7 @@ import torch
 from . import _lib
 
 FP_OPS = {"lb": 0, "dg": 1}
-PHASE_EXACT, PHASE_TABLE = 0, 1
+PHASE_EXACT, PHASE_TABLE, FORCE_GENERIC = 0, 1, 2
 
 # number of kernels of this library launched since the last reset (bench.py's gpu_launches claim)
 launch_count = 0
@@ -56,7 +56,7 @@ def _is_pow2(n):
 
 def adv_launches(mode, n):
     """kernels per advection call: one when the sequence fits a CTA, else the three passes"""
-    return 1 if n <= (2048 if mode == "cols" else 8192) else 3
+    return 1 if n <= 2048 else 3
 
 
 def edfdv_exp(f, e, kv, dt, out=None, flags=PHASE_EXACT):
