@@ -1,0 +1,372 @@
+#!/usr/bin/env python
+"""bench.py -- phase-space cell-updates/s of the full collisional VPFP timestep.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload c5|c3|c2|c1]
+
+A "step" is one full timestep of the reference's inner loop (vlapy/core/step.py:302-326): the
+Vlasov-Poisson splitting schedule (leapfrog: e df/dv half step, v df/dx, Poisson, e df/dv half
+step), the implicit Lenard-Bernstein step, and the per-step stored quantities (six v-moments,
+series means, two x-modes of f).  Default workload: C5 of BASELINE.json, 16384 x 16384 fp64.
+
+  value  -- nx*nv*K / t, state resident in HBM, CUDA-event timed, max over ranks
+  e2e    -- same metric through the public inner-loop API with HOST buffers: every timed call
+            uploads f, e, the driver rows and times from pinned host memory, runs K steps, and
+            downloads everything the reference's storage layer reads (fields, series, stored
+            modes, f, e) -- the host-copy cadence of vlapy/manager.py:138-150
+  roofline -- the dominant kernel: algorithmic bytes (16 B per cell per launch: one fp64 read and
+            one write of f) / its mean launch duration from CUDA events on the launching stream,
+            against MEASURED_PEAKS.json
+  cpu_baseline -- the oracle (numpy/scipy restatement of the reference) on the host cores, on a
+            bounded sample (a smaller grid of the same physics), reported only
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (nx, nv, description)
+    "c5": (16384, 16384, "C5: collisional NLEPW (k0=0.35, nu=1e-4|nu_ld|, leapfrog+LB) 16384x16384 fp64"),
+    "c3": (4096, 4096, "C3: collisional NLEPW (k0=0.35, leapfrog+LB) 4096x4096 fp64"),
+    "c2": (256, 2048, "C2: NLEPW as run_nlepw.py (k0=0.35, leapfrog+LB) 256x2048 fp64"),
+    "c1": (32, 512, "C1: Landau damping (tests/test_landau_damping.py grid, collisionless leapfrog) 32x512 fp64"),
+}
+EPW = {0.3: (1.1598464805919155, -0.012620368421117013), 0.35: (1.220953506161683, -0.03431805085829906)}
+
+
+def make_config(workload, nx=None, nv=None):
+    """Grids, dt, driver parameters and initial state as vlapy/outer_loop.py:98-144 builds them
+    (numpy only; deliberately independent of oracle/ so the GPU arm never touches it)."""
+    wnx, wnv, desc = WORKLOADS[workload]
+    nx, nv = nx or wnx, nv or wnv
+    landau = workload == "c1"
+    k0 = 0.3 if landau else 0.35
+    w_epw, nu_ld = EPW[k0]
+    tmax, nt, a0, t_R = (80, 500, 1e-7, 20) if landau else (1000, 4000, 4e-2, 25)
+    vmax, xmax = 6.4, 2.0 * np.pi / k0
+    dx = xmax / nx
+    x = np.linspace(dx / 2.0, xmax - dx / 2.0, nx)
+    kx = np.fft.fftfreq(nx, d=dx) * 2.0 * np.pi
+    ook = np.zeros_like(kx)
+    ook[1:] = 1.0 / kx[1:]
+    dv = 2 * vmax / nv
+    v = np.linspace(-vmax + dv / 2.0, vmax - dv / 2.0, nv)
+    kv = np.fft.fftfreq(nv, d=dv) * 2.0 * np.pi
+    t_dummy = np.linspace(0, tmax, nt)
+    dt = t_dummy[1] - t_dummy[0]
+    pulses = {"first pulse": {"start_time": 0, "t_L": 6, "t_wL": 2.5, "t_R": t_R, "t_wR": 2.5,
+                              "w0": w_epw, "a0": a0, "k0": k0}}
+    nu = 0.0 if landau else abs(nu_ld) * 1e-4
+    return dict(nx=nx, nv=nv, k0=k0, x=x, kx=kx, one_over_kx=ook, v=v, dv=dv, kv=kv, dt=dt, nu=nu,
+                pulses=pulses, desc=desc, vmax=vmax)
+
+
+def host_driver(cfg):
+    p = cfg["pulses"]["first pulse"]
+
+    def drv(t):
+        env = 0.5 * (np.tanh((t - p["t_L"]) / p["t_wL"]) - np.tanh((t - p["t_R"]) / p["t_wR"]))
+        return env * p["k0"] * p["a0"] * np.sin(p["k0"] * cfg["x"] - p["w0"] * t)
+
+    return drv
+
+
+def initial_state(cfg, pinned=False):
+    """mid-run-like synthetic state: Maxwellian x (1 + 0.05 sin k0 x), e = 0.01 cos k0 x"""
+    import torch
+    nx, nv = cfg["nx"], cfg["nv"]
+    fv = np.exp(-cfg["v"] ** 2 / 2.0)
+    fv /= (cfg["dv"] * (fv[1:] + fv[:-1]) / 2.0).sum()
+    pert = 1.0 + 0.05 * np.sin(cfg["k0"] * cfg["x"])
+    f = torch.empty((nx, nv), dtype=torch.float64, pin_memory=pinned)
+    fn = f.numpy()
+    blk = max(1, (1 << 24) // nv)
+    for i in range(0, nx, blk):
+        np.multiply(pert[i:i + blk, None], fv[None, :], out=fn[i:i + blk])
+    e = torch.empty(nx, dtype=torch.float64, pin_memory=pinned)
+    e.numpy()[:] = 0.01 * np.cos(cfg["k0"] * cfg["x"])
+    return f, e
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.rows, self.stop_flag = index, [], False
+
+    def run(self):
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5)
+                if out.returncode == 0 and out.stdout.strip():
+                    self.rows.append([c.strip() for c in out.stdout.strip().split(",")])
+            except Exception:
+                pass
+            time.sleep(0.1)
+
+    def summary(self):
+        self.stop_flag = True
+        self.join(timeout=3)
+        if not self.rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        sm = [float(r[0]) for r in self.rows if r[0].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for j, n in enumerate(names) if any(r[3 + j].lower().startswith("active") for r in self.rows)]
+        return {"sm_mhz": float(np.median(sm)) if sm else None,
+                "sm_max_mhz": float(self.rows[0][1]) if self.rows[0][1].replace(".", "").isdigit() else None,
+                "power_w_max": max(float(r[2]) for r in self.rows if r[2].replace(".", "").isdigit()),
+                "reasons": reasons, "samples": len(self.rows)}
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        return float(json.load(open(path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# ---------------------------------------------------------------------------------------------
+# reference arm / cpu baseline: the oracle port on the host cores, bounded sample
+# ---------------------------------------------------------------------------------------------
+
+def cpu_sample_grid(total_steps, budget_s=100.0):
+    """largest sample grid whose (warmup + steps) fits the time budget; ~0.4 us per cell-update
+    per core for the numpy/scipy path."""
+    for n in (4096, 2048, 1024, 512):
+        if n * n * 0.4e-6 * total_steps <= budget_s:
+            return n
+    return 512
+
+
+def run_cpu_steps(workload, n, steps, warmup, workers):
+    import scipy.fft as sfft
+    from oracle import vpfp_oracle as O
+    cfg = O.landau_config(n, n) if workload == "c1" else O.nlepw_config(n, n)
+    e = 0.01 * np.cos(cfg["k0"] * cfg["x"])
+    f = cfg["f0"] * (1.0 + 0.05 * np.sin(cfg["k0"] * cfg["x"]))[:, None]
+    kw = dict(integrator="leapfrog", dt=cfg["dt"], kx=cfg["kx"], kv=cfg["kv"], v=cfg["v"], dv=cfg["dv"],
+              one_over_kx=cfg["one_over_kx"], driver_function=cfg["driver_function"])
+    ts = []
+    with sfft.set_workers(workers):
+        for i in range(warmup + steps):
+            t0 = time.perf_counter()
+            t = cfg["dt"] * i
+            e, f, mom, ser = O.timestep(e, f, t, cfg["driver_function"](t), nu=cfg["nu"], fp_operator="lb", **kw)
+            O.stored_f_modes(f)
+            ts.append(time.perf_counter() - t0)
+    ts = ts[warmup:]
+    return n * n * len(ts) / sum(ts), float(np.mean(ts))
+
+
+def reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    n = cpu_sample_grid(args.steps + args.warmup)
+    value, sec = run_cpu_steps(args.workload, n, args.steps, args.warmup, workers=cores)
+    nx, nv, desc = WORKLOADS[args.workload]
+    sample = ("%dx%d sub-grid of the same physics; scipy.fft workers=%d (numpy Thomas loop is single-threaded), "
+              "cell-updates/s is size-normalised" % (n, n, cores))
+    line = {
+        "impl": "reference", "metric": "phase-space cell-updates/s (full collisional VPFP timestep)",
+        "value": value, "unit": "cell-updates/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {"workload": desc, "nx": nx, "nv": nv, "integrator": "leapfrog", "collisions": "lb",
+                   "reference_kind": "oracle port of the pure-Python reference (numpy/scipy), see oracle/"},
+        "cpu_baseline": {"value": value, "unit": "cell-updates/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "cell-updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+
+
+# ---------------------------------------------------------------------------------------------
+# GPU arm
+# ---------------------------------------------------------------------------------------------
+
+def gpu_arm(args):
+    import torch
+    import torch.distributed as dist
+    from vlapy_b200 import ops, outer_loop
+    from vlapy_b200.core import step
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    cfg = make_config(args.workload, args.nx, args.nv)
+    nx, nv = cfg["nx"], cfg["nv"]
+    rules = {"time": "first-last", "space": ["k0", "k1"]}
+    params = {"backend": {"core": "b200"}, "nu": cfg["nu"],
+              "vlasov-poisson": {"time": "leapfrog", "vdfdx": "exponential", "edfdv": "exponential",
+                                 "poisson": "spectral"},
+              "fokker-planck": {"type": "lb", "solver": "batched_tridiagonal"}}
+    drv_fn = host_driver(cfg)
+    K, W = args.steps, args.warmup
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    if world > 1:
+        from vlapy_b200 import dist as vdist
+        result = vdist.bench_sharded(cfg, params, rules, K, W, dev, barrier)
+    else:
+        f_host, e_host = initial_state(cfg, pinned=True)
+        stuff = {k: cfg[k] for k in ("kx", "x", "one_over_kx", "v", "kv", "nv", "nx", "dv", "dt", "nu")}
+        stuff.update(e=e_host.numpy(), f=f_host.numpy(), rules_to_store_f=rules, driver_function=drv_fn,
+                     pulse_dictionary=cfg["pulses"])
+        one_step = step.get_timestep(all_params=params, stuff_for_time_loop=stuff)
+        total = W + K
+        times = cfg["dt"] * np.arange(total)
+        drv_rows = torch.from_numpy(np.stack([drv_fn(t) for t in times])).to(dev)
+        work = {
+            "time_batch": times, "driver_array_batch": drv_rows,
+            "e": e_host.to(dev), "f": f_host.to(dev),
+            "stored_f": torch.zeros((total, 2, nv), dtype=torch.complex128, device=dev),
+            "fields": {k: torch.zeros((total, nx), dtype=torch.float64, device=dev) for k in step.FIELD_KEYS},
+            "series": {"_rows": torch.zeros((total, 7), dtype=torch.float64, device=dev)},
+            "_moment_scratch": torch.zeros((8, nx), dtype=torch.float64, device=dev),
+        }
+        for i in range(W):
+            work, _ = one_step(work, i)
+        barrier()
+        sampler = ClockSampler(local_rank)
+        sampler.start()
+        ops.launch_count = 0
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record()
+        for i in range(W, W + K):
+            work, _ = one_step(work, i)
+        ev1.record()
+        barrier()
+        ms = ev0.elapsed_time(ev1)
+        launches = ops.launch_count
+        clocks = sampler.summary()
+        # ---- per-kernel durations (second pass over the same steps, events around every launch)
+        ops.profile_enable(True)
+        for i in range(W, W + K):
+            work, _ = one_step(work, i)
+        prof = ops.profile_report()
+        ops.profile_enable(False)
+        mean_n = float(work["series"]["_rows"][W + K - 1, 0])
+        del work, drv_rows
+        torch.cuda.empty_cache()
+        # ---- end to end through the public inner-loop API with host buffers
+        e2e = None
+        if not args.no_e2e:
+            sim, inner = outer_loop.get_sim_config_and_inner_loop_step(params, stuff, K, rules)
+            t_arr = cfg["dt"] * np.arange(K)
+            d_arr = torch.empty((K, nx), dtype=torch.float64, pin_memory=True)
+            d_arr.numpy()[:] = np.stack([drv_fn(t) for t in t_arr])
+            sim = inner(time_array=t_arr, driver_array=d_arr.numpy(), temp_storage=sim)   # warm-up (allocations)
+            sim.pop("_dev", None)                      # force the next call to upload f and e again
+            sim["f"], sim["e"] = f_host.numpy(), e_host.numpy()
+            torch.cuda.empty_cache()
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            sim = inner(time_array=t_arr, driver_array=d_arr.numpy(), temp_storage=sim)
+            torch.cuda.synchronize()
+            sec = time.perf_counter() - t0
+            h2d = (nx * nv * 8 + nx * 8 + K * nx * 8) / K
+            d2h = (8 * K * nx * 8 + 7 * K * 8 + K * 2 * nv * 16 + nx * nv * 8 + nx * 8) / K
+            e2e = {"value": nx * nv * K / sec, "unit": "cell-updates/s", "h2d_bytes_per_step": h2d,
+                   "d2h_bytes_per_step": d2h, "ms_per_step": sec * 1e3 / K,
+                   "note": "one inner-loop call of %d steps: uploads f,e,driver rows; downloads fields, series, "
+                           "stored modes, f, e (storage cadence of vlapy/manager.py:138-150)" % K}
+        result = dict(ms=ms, launches=launches, clocks=clocks, prof=prof, e2e=e2e, mean_n=mean_n, scaling="strong",
+                      parallelism="1 GPU")
+
+    if world > 1:
+        t = torch.tensor([result["ms"]], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        result["ms"] = float(t.item())
+    if rank == 0:
+        peak, peak_src = peaks()
+        ms = result["ms"]
+        value = nx * nv * K / (ms * 1e-3)
+        cells = nx * nv / world
+        prof = result["prof"]
+        ops_ms = {}
+        for label, (n, tot) in prof.items():
+            opname = label.split(".")[0]
+            ops_ms[opname] = ops_ms.get(opname, 0.0) + tot / K
+        kernels = {label: {"launches_per_step": n / K, "ms_per_launch": tot / n,
+                           "gbs_algorithmic": 16.0 * cells / (tot / n * 1e-3) / 1e9}
+                   for label, (n, tot) in prof.items() if tot / n > 0.02}
+        dom = max(prof.items(), key=lambda kv: kv[1][1])
+        dom_label, (dom_n, dom_tot) = dom
+        achieved = 16.0 * cells / (dom_tot / dom_n * 1e-3) / 1e9
+        step_bytes = (64.0 if cfg["nu"] > 0 else 48.0) * nx * nv
+        line = {
+            "metric": "phase-space cell-updates/s (full collisional VPFP timestep)",
+            "value": value, "unit": "cell-updates/s", "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": ms / K, "higher_is_better": True, "scaling": result["scaling"], "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": cfg["desc"], "nx": nx, "nv": nv, "integrator": "leapfrog", "collisions": "lb",
+                       "per_step": "edfdv(dt/2), vdfdx(dt), density+Poisson, edfdv(dt/2), FP solve + 8 moments, "
+                                   "series, 2 x-modes",
+                       "l2": "state (%.2f GB) exceeds the 126 MB L2; no flush needed" % (nx * nv * 8 / 1e9),
+                       "parallelism": result["parallelism"], "phase_factors": "geometric tables (VPFP_PHASE_TABLE)"},
+            "clocks": result["clocks"], "gpu_launches": result["launches"],
+            "roofline": {"bound": "hbm", "kernel": dom_label, "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                         "algorithmic_bytes_per_launch": 16.0 * cells,
+                         "step": {"bytes_per_cell_update": step_bytes / (nx * nv),
+                                  "achieved": step_bytes / (ms / K * 1e-3) / 1e9 / world,
+                                  "frac": step_bytes / (ms / K * 1e-3) / 1e9 / world / peak},
+                         "operators_ms_per_step": ops_ms, "kernels": kernels},
+            "e2e": result["e2e"], "mean_n_last_step": result["mean_n"],
+        }
+        if world == 1 and not args.no_cpu:
+            cores = os.cpu_count() or 1
+            n = cpu_sample_grid(3, budget_s=30.0)
+            v1, s1 = run_cpu_steps(args.workload, n, 2, 1, workers=1)
+            line["cpu_baseline"] = {"value": v1, "unit": "cell-updates/s", "cores": 1, "kind": "port",
+                                    "sample": "oracle port (numpy/scipy, scipy.fft workers=1 as the reference runs it) on a "
+                                              "%dx%d sub-grid of the same physics, 2 steps after 1 warm-up; host has %d cores"
+                                              % (n, n, cores)}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="c5", choices=sorted(WORKLOADS))
+    ap.add_argument("--nx", type=int, default=None)
+    ap.add_argument("--nv", type=int, default=None)
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        reference_arm(args)
+    else:
+        gpu_arm(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -42,6 +42,12 @@ int vpfp_abi_version(void);
 const char *vpfp_last_error(void);
 int vpfp_shutdown(void);
 
+/* Per-launch timing for benchmarking: when enabled, every kernel launch of this library is
+ * bracketed by CUDA events on its stream.  vpfp_profile_report() synchronises the device, writes
+ * one "label count total_ms" line per kernel label into buf and clears the records. */
+int vpfp_profile_enable(int on);
+int vpfp_profile_report(char *buf, int buflen);
+
 /* e df/dv, exponential integrator: f_out = Re ifft_v( exp(-i kv dt e[x]) fft_v f_in ).
  * Replaces vlapy/core/vlasov.py:113-140 (step_edfdv_exponential).
  * f_in/f_out: (rows, nv) with row strides ld_in/ld_out; e: (rows); kv: (nv) = 2*pi*fftfreq.
@@ -83,6 +89,14 @@ int vpfp_poisson(const double *n, const double *one_over_kx, const double *drive
 int vpfp_fp_step(const double *f_in, long ld_in, double *f_out, long ld_out, const double *v,
                  double nu, double dt, double dv, int op, double *moments_out, long mom_ld,
                  int rows, int nv, void *stream);
+
+/* Same operator for velocity grids built by np.linspace (vlapy/initializers.py:66):
+ * v_i = v0 + i*vstep for i < nv-1 and v_{nv-1} = vlast, bit for bit.  The diagonals are then affine
+ * in the cell index and nothing but f is loaded.  nv must be a power of two in [128, 16384];
+ * other sizes return VPFP_ERR_UNSUPPORTED (callers fall back to vpfp_fp_step). */
+int vpfp_fp_step_linspace(const double *f_in, long ld_in, double *f_out, long ld_out, double v0,
+                          double vstep, double vlast, double nu, double dt, double dv, int op,
+                          double *moments_out, long mom_ld, int rows, int nv, void *stream);
 
 /* First nmodes x-Fourier modes of f per v: out[(b*nmodes + m)*ncols + j] = sum_x f[b,x,j] w^(m x)
  * as interleaved (re, im) doubles.  Replaces vlapy/core/step.py:130-135 (get_f_to_store). */

@@ -217,17 +217,27 @@ def test_collision_unit_cases(dev):
 
 
 @pytest.mark.parametrize("op", ["lb", "dg"])
-@pytest.mark.parametrize("nv", [8, 64, 512, 2048, 4096, 16384])
-def test_fp_sizes_vs_oracle(dev, op, nv):
+@pytest.mark.parametrize("nv", [8, 64, 128, 256, 512, 1024, 2048, 4096, 8192, 16384])
+@pytest.mark.parametrize("linspace_kernel", [False, True])
+def test_fp_sizes_vs_oracle(dev, op, nv, linspace_kernel):
+    """generic phase program (any v array) and the kernel specialised for np.linspace grids"""
     from vlapy_b200 import ops
     dv, v, kv = O.velocity_grid(6.4, nv)
     nu = 3.4e-6 if nv >= 4096 else 1e-3
     f = O.shifted_maxwellian(5, v, 1.0, 0.3) * np.array([1.0, 0.7, 1.3, 0.2, 2.0])[:, None]
     ref = O.collision_step(f, v, nu, 0.25, dv, op)
     mom = torch.zeros((8, 5), dtype=torch.float64, device=dev)
-    out = ops.fp_step(torch.from_numpy(f).to(dev), torch.from_numpy(v).to(dev), nu, 0.25, dv, op, moments_out=mom)
+    vgrid = ops.linspace_params(v) if linspace_kernel else None
+    assert (vgrid is not None) == linspace_kernel
+    out = ops.fp_step(torch.from_numpy(f).to(dev), torch.from_numpy(v).to(dev), nu, 0.25, dv, op, moments_out=mom,
+                      vgrid=vgrid)
     assert rel_err(out.cpu().numpy(), ref) < TOL
     assert rel_err(mom[:6].cpu().numpy(), O.field_moments(ref, v, dv)) < TOL
+    ser = O.series_moments(ref, np.zeros(5), np.zeros(5), O.field_moments(ref, v, dv), dv)
+    np.testing.assert_allclose(mom[6].cpu().numpy().mean(), ser[5], rtol=1e-12)
+    np.testing.assert_allclose(mom[7].cpu().numpy().mean(), ser[6], rtol=1e-11)
+    out2 = ops.fp_step(torch.from_numpy(f).to(dev), torch.from_numpy(v).to(dev), nu, 0.25, dv, op, vgrid=vgrid)
+    assert torch.equal(out, out2)          # with and without the fused moments: same bits
 
 
 def field_tolerances(cfg, fmax):

@@ -34,6 +34,7 @@ def main():
     mom = torch.zeros((8, nx), dtype=torch.float64, device=dev)
     n = torch.ones(nx, dtype=torch.float64, device=dev)
     gb = 16.0 * nx * nv / 1e9
+    vg = ops.linspace_params(cfg["v"])
     res = {}
     cases = {
         "copy(torch)": (lambda: out.copy_(f), gb),
@@ -41,8 +42,10 @@ def main():
         "vdfdx_exp(table)": (lambda: ops.vdfdx_exp(f, kx, v, 0.25, out=out, flags=1), gb),
         "edfdv_exp(exact)": (lambda: ops.edfdv_exp(f, e, kv, 0.125, out=out, flags=0), gb),
         "vdfdx_exp(exact)": (lambda: ops.vdfdx_exp(f, kx, v, 0.25, out=out, flags=0), gb),
-        "fp_step+mom": (lambda: ops.fp_step(f, v, cfg["nu"], cfg["dt"], cfg["dv"], "lb", out=out, moments_out=mom), gb),
-        "fp_step": (lambda: ops.fp_step(f, v, cfg["nu"], cfg["dt"], cfg["dv"], "lb", out=out), gb),
+        "fp_fast+mom": (lambda: ops.fp_step(f, v, cfg["nu"], cfg["dt"], cfg["dv"], "lb", out=out, moments_out=mom, vgrid=vg), gb),
+        "fp_fast": (lambda: ops.fp_step(f, v, cfg["nu"], cfg["dt"], cfg["dv"], "lb", out=out, vgrid=vg), gb),
+        "fp_fast_dg": (lambda: ops.fp_step(f, v, cfg["nu"], cfg["dt"], cfg["dv"], "dg", out=out, vgrid=vg), gb),
+        "fp_generic": (lambda: ops.fp_step(f, v, cfg["nu"], cfg["dt"], cfg["dv"], "lb", out=out), gb),
         "moments8": (lambda: ops.moments(f, v, cfg["dv"], out=mom), gb / 2),
         "density": (lambda: ops.moments(f, v, cfg["dv"], nmom=1, out=mom[:1]), gb / 2),
         "xmodes": (lambda: ops.xmodes(f, 2), gb / 2),

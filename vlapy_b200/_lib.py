@@ -10,7 +10,8 @@ PKG = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(PKG)
 SO = os.path.join(PKG, "lib", "libvpfp_b200.so")
 SRC = os.path.join(PKG, "csrc", "vpfp_cuda.cu")
-HEADERS = [os.path.join(PKG, "csrc", n) for n in ("vpfp_common.h", "advect.h", "rowops.h")] + [
+HEADERS = [os.path.join(PKG, "csrc", n) for n in ("vpfp_common.h", "advect.h", "rowops.h", "butterflies.h",
+                                                    "advect_fast.cuh", "fp_fast.cuh")] + [
     os.path.join(ROOT, "include", "vpfp_b200.h")]
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
@@ -40,12 +41,15 @@ _SIGS = {
     "vpfp_abi_version": ([], _I),
     "vpfp_last_error": ([], _c.c_char_p),
     "vpfp_shutdown": ([], _I),
+    "vpfp_profile_enable": ([_I], _I),
+    "vpfp_profile_report": ([_c.c_char_p, _I], _I),
     "vpfp_edfdv_exp": ([_P, _L, _P, _L, _P, _P, _D, _I, _I, _I, _P], _I),
     "vpfp_vdfdx_exp": ([_P, _L, _P, _L, _P, _P, _D, _I, _I, _I, _I, _P], _I),
     "vpfp_edfdv_cd2": ([_P, _L, _P, _L, _P, _D, _D, _I, _I, _P], _I),
     "vpfp_moments": ([_P, _L, _P, _D, _P, _L, _I, _I, _I, _I, _P], _I),
     "vpfp_poisson": ([_P, _P, _P, _P, _I, _I, _P], _I),
     "vpfp_fp_step": ([_P, _L, _P, _L, _P, _D, _D, _D, _I, _P, _L, _I, _I, _P], _I),
+    "vpfp_fp_step_linspace": ([_P, _L, _P, _L, _D, _D, _D, _D, _D, _D, _I, _P, _L, _I, _I, _P], _I),
     "vpfp_xmodes": ([_P, _L, _P, _I, _I, _I, _I, _P], _I),
     "vpfp_driver": ([_P, _D, _P, _I, _P, _I, _P], _I),
     "vpfp_series": ([_P, _L, _P, _P, _P, _I, _P], _I),

@@ -18,9 +18,10 @@ def get_collision_operator(vax, nv, nx, nu, dt, dv, operator="lb"):
         raise NotImplementedError(
             "Collision Operator: <" + str(operator) + "> has not yet been implemented on the b200 backend")
     v_d = const(vax)
+    vgrid = ops.linspace_params(vax)      # np.linspace grids get the specialised kernel
 
     def collide(f_xv, moments_out=None):
-        return ops.fp_step(f_xv, v_d, nu, dt, dv, operator, moments_out=moments_out)
+        return ops.fp_step(f_xv, v_d, nu, dt, dv, operator, moments_out=moments_out, vgrid=vgrid)
 
     return collide
 

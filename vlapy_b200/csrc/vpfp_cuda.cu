@@ -15,6 +15,7 @@
 #include "../../include/vpfp_b200.h"
 #include "advect.h"
 #include "advect_fast.cuh"
+#include "fp_fast.cuh"
 #include "rowops.h"
 
 // ------------------------------------------------------------------------------------------
@@ -35,6 +36,26 @@ static int fail(int code, const std::string& msg) {
 static bool is_pow2(long n) { return n > 0 && (n & (n - 1)) == 0; }
 
 // ------------------------------------------------------------------------------------------
+// optional per-launch timing (vpfp_profile_*): CUDA events recorded on the launching stream around
+// every kernel of this library, read back by bench.py for the roofline block.  Off by default.
+// ------------------------------------------------------------------------------------------
+struct ProfRec { const char* label; cudaEvent_t a, b; };
+static bool g_prof_on = false;
+static std::vector<ProfRec> g_prof;
+static const char* g_prof_op = "";
+struct ProfScope {
+  cudaStream_t st; bool on; size_t idx;
+  ProfScope(const char* label, cudaStream_t s) : st(s), on(g_prof_on), idx(0) {
+    if (!on) return;
+    ProfRec r; r.label = label;
+    cudaEventCreate(&r.a); cudaEventCreate(&r.b);
+    cudaEventRecord(r.a, st);
+    idx = g_prof.size(); g_prof.push_back(r);
+  }
+  ~ProfScope() { if (on) cudaEventRecord(g_prof[idx].b, st); }
+};
+
+// ------------------------------------------------------------------------------------------
 // generic phase-program driver: phases separated by CTA barriers (see vpfp_common.h)
 // ------------------------------------------------------------------------------------------
 template <class Prog>
@@ -48,7 +69,7 @@ __global__ void __launch_bounds__(1024) prog_kernel(const Prog prog, const int n
 
 template <class Prog>
 static int launch_prog(const Prog& prog, long nblocks, int threads, long smem, int nph,
-                       cudaStream_t st) {
+                       cudaStream_t st, const char* label = "generic") {
   if (nblocks <= 0) return VPFP_OK;
   if (nblocks > 2147483647L) return fail(VPFP_ERR_UNSUPPORTED, "grid too large");
   if (smem > 227 * 1024) return fail(VPFP_ERR_UNSUPPORTED, "tile does not fit shared memory");
@@ -64,7 +85,10 @@ static int launch_prog(const Prog& prog, long nblocks, int threads, long smem, i
       configured[dev] = 227 * 1024;
     }
   }
-  prog_kernel<Prog><<<(unsigned)nblocks, threads, smem, st>>>(prog, nph);
+  {
+    ProfScope ps(label, st);
+    prog_kernel<Prog><<<(unsigned)nblocks, threads, smem, st>>>(prog, nph);
+  }
   CUDA_TRY(cudaGetLastError());
   return VPFP_OK;
 }
@@ -145,7 +169,10 @@ static int launch_pass13(const fast::FastArgs& fa, cudaStream_t st) {
   if (MODE == ADV_COLS) grid = (long)fa.nsim * fa.N2 * ((fa.nseq + CB - 1) / CB);
   else grid = (long)fa.nseq * (fa.N2 / CB);
   if (grid > 2147483647L) return fail(VPFP_ERR_UNSUPPORTED, "grid too large");
-  fast::pass13_kernel<L, MODE, INV, CB><<<(unsigned)grid, threads, smem, st>>>(fa);
+  {
+    ProfScope ps(MODE == ADV_COLS ? (INV ? "vdfdx.pass3" : "vdfdx.pass1") : (INV ? "edfdv.pass3" : "edfdv.pass1"), st);
+    fast::pass13_kernel<L, MODE, INV, CB><<<(unsigned)grid, threads, smem, st>>>(fa);
+  }
   CUDA_TRY(cudaGetLastError());
   return VPFP_OK;
 }
@@ -166,7 +193,10 @@ static int launch_pass2(const fast::FastArgs& fa, cudaStream_t st) {
   const int nchunks = (T1 + t1_chunk - 1) / t1_chunk;
   const long grid = (long)(MODE == ADV_COLS ? fa.nsim : 1) * ((fa.nseq + CB - 1) / CB) * nchunks;
   if (grid > 2147483647L) return fail(VPFP_ERR_UNSUPPORTED, "grid too large");
-  fast::pass2_kernel<L, MODE, CB><<<(unsigned)grid, threads, smem, st>>>(fa, t1_chunk);
+  {
+    ProfScope ps(MODE == ADV_COLS ? "vdfdx.pass2" : "edfdv.pass2", st);
+    fast::pass2_kernel<L, MODE, CB><<<(unsigned)grid, threads, smem, st>>>(fa, t1_chunk);
+  }
   CUDA_TRY(cudaGetLastError());
   return VPFP_OK;
 }
@@ -194,7 +224,8 @@ static int run_advect(AdvectProg a, cudaStream_t st, int flags = VPFP_PHASE_EXAC
   if (rc) return rc;
   if (pl.N1 == 1) {
     advect_set_pass(a, pl, 0);
-    return launch_prog(a, a.ntiles(), pl.threads[0], a.smem_bytes(), a.nphases(), st);
+    return launch_prog(a, a.ntiles(), pl.threads[0], a.smem_bytes(), a.nphases(), st,
+                       a.op == OP_POISSON ? "poisson" : (a.mode == ADV_COLS ? "vdfdx.single" : "edfdv.single"));
   }
   if (a.mode == ADV_ROWS && (a.nrows & 1)) {
     void* ph = nullptr;
@@ -218,7 +249,8 @@ static int run_advect(AdvectProg a, cudaStream_t st, int flags = VPFP_PHASE_EXAC
   }
   for (int pass = 1; pass <= 3; ++pass) {
     advect_set_pass(a, pl, pass);
-    rc = launch_prog(a, a.ntiles(), pl.threads[pass], a.smem_bytes(), a.nphases(), st);
+    rc = launch_prog(a, a.ntiles(), pl.threads[pass], a.smem_bytes(), a.nphases(), st,
+                     a.op == OP_POISSON ? "poisson" : (a.mode == ADV_COLS ? "vdfdx.generic" : "edfdv.generic"));
     if (rc) return rc;
   }
   return VPFP_OK;
@@ -272,6 +304,28 @@ struct PoissonDftProg {
   }
 };
 
+template <int M, int T>
+static int launch_fp_fast(const fpfast::Args& a, cudaStream_t st) {
+  const size_t smem = fpfast::smem_bytes<M, T>();
+  static bool configured = false;
+  if (!configured) {
+    if (smem > 48 * 1024)
+      CUDA_TRY(cudaFuncSetAttribute(fpfast::fp_kernel<M, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = true;
+  }
+  int per_sm = (int)((227 * 1024) / smem);
+  if (per_sm > 2048 / T) per_sm = 2048 / T;
+  if (per_sm < 1) per_sm = 1;
+  long grid = 148L * per_sm * 4;
+  if (grid > a.rows) grid = a.rows;
+  {
+    ProfScope ps("fp_step", st);
+    fpfast::fp_kernel<M, T><<<(unsigned)grid, T, smem, st>>>(a);
+  }
+  CUDA_TRY(cudaGetLastError());
+  return VPFP_OK;
+}
+
 // ------------------------------------------------------------------------------------------
 // C ABI
 // ------------------------------------------------------------------------------------------
@@ -289,6 +343,35 @@ int vpfp_shutdown(void) {
       if (kv.second.scratch[i]) cudaFree(kv.second.scratch[i]);
   }
   g_cache.clear();
+  return VPFP_OK;
+}
+
+int vpfp_profile_enable(int on) {
+  g_prof_on = on != 0;
+  return VPFP_OK;
+}
+
+// Synchronises the device, writes "label count total_ms\n" lines into buf and clears the records.
+int vpfp_profile_report(char* buf, int buflen) {
+  cudaDeviceSynchronize();
+  std::map<std::string, std::pair<long, double>> agg;
+  for (auto& r : g_prof) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, r.a, r.b) == cudaSuccess) {
+      auto& e = agg[r.label];
+      e.first += 1; e.second += ms;
+    }
+    cudaEventDestroy(r.a); cudaEventDestroy(r.b);
+  }
+  g_prof.clear();
+  std::string out;
+  for (auto& kv : agg) {
+    char line[256];
+    snprintf(line, sizeof(line), "%s %ld %.6f\n", kv.first.c_str(), kv.second.first, kv.second.second);
+    out += line;
+  }
+  if ((int)out.size() + 1 > buflen) return fail(VPFP_ERR_ARG, "vpfp_profile_report: buffer too small");
+  memcpy(buf, out.c_str(), out.size() + 1);
   return VPFP_OK;
 }
 
@@ -334,7 +417,7 @@ int vpfp_edfdv_cd2(const double* f_in, long ld_in, double* f_out, long ld_out, c
   p.dt = dt; p.dv = dv; p.rows = rows; p.nv = nv;
   const int threads = 256;
   p.cblocks = (nv + threads * 4 - 1) / (threads * 4);
-  return launch_prog(p, (long)rows * p.cblocks, threads, 0, 1, (cudaStream_t)stream);
+  return launch_prog(p, (long)rows * p.cblocks, threads, 0, 1, (cudaStream_t)stream, "edfdv.cd2");
 }
 
 int vpfp_moments(const double* f, long ld, const double* v, double dv, double* out, long out_ld,
@@ -346,7 +429,7 @@ int vpfp_moments(const double* f, long ld, const double* v, double dv, double* o
   p.nmom = nmom; p.rows = rows; p.ncols = ncols; p.edge_flags = edge_flags;
   int threads = 256;
   while (threads > 32 && threads * 2 > ncols) threads >>= 1;
-  return launch_prog(p, rows, threads, p.smem_bytes(threads), p.nphases(threads), (cudaStream_t)stream);
+  return launch_prog(p, rows, threads, p.smem_bytes(threads), p.nphases(threads), (cudaStream_t)stream, "moments");
 }
 
 int vpfp_poisson(const double* n, const double* one_over_kx, const double* driver, double* e,
@@ -356,7 +439,7 @@ int vpfp_poisson(const double* n, const double* one_over_kx, const double* drive
     if (nx > 4096) return fail(VPFP_ERR_UNSUPPORTED, "spectral Poisson: non power-of-two nx > 4096");
     PoissonDftProg p;
     p.n = n; p.ook = one_over_kx; p.driver = driver; p.e = e; p.N = nx;
-    return launch_prog(p, batch, 256, p.smem_bytes(), 3, (cudaStream_t)stream);
+    return launch_prog(p, batch, 256, p.smem_bytes(), 3, (cudaStream_t)stream, "poisson");
   }
   AdvectProg a;
   memset(&a, 0, sizeof(a));
@@ -389,6 +472,30 @@ int vpfp_fp_step(const double* f_in, long ld_in, double* f_out, long ld_out, con
   return launch_prog(p, rows, threads, p.smem_bytes(threads), p.nphases(threads), (cudaStream_t)stream);
 }
 
+int vpfp_fp_step_linspace(const double* f_in, long ld_in, double* f_out, long ld_out, double v0,
+                          double vstep, double vlast, double nu, double dt, double dv, int op,
+                          double* moments_out, long mom_ld, int rows, int nv, void* stream) {
+  if (!f_in || !f_out || rows <= 0 || nv <= 0) return fail(VPFP_ERR_ARG, "vpfp_fp_step_linspace: bad argument");
+  if (op != VPFP_FP_LB && op != VPFP_FP_DG)
+    return fail(VPFP_ERR_UNSUPPORTED, "Collision Operator: unknown operator id");
+  fpfast::Args a;
+  a.fin = f_in; a.ld_in = ld_in; a.fout = f_out; a.ld_out = ld_out;
+  a.v0 = v0; a.vstep = vstep; a.vlast = vlast; a.nu = nu; a.dt = dt; a.dv = dv; a.op = op;
+  a.mom_out = moments_out; a.mom_ld = mom_ld; a.rows = rows; a.nv = nv;
+  cudaStream_t st = (cudaStream_t)stream;
+  switch (nv) {
+    case 16384: return launch_fp_fast<32, 512>(a, st);
+    case 8192: return launch_fp_fast<16, 512>(a, st);
+    case 4096: return launch_fp_fast<16, 256>(a, st);
+    case 2048: return launch_fp_fast<8, 256>(a, st);
+    case 1024: return launch_fp_fast<8, 128>(a, st);
+    case 512: return launch_fp_fast<4, 128>(a, st);
+    case 256: return launch_fp_fast<4, 64>(a, st);
+    case 128: return launch_fp_fast<4, 32>(a, st);
+    default: return fail(VPFP_ERR_UNSUPPORTED, "vpfp_fp_step_linspace: nv must be a power of two in [128, 16384]");
+  }
+}
+
 int vpfp_xmodes(const double* f, long ld, double* out, int nmodes, int batch, int nx, int ncols,
                 void* stream) {
   if (!f || !out || nmodes < 1 || batch <= 0 || nx <= 0 || ncols <= 0)
@@ -406,12 +513,12 @@ int vpfp_xmodes(const double* f, long ld, double* out, int nmodes, int batch, in
   int rc = get_scratch(SCR_XMODES, bytes, &scratch);
   if (rc) return rc;
   p.partial = (double*)scratch;
-  rc = launch_prog(p, (long)batch * xch * p.cblocks, threads, 0, 1, (cudaStream_t)stream);
+  rc = launch_prog(p, (long)batch * xch * p.cblocks, threads, 0, 1, (cudaStream_t)stream, "xmodes");
   if (rc) return rc;
   XmodesReduceProg r;
   r.partial = p.partial; r.out = out; r.nmodes = nmodes; r.batch = batch; r.ncols = ncols; r.xchunks = xch;
   long total = (long)batch * nmodes * ncols * 2;
-  return launch_prog(r, (total + 255) / 256, 256, 0, 1, (cudaStream_t)stream);
+  return launch_prog(r, (total + 255) / 256, 256, 0, 1, (cudaStream_t)stream, "xmodes.reduce");
 }
 
 int vpfp_driver(const double* x, double t, const double* pulses, int npulse, double* out, int nx,
@@ -422,7 +529,7 @@ int vpfp_driver(const double* x, double t, const double* pulses, int npulse, dou
   DriverProg p;
   p.x = x; p.out = out; p.t = t; p.nx = nx; p.npulse = npulse;
   for (int i = 0; i < npulse * 7; ++i) p.pulses[i] = pulses[i];
-  return launch_prog(p, (nx + 255) / 256, 256, 0, 1, (cudaStream_t)stream);
+  return launch_prog(p, (nx + 255) / 256, 256, 0, 1, (cudaStream_t)stream, "driver");
 }
 
 int vpfp_series(const double* moments, long mom_ld, const double* e, const double* de, double* out,
@@ -432,7 +539,7 @@ int vpfp_series(const double* moments, long mom_ld, const double* e, const doubl
   p.mom = moments; p.mom_ld = mom_ld; p.e = e; p.de = de; p.out = out; p.nx = nx;
   int threads = 256;
   while (threads > 32 && threads > nx) threads >>= 1;
-  return launch_prog(p, 1, threads, p.smem_bytes(threads), p.nphases(threads), (cudaStream_t)stream);
+  return launch_prog(p, 1, threads, p.smem_bytes(threads), p.nphases(threads), (cudaStream_t)stream, "series");
 }
 
 }  // extern "C"

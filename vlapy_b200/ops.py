@@ -131,8 +131,22 @@ def poisson(n, one_over_kx, driver=None, out=None):
     return out
 
 
-def fp_step(f, v, nu, dt, dv, op="lb", out=None, moments_out=None):
-    """Implicit LB / Dougherty step (vlapy/core/collisions.py via step.py:102-108) on device."""
+def linspace_params(v):
+    """(v0, step, vlast) when the host array v is bit-for-bit np.linspace(v[0], v[-1], len(v)) --
+    how vlapy/initializers.py:66 builds the velocity grid -- else None."""
+    v = np.asarray(v, dtype=np.float64)
+    n = v.size
+    if n < 2 or not np.array_equal(v, np.linspace(v[0], v[-1], n)):
+        return None
+    return float(v[0]), float((v[-1] - v[0]) / (n - 1)), float(v[-1])
+
+
+FAST_FP_SIZES = (128, 256, 512, 1024, 2048, 4096, 8192, 16384)
+
+
+def fp_step(f, v, nu, dt, dv, op="lb", out=None, moments_out=None, vgrid=None):
+    """Implicit LB / Dougherty step (vlapy/core/collisions.py via step.py:102-108) on device.
+    vgrid = linspace_params(v) selects the kernel specialised for np.linspace velocity grids."""
     rows, ld = _chk_f(f)
     nv = f.shape[-1]
     if op not in FP_OPS:
@@ -142,6 +156,12 @@ def fp_step(f, v, nu, dt, dv, op="lb", out=None, moments_out=None):
         out = torch.empty(f.shape, dtype=f.dtype, device=f.device)
     _, ldo = _chk_f(out, "out")
     mp, mld = (None, 0) if moments_out is None else (moments_out.data_ptr(), moments_out.stride(0))
+    if vgrid is not None and nv in FAST_FP_SIZES:
+        _lib.check(_lib.lib().vpfp_fp_step_linspace(f.data_ptr(), ld, out.data_ptr(), ldo, vgrid[0], vgrid[1],
+                                                    vgrid[2], float(nu), float(dt), float(dv), FP_OPS[op], mp, mld,
+                                                    rows, nv, _stream()))
+        _count(1)
+        return out
     _lib.check(_lib.lib().vpfp_fp_step(f.data_ptr(), ld, out.data_ptr(), ldo, v.data_ptr(), float(nu), float(dt),
                                        float(dv), FP_OPS[op], mp, mld, rows, nv, _stream()))
     _count(1)
@@ -186,3 +206,19 @@ def pulses_to_array(pulse_dictionary):
     """{name: {k0, w0, a0, t_L, t_R, t_wL, t_wR, ...}} -> (npulse, 7) float64 in ABI order."""
     return np.array([[p["k0"], p["w0"], p["a0"], p["t_L"], p["t_R"], p["t_wL"], p["t_wR"]]
                      for p in pulse_dictionary.values()], dtype=np.float64).reshape(-1, 7)
+
+
+def profile_enable(on=True):
+    """bracket every kernel launch of the library with CUDA events (bench.py roofline block)"""
+    _lib.check(_lib.lib().vpfp_profile_enable(1 if on else 0))
+
+
+def profile_report():
+    """{label: (launches, total_ms)} since profiling was enabled; synchronises the device"""
+    buf = ctypes.create_string_buffer(1 << 16)
+    _lib.check(_lib.lib().vpfp_profile_report(buf, len(buf)))
+    out = {}
+    for line in buf.value.decode().splitlines():
+        label, n, ms = line.split()
+        out[label] = (int(n), float(ms))
+    return out

@@ -60,23 +60,38 @@ def post_inner_loop_update(temp_storage, this_np=np):
 
 
 def _device_storage(temp_storage, nt, nx, nv, dev):
-    """Device twins of the per-loop buffers of vlapy/outer_loop.py:190-215."""
+    """Device twins of the per-loop buffers of vlapy/outer_loop.py:190-215 (key ``_dev``) and pinned
+    host mirrors for the once-per-loop download (key ``_pin``).  The device copies of e and f are
+    authoritative between calls; delete ``temp_storage["_dev"]`` to make the next call upload
+    ``temp_storage["e"]`` / ``["f"]`` again."""
     d = temp_storage.get("_dev")
-    if d is not None and d["nt"] == nt:
-        return d
-    stored = temp_storage["stored_f"]
-    d = {
-        "nt": nt,
-        "fields": {k: torch.zeros((nt, nx), dtype=torch.float64, device=dev) for k in step.FIELD_KEYS},
-        "series_rows": torch.zeros((nt, 7), dtype=torch.float64, device=dev),
-        "stored_f": torch.zeros(stored.shape, dtype=torch.complex128 if np.iscomplexobj(stored) else torch.float64,
-                                device=dev),
-        "moments": torch.zeros((8, nx), dtype=torch.float64, device=dev),
-        "e": torch.from_numpy(np.ascontiguousarray(temp_storage["e"], dtype=np.float64)).to(dev),
-        "f": torch.from_numpy(np.ascontiguousarray(temp_storage["f"], dtype=np.float64)).to(dev),
-    }
-    temp_storage["_dev"] = d
-    return d
+    if d is None or d["nt"] != nt:
+        stored = temp_storage["stored_f"]
+        cplx = np.iscomplexobj(stored)
+        d = {
+            "nt": nt,
+            "fields": torch.zeros((len(step.FIELD_KEYS), nt, nx), dtype=torch.float64, device=dev),
+            "series_rows": torch.zeros((nt, 7), dtype=torch.float64, device=dev),
+            "stored_f": torch.zeros(stored.shape, dtype=torch.complex128 if cplx else torch.float64, device=dev),
+            "moments": torch.zeros((8, nx), dtype=torch.float64, device=dev),
+            "e": torch.from_numpy(np.ascontiguousarray(temp_storage["e"], dtype=np.float64)).to(dev),
+            "f": torch.from_numpy(np.ascontiguousarray(temp_storage["f"], dtype=np.float64)).to(dev),
+        }
+        temp_storage["_dev"] = d
+    p = temp_storage.get("_pin")
+    if p is None or p["nt"] != nt:
+        sf = d["stored_f"]
+        p = {
+            "nt": nt,
+            "fields": torch.empty(d["fields"].shape, dtype=torch.float64, pin_memory=True),
+            "series_rows": torch.empty((nt, 7), dtype=torch.float64, pin_memory=True),
+            "stored_f": torch.empty(sf.shape, dtype=torch.complex64 if sf.is_complex() else torch.float64,
+                                    pin_memory=True),
+            "e": torch.empty(nx, dtype=torch.float64, pin_memory=True),
+            "f": torch.empty((nx, nv), dtype=torch.float64, pin_memory=True),
+        }
+        temp_storage["_pin"] = p
+    return d, p
 
 
 def get_inner_loop_stepper(all_params, stuff_for_time_loop, steps_in_loop):
@@ -89,33 +104,42 @@ def get_inner_loop_stepper(all_params, stuff_for_time_loop, steps_in_loop):
     def inner_loop(time_array, driver_array, temp_storage):
         dev = device()
         nx, nv = np.asarray(temp_storage["f"]).shape[-2:]
-        d = _device_storage(temp_storage, steps_in_loop, nx, nv, dev)
-        # host -> device: the driver rows and times of this loop (pinned when the caller pinned them)
+        d, pin = _device_storage(temp_storage, steps_in_loop, nx, nv, dev)
+        # host -> device: the driver rows of this loop (asynchronous when the caller pinned them)
         drv = torch.as_tensor(np.ascontiguousarray(driver_array, dtype=np.float64)).to(dev, non_blocking=True)
         work = {
             "time_batch": np.asarray(time_array, dtype=np.float64),
             "driver_array_batch": drv,
             "e": d["e"], "f": d["f"],
             "stored_f": d["stored_f"],
-            "fields": dict(d["fields"]),
+            "fields": {k: d["fields"][j] for j, k in enumerate(step.FIELD_KEYS)},
             "series": {"_rows": d["series_rows"]},
             "_moment_scratch": d["moments"],
         }
         for it in range(steps_in_loop):
             work, _ = one_step(work, it)
         d["e"], d["f"] = work["e"], work["f"]
-        # device -> host, once per inner loop (the storage cadence of vlapy/manager.py:138-150)
+        # device -> host once per inner loop (the storage cadence of vlapy/manager.py:138-150),
+        # into pinned mirrors; the returned arrays are views that the next call overwrites, as the
+        # reference's in-place temp_storage arrays are.
+        pin["fields"].copy_(d["fields"], non_blocking=True)
+        pin["series_rows"].copy_(d["series_rows"], non_blocking=True)
+        sf = d["stored_f"]
+        pin["stored_f"].copy_(sf.to(torch.complex64) if sf.is_complex() else sf, non_blocking=True)
+        pin["e"].copy_(d["e"], non_blocking=True)
+        pin["f"].copy_(d["f"], non_blocking=True)
+        torch.cuda.current_stream().synchronize()
         temp_storage["time_batch"] = np.asarray(time_array)
         temp_storage["driver_array_batch"] = np.asarray(driver_array)
-        for k in step.FIELD_KEYS:
-            temp_storage["fields"][k] = d["fields"][k].cpu().numpy()
-        rows = d["series_rows"].cpu().numpy()
+        fields = pin["fields"].numpy()
+        for j, k in enumerate(step.FIELD_KEYS):
+            temp_storage["fields"][k] = fields[j]
+        rows = pin["series_rows"].numpy()
         for j, k in enumerate(step.SERIES_KEYS):
             temp_storage["series"][k] = rows[:, j].copy()
-        sf = d["stored_f"].cpu().numpy()
-        temp_storage["stored_f"] = sf.astype(np.complex64) if np.iscomplexobj(sf) else sf
-        temp_storage["e"] = d["e"].cpu().numpy()
-        temp_storage["f"] = d["f"].cpu().numpy()
+        temp_storage["stored_f"] = pin["stored_f"].numpy()
+        temp_storage["e"] = pin["e"].numpy()
+        temp_storage["f"] = pin["f"].numpy()
         post_inner_loop_update(temp_storage, np)
         return temp_storage
 
