@@ -80,7 +80,8 @@ __device__ __forceinline__ void gstore(const FastArgs& a, int sim, int seq, long
 }
 
 // ------------------------------------------------------------------------------------------
-// pass 1 (INV = 0): forward length-L transform over n1 for fixed n2, times W_N^(n2 k1)
+// pass 1 (INV = 0): forward length-L transform over n1 for fixed n2 (the four-step twiddle
+//                    W_N^(n2 k1) is applied by pass 2 when it loads, where it is a broadcast)
 // pass 3 (INV = 1): inverse length-L transform over k1 for fixed n2
 // Tile: CB batch lanes (COLS: packed columns of one n2; ROWS: consecutive n2 of one row pair).
 // Block: CB * TPC threads, lanes run along the batch.
@@ -144,10 +145,7 @@ __global__ void __launch_bounds__(CB* Geo<L>::TPC) pass13_kernel(const FastArgs 
 #pragma unroll
       for (int kp = 0; kp < 8; ++kp) {
         const int k1 = m + R1 * kp;
-        cplx val = x[s * 8 + kp];
-        const long tw = (long)n2 * k1;  // < N
-        if (tw != 0) val = cmul(val, ldg_c(a.twN + tw));
-        if (valid) gstore<MODE>(a, sim, seq, (long)k1 * N2 + n2, val, false);
+        if (valid) gstore<MODE>(a, sim, seq, (long)k1 * N2 + n2, x[s * 8 + kp], false);
       }
     }
   } else {
@@ -183,32 +181,68 @@ __global__ void __launch_bounds__(CB* Geo<L>::TPC) pass13_kernel(const FastArgs 
 }
 
 // ------------------------------------------------------------------------------------------
-// pass 2: for the group pair {k1, N1-k1}: forward length-L transform over n2, pointwise phase
-// multiply with un-mixing, inverse transform, times conj W_N^(n2 k1).  L = N2.
-// Block: CB * 2*TPC threads; the CTA keeps its CB packed sequences and walks over T1CHUNK
-// consecutive group-pair tiles so the phase tables are built once.
+// pass 2: for the group pair {k1, N1-k1}: four-step twiddle, forward length-L transform over n2,
+// pointwise phase multiply with un-mixing, inverse transform, conjugate twiddle.  L = N2.
+// Block: CB * 2*TPC threads.  The CTA keeps its CB packed sequences and walks over t1_chunk
+// consecutive group-pair tiles: phase tables are built once, and the next tile is prefetched
+// with cp.async into a staging buffer while the current one is transformed.
 // ------------------------------------------------------------------------------------------
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
+  const unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(sa), "l"(gmem));
+}
+__device__ __forceinline__ void cp_async8(void* smem, const void* gmem) {
+  const unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(sa), "l"(gmem));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;\n" ::: "memory"); }
+
 template <int L, int MODE, int CB>
-__global__ void __launch_bounds__(CB * 2 * Geo<L>::TPC) pass2_kernel(const FastArgs a, const int t1_chunk) {
+struct P2Layout {
   using G = Geo<L>;
+  static constexpr int R1 = G::R1;
+  // exchange buffer index of (group g, sub-transform m, position r, sequence b)
+  __device__ static __forceinline__ int sidx(int g, int m, int r, int b) {
+    if (MODE == ADV_COLS) return (g * L + m * 8 + r) * CB + b;
+    return (b * 2 + g) * (R1 * 9) + m * 9 + r;   // 9: odd pitch, conflict free for lanes along r or m
+  }
+  static constexpr int S_ELEMS = (MODE == ADV_COLS) ? 2 * L * CB : CB * 2 * R1 * 9;
+  // staging buffer index of (group g, position l, sequence b)
+  __device__ static __forceinline__ int tidx(int g, int l, int b) {
+    if (MODE == ADV_COLS) return (g * L + l) * CB + b;
+    return (b * 2 + g) * L + l;
+  }
+  static constexpr int T_ELEMS = 2 * L * CB;
+};
+
+template <int L, int MODE, int CB>
+__global__ void __launch_bounds__(CB * 2 * Geo<L>::TPC, 2) pass2_kernel(const FastArgs a, const int t1_chunk) {
+  using G = Geo<L>;
+  using LY = P2Layout<L, MODE, CB>;
   constexpr int R1 = G::R1, TPC = G::TPC, NA = G::NA;
   constexpr int NT = CB * 2 * TPC;
-  constexpr int PITCH = (MODE == ADV_ROWS) ? CB + 1 : CB;  // odd pitch: conflict-free transposing access
   constexpr int HALF = L / 2;
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  cplx* S = reinterpret_cast<cplx*>(smem_raw);        // [2][L][PITCH] exchange / staging
-  cplx* PT = S + 2 * L * PITCH;                       // [2 chan][CB][HALF+1]  G^j
+  cplx* S = reinterpret_cast<cplx*>(smem_raw);        // exchange
+  cplx* STG = S + LY::S_ELEMS;                        // staging (prefetched tile)
+  cplx* PT = STG + LY::T_ELEMS;                       // [2 chan][CB][HALF+1]  G^j
   cplx* BASE = PT + 2 * CB * (HALF + 1);              // [2 groups][2 chan][CB]
-  double* PHI = reinterpret_cast<double*>(BASE + 4 * CB);  // [2 chan][CB]
+  cplx* TWL = BASE + 4 * CB;                          // [L]     exp(-2 pi i m / L)
+  cplx* TWT = TWL + L;                                // [2][L]  four-step twiddles W_N^(n2 k1) of the staged tile
+  cplx* TWC = TWT + 2 * L;                            // [2][L]  the same for the tile being transformed
+  double* PHI = reinterpret_cast<double*>(TWC + 2 * L);    // [2 chan][CB]
 
-  const int b = threadIdx.x % CB;
-  const int u = threadIdx.x / CB;  // 0..2*TPC-1 = 0..R1-1
+  // thread roles: b = packed sequence, u = 0..R1-1 (step A: group u / TPC, r-slot u % TPC)
+  int b, u;
+  if (MODE == ADV_COLS) { b = threadIdx.x % CB; u = threadIdx.x / CB; }
+  else { const int ta = threadIdx.x % TPC; b = (threadIdx.x / TPC) % CB; u = (threadIdx.x / (TPC * CB)) * TPC + ta; }
   const int T1 = a.N1 / 2;
   const int nchunks = (T1 + t1_chunk - 1) / t1_chunk;
   const int tiles_b = (a.nseq + CB - 1) / CB;
   int sim = 0;
   const int chunk = blockIdx.x % nchunks;
-  long rest = blockIdx.x / nchunks;
+  const long rest = blockIdx.x / nchunks;
   const int bt = (int)(rest % tiles_b);
   if (MODE == ADV_COLS) sim = (int)(rest / tiles_b);
   const int seq = bt * CB + b;
@@ -216,7 +250,6 @@ __global__ void __launch_bounds__(CB * 2 * Geo<L>::TPC) pass2_kernel(const FastA
   const long N = a.N, N1 = a.N1;
   const double inv_n = 1.0 / (double)N;
 
-  // advection constants of the two packed channels
   double ca = 0.0, cb = 0.0;
   if (valid) {
     const long ra = 2 * (long)seq, rb = ra + 1;
@@ -225,83 +258,106 @@ __global__ void __launch_bounds__(CB * 2 * Geo<L>::TPC) pass2_kernel(const FastA
   }
   const double* K = a.kvec + (MODE == ADV_COLS ? (long)sim * N : 0);
 
+  // asynchronous load of the tile of group pair t1 into STG
+  auto prefetch = [&](int t1) {
+    const int k1g0 = (t1 == 0) ? 0 : t1, k1g1 = (t1 == 0) ? (int)(N1 / 2) : (int)(N1 - t1);
+    if (MODE == ADV_COLS) {
+      for (int w = threadIdx.x; w < 2 * L * CB; w += NT) {
+        const int bb = w % CB, l = (w / CB) % L, gg = w / (CB * L);
+        const int sq = bt * CB + bb;
+        cplx* dst = STG + LY::tidx(gg, l, bb);
+        if (sq < a.nseq)
+          cp_async16(dst, a.fout + ((long)sim * N + (long)(gg ? k1g1 : k1g0) * L + l) * a.ld_out + 2 * (long)sq);
+        else *dst = cmake(0.0, 0.0);
+      }
+    } else {
+      for (int w = threadIdx.x; w < 2 * L * CB; w += NT) {
+        const int l = w % L, bb = (w / L) % CB, gg = w / (L * CB);
+        const int sq = bt * CB + bb;
+        cplx* dst = STG + LY::tidx(gg, l, bb);
+        const long n = (long)(gg ? k1g1 : k1g0) * L + l;
+        if (sq < a.nseq) {
+          const long ra = 2 * (long)sq, rb = ra + 1;
+          cp_async8(&dst->x, a.fout + ra * a.ld_out + n);
+          if (rb < a.nrows) cp_async8(&dst->y, a.fout + rb * a.ld_out + n);
+          else dst->y = a.phantom ? a.phantom[n] : 0.0;
+        } else *dst = cmake(0.0, 0.0);
+      }
+    }
+    for (int w = threadIdx.x; w < 2 * L; w += NT) {
+      const int n2 = w % L, gg = w / L;
+      cp_async16(TWT + w, a.twN + (long)n2 * (gg ? k1g1 : k1g0));
+    }
+    cp_async_commit();
+  };
+
+  for (int w = threadIdx.x; w < L; w += NT) TWL[w] = ldg_c(a.twL2 + w);
+  const int t1_begin = chunk * t1_chunk, t1_end = min(T1, (chunk + 1) * t1_chunk);
+  prefetch(t1_begin);
+
   if (!a.exact) {
-    // phi = (K[1] dt) c ; G = exp(-i N1 phi); PT[j] = G^j = H[j>>3] * Lo[j&7], scaled by 1/(2N)
-    if (u == 0) {
-      const double k1dt = mul_rn(K[1], a.dt);
-      PHI[b] = mul_rn(k1dt, ca);
-      PHI[CB + b] = mul_rn(k1dt, cb);
+    // phi = (K[1] dt) c ; G = exp(-i N1 phi); PT[j] = G^j = H[j>>3] * Lo[j&7]
+    for (int w = threadIdx.x; w < 2 * CB; w += NT) {
+      const int ch = w / CB, bb = w % CB;
+      const int sq = bt * CB + bb;
+      double c = 0.0;
+      if (sq < a.nseq) {
+        const long rr = 2 * (long)sq + ch;
+        c = (MODE == ADV_COLS || rr < a.nrows) ? a.cvec[rr] : 0.0;
+      }
+      PHI[w] = mul_rn(mul_rn(K[1], a.dt), c);
     }
     __syncthreads();
-    // Lo[j] j = 0..7 -> PT[..][j], H[j] j = 1..HALF/8 -> PT[..][8 j]
     for (int w = threadIdx.x; w < 2 * CB * (8 + HALF / 8); w += NT) {
       const int sq = w / (8 + HALF / 8), i = w % (8 + HALF / 8);
       const int j = (i < 8) ? i : 8 * (i - 7);
       const double th = (double)N1 * PHI[sq] * (double)j;
-      double s, c;
-      sincos(th, &s, &c);
-      PT[sq * (HALF + 1) + j] = cmake(c, -s);
+      double sn, cs;
+      sincos(th, &sn, &cs);
+      PT[sq * (HALF + 1) + j] = cmake(cs, -sn);
     }
     __syncthreads();
     for (int w = threadIdx.x; w < 2 * CB * (HALF + 1); w += NT) {
       const int sq = w / (HALF + 1), j = w % (HALF + 1);
       if (j >= 8 && (j & 7)) PT[sq * (HALF + 1) + j] = cmul(PT[sq * (HALF + 1) + (j & ~7)], PT[sq * (HALF + 1) + (j & 7)]);
     }
-    __syncthreads();
   }
 
-  for (int t1 = chunk * t1_chunk; t1 < min(T1, (chunk + 1) * t1_chunk); ++t1) {
+  for (int t1 = t1_begin; t1 < t1_end; ++t1) {
     const bool self = (t1 == 0);
     const int k1g0 = self ? 0 : t1, k1g1 = self ? (int)(N1 / 2) : (int)(N1 - t1);
 #define K1G(g) ((g) ? k1g1 : k1g0)
     if (!a.exact) {
-      // base(k1) per group/channel
-      if (u < 4) {
-        const int g = u >> 1, ch = u & 1;
-        double s, c;
-        sincos((double)K1G(g) * PHI[ch * CB + b], &s, &c);
-        BASE[(g * 2 + ch) * CB + b] = cmake(c * 0.5 * inv_n, -s * 0.5 * inv_n);
+      for (int w = threadIdx.x; w < 4 * CB; w += NT) {     // base(k1) per group/channel, scaled by 1/(2N)
+        const int bb = w % CB, gc = w / CB, g = gc >> 1, ch = gc & 1;
+        double sn, cs;
+        sincos((double)K1G(g) * PHI[ch * CB + bb], &sn, &cs);
+        BASE[(g * 2 + ch) * CB + bb] = cmake(cs * 0.5 * inv_n, -sn * 0.5 * inv_n);
       }
     }
     cplx x[16];
-    // ---------------- load + step A (group gA = u / TPC, r = (u % TPC) + TPC q)
-    {
-      const int g = u / TPC, ta = u % TPC;
-      if (MODE == ADV_ROWS) {
-        // stage the tile through shared memory with lanes along the contiguous n2 axis
-        __syncthreads();
-        for (int w = threadIdx.x; w < 2 * L * CB; w += NT) {
-          const int l = w % L, bb = (w / L) % CB, gg = w / (L * CB);
-          const int sq = bt * CB + bb;
-          cplx val = cmake(0.0, 0.0);
-          if (sq < a.nseq) val = gload<MODE>(a, a.fout, a.ld_out, sim, sq, (long)K1G(gg) * L + l, false);
-          S[(gg * L + l) * PITCH + bb] = val;
-        }
-        __syncthreads();
+    const int g = u / TPC, ta = u % TPC;
+    cp_async_wait_all();
+    __syncthreads();                                   // tile t1 is in STG
+    // ---------------- step A: staged tile -> registers, four-step twiddle, radix-R1
 #pragma unroll
-        for (int q = 0; q < NA; ++q)
+    for (int q = 0; q < NA; ++q)
 #pragma unroll
-          for (int j = 0; j < R1; ++j) x[q * R1 + j] = S[(g * L + (ta + TPC * q) + 8 * j) * PITCH + b];
-        __syncthreads();
-      } else {
-#pragma unroll
-        for (int q = 0; q < NA; ++q)
-#pragma unroll
-          for (int j = 0; j < R1; ++j)
-            x[q * R1 + j] = valid ? gload<MODE>(a, a.fout, a.ld_out, sim, seq,
-                                                (long)K1G(g) * L + (ta + TPC * q) + 8 * j, false)
-                                  : cmake(0.0, 0.0);
-        __syncthreads();  // previous iteration's readers of S are done
+      for (int j = 0; j < R1; ++j) {
+        const int n2 = (ta + TPC * q) + 8 * j;
+        x[q * R1 + j] = cmul(STG[LY::tidx(g, n2, b)], TWT[g * L + n2]);
       }
+    for (int w = threadIdx.x; w < 2 * L; w += NT) TWC[w] = TWT[w];   // keep for the inverse (TWT gets the next tile's)
+    __syncthreads();                                   // STG consumed, S free (previous tile's readers done)
+    if (t1 + 1 < t1_end) prefetch(t1 + 1);
 #pragma unroll
-      for (int q = 0; q < NA; ++q) {
-        const int r = ta + TPC * q;
-        fftR<R1, -1>(x + q * R1);
+    for (int q = 0; q < NA; ++q) {
+      const int r = ta + TPC * q;
+      fftR<R1, -1>(x + q * R1);
 #pragma unroll
-        for (int m = 1; m < R1; ++m) x[q * R1 + m] = cmul(x[q * R1 + m], ldg_c(a.twL2 + r * m));
+      for (int m = 1; m < R1; ++m) x[q * R1 + m] = cmul(x[q * R1 + m], TWL[r * m]);
 #pragma unroll
-        for (int m = 0; m < R1; ++m) S[(g * L + m * 8 + r) * PITCH + b] = x[q * R1 + m];
-      }
+      for (int m = 0; m < R1; ++m) S[LY::sidx(g, m, r, b)] = x[q * R1 + m];
     }
     __syncthreads();
     // ---------------- step B: sub-transforms (gA, mA) in x[0..7], (gB, mB) in x[8..15]
@@ -318,14 +374,14 @@ __global__ void __launch_bounds__(CB * 2 * Geo<L>::TPC) pass2_kernel(const FastA
     }
 #pragma unroll
     for (int r = 0; r < 8; ++r) {
-      x[r] = S[(gA * L + mA * 8 + r) * PITCH + b];
-      x[8 + r] = S[(gB * L + mB * 8 + r) * PITCH + b];
+      x[r] = S[LY::sidx(gA, mA, r, b)];
+      x[8 + r] = S[LY::sidx(gB, mB, r, b)];
     }
     fft8<-1>(x);
     fft8<-1>(x + 8);
     // ---------------- pointwise: pairs (Z at bin k, Zp at bin N - k), both in this thread
     {
-      const long k1A = self ? (gA ? N1 / 2 : 0) : (gA ? N1 - t1 : t1);
+      const long k1A = K1G(gA);
       auto pair_op = [&](cplx& Zr, cplx& Zpr, const long kbin, const long k1, const int gsel, const bool selfpair) {
         const bool neg = (2 * kbin > N);
         const bool nyq = (2 * kbin == N);
@@ -333,11 +389,11 @@ __global__ void __launch_bounds__(CB * 2 * Geo<L>::TPC) pass2_kernel(const FastA
         if (a.exact) {
           const long kr = neg ? N - kbin : kbin;
           const double kdt = mul_rn(K[kr], a.dt);
-          double s, c;
-          sincos(mul_rn(kdt, ca), &s, &c);
-          Pa = cmake(c * 0.5 * inv_n, (nyq ? 0.0 : (neg ? s : -s)) * 0.5 * inv_n);
-          sincos(mul_rn(kdt, cb), &s, &c);
-          Pb = cmake(c * 0.5 * inv_n, (nyq ? 0.0 : (neg ? s : -s)) * 0.5 * inv_n);
+          double sn, cs;
+          sincos(mul_rn(kdt, ca), &sn, &cs);
+          Pa = cmake(cs * 0.5 * inv_n, (nyq ? 0.0 : (neg ? sn : -sn)) * 0.5 * inv_n);
+          sincos(mul_rn(kdt, cb), &sn, &cs);
+          Pb = cmake(cs * 0.5 * inv_n, (nyq ? 0.0 : (neg ? sn : -sn)) * 0.5 * inv_n);
         } else {
           const int k2 = (int)((kbin - k1) / N1);           // 0..L-1
           const int j = neg ? (L - k2) : k2;                // |signed k2| in 0..HALF
@@ -374,58 +430,34 @@ __global__ void __launch_bounds__(CB * 2 * Geo<L>::TPC) pass2_kernel(const FastA
 #pragma unroll
     for (int r = 0; r < 8; ++r) {
       cplx va = x[r], vb = x[8 + r];
-      if (r * mA != 0) va = cmulc(va, ldg_c(a.twL2 + r * mA));
-      if (r * mB != 0) vb = cmulc(vb, ldg_c(a.twL2 + r * mB));
-      S[(gA * L + mA * 8 + r) * PITCH + b] = va;
-      S[(gB * L + mB * 8 + r) * PITCH + b] = vb;
+      va = cmulc(va, TWL[r * mA]);
+      vb = cmulc(vb, TWL[r * mB]);
+      S[LY::sidx(gA, mA, r, b)] = va;
+      S[LY::sidx(gB, mB, r, b)] = vb;
     }
     __syncthreads();
     // ---------------- step A': inverse radix-R1, conj four-step twiddle, store
-    {
-      const int g = u / TPC, ta = u % TPC;
 #pragma unroll
-      for (int q = 0; q < NA; ++q) {
-        const int r = ta + TPC * q;
+    for (int q = 0; q < NA; ++q) {
+      const int r = ta + TPC * q;
 #pragma unroll
-        for (int m = 0; m < R1; ++m) x[q * R1 + m] = S[(g * L + m * 8 + r) * PITCH + b];
-        fftR<R1, 1>(x + q * R1);
+      for (int m = 0; m < R1; ++m) x[q * R1 + m] = S[LY::sidx(g, m, r, b)];
+      fftR<R1, 1>(x + q * R1);
 #pragma unroll
-        for (int j = 0; j < R1; ++j) {
-          const int n2 = r + 8 * j;
-          cplx val = x[q * R1 + j];
-          const long tw = (long)n2 * K1G(g);
-          if (tw != 0) val = cmulc(val, ldg_c(a.twN + tw));
-          x[q * R1 + j] = val;
-        }
-      }
-      if (MODE == ADV_ROWS) {
-        __syncthreads();
-#pragma unroll
-        for (int q = 0; q < NA; ++q)
-#pragma unroll
-          for (int j = 0; j < R1; ++j) S[(g * L + (ta + TPC * q) + 8 * j) * PITCH + b] = x[q * R1 + j];
-        __syncthreads();
-        for (int w = threadIdx.x; w < 2 * L * CB; w += NT) {
-          const int l = w % L, bb = (w / L) % CB, gg = w / (L * CB);
-          const int sq = bt * CB + bb;
-          if (sq < a.nseq) gstore<MODE>(a, sim, sq, (long)K1G(gg) * L + l, S[(gg * L + l) * PITCH + bb], false);
-        }
-      } else if (valid) {
-#pragma unroll
-        for (int q = 0; q < NA; ++q)
-#pragma unroll
-          for (int j = 0; j < R1; ++j)
-            gstore<MODE>(a, sim, seq, (long)K1G(g) * L + (ta + TPC * q) + 8 * j, x[q * R1 + j], false);
+      for (int j = 0; j < R1; ++j) {
+        const int n2 = r + 8 * j;
+        const cplx val = cmulc(x[q * R1 + j], TWC[g * L + n2]);
+        if (valid) gstore<MODE>(a, sim, seq, (long)K1G(g) * L + n2, val, false);
       }
     }
+#undef K1G
   }
 }
 
-#undef K1G
-
 template <int L, int CB>
 constexpr size_t pass2_smem(int mode) {
-  return sizeof(cplx) * (size_t)(2 * L * ((mode == ADV_ROWS) ? CB + 1 : CB) + 2 * CB * (L / 2 + 1) + 4 * CB) +
+  return sizeof(cplx) * (size_t)(((mode == ADV_ROWS) ? CB * 2 * (L / 8) * 9 : 2 * L * CB) + 2 * L * CB +
+                                 2 * CB * (L / 2 + 1) + 4 * CB + 5 * L) +
          sizeof(double) * 2 * CB;
 }
 

@@ -5,8 +5,9 @@
 //
 //  * the row sits in shared memory with one padding word per chunk, so both the coalesced
 //    row-order accesses and the per-thread chunk sweeps (stride M+1 doubles) are conflict free;
-//  * the LU pivots 1/p_i of a thread's chunk stay in registers between the reduction sweep and the
-//    back-substitution: one reciprocal per element per sweep direction, none in the final solve;
+//  * the reduction sweeps keep only running scalars; the back-substitution keeps the pivots of
+//    the upper half of a thread's chunk in registers and recomputes the lower half's;
+//    reciprocals of consecutive pivots are refined from one another by two Newton steps;
 //  * diagonals are affine in the cell index (the velocity grid is np.linspace: v_i = v0 + i*step,
 //    checked bit-for-bit on the host before this kernel is chosen): A_i = a0 + a1 i,
 //    C_i = c0 + c1 i, one FMA each, nothing is loaded;
@@ -46,10 +47,25 @@ __device__ __forceinline__ double block_sum(double x, double* red) {
   return warp_sum(y);
 }
 
+// reciprocal of p given the reciprocal r of a nearby value (the pivots of a diagonally dominant
+// tridiagonal matrix with slowly varying coefficients converge geometrically): two Newton steps
+// when the first residual is below 2^-14 (then the result is good to < 1 ulp), else a division.
+__device__ __forceinline__ double rcp_near(double p, double r) {
+  const double e = fma(-p, r, 1.0);
+  if (fabs(e) < 6.0e-5) {
+    const double r1 = fma(r, e, r);
+    const double e1 = fma(-p, r1, 1.0);
+    return fma(r1, e1, r1);
+  }
+  return 1.0 / p;
+}
+
 template <int M, int T>
 __global__ void __launch_bounds__(T, 1) fp_kernel(const Args a) {
   constexpr int NV = M * T;
   constexpr int NW = T / 32;
+  constexpr int MI = M - 1;          // interior cells of a chunk
+  constexpr int H = MI / 2;          // pivots of cells [H, MI) are kept, [0, H) are recomputed
   extern __shared__ __align__(16) unsigned char smem_raw[];
   double* row = reinterpret_cast<double*>(smem_raw);  // NV + T (one pad per chunk)
   double* red = row + NV + T;                          // 64
@@ -57,95 +73,108 @@ __global__ void __launch_bounds__(T, 1) fp_kernel(const Args a) {
   const int t = threadIdx.x;
   const int lane = t & 31, warp = t >> 5;
   auto sk = [](int i) { return i + i / M; };           // skewed index
-  auto vel = [&](int i) { return (i == NV - 1) ? a.vlast : __dadd_rn(a.v0, __dmul_rn((double)i, a.vstep)); };
-  auto wgt = [&](int i) { return (i == 0 || i == NV - 1) ? 0.5 * a.dv : a.dv; };
+  // velocity of cell t + k*T (row-order loops) -- affine in k; the reference grid is np.linspace
+  const double vt = fma((double)t, a.vstep, a.v0);
+  const double hdv = 0.5 * a.dv;
 
   for (long r = blockIdx.x; r < a.rows; r += gridDim.x) {
     // ---------------- load + first moment
     const double* src = a.fin + r * a.ld_in;
     double acc0 = 0.0;
-#pragma unroll 4
-    for (int k = 0; k < M; ++k) {
-      const int i = t + k * T;
-      const double fv = src[i];
-      row[sk(i)] = fv;
-      const double vi = vel(i);
-      acc0 += (a.op == 0) ? wgt(i) * fv * vi * vi : wgt(i) * fv * vi;
+    const double vinc = (double)T * a.vstep;
+    {
+      double vi = vt;
+#pragma unroll 8
+      for (int k = 0; k < M; ++k) {
+        const int i = t + k * T;
+        const double fv = src[i];
+        row[sk(i)] = fv;
+        const double w = ((k == 0 && t == 0) || (k == M - 1 && t == T - 1)) ? hdv : a.dv;
+        acc0 += (a.op == 0) ? w * fv * vi * vi : w * fv * vi;
+        vi += vinc;
+      }
     }
     const double first = block_sum<T>(acc0, red);   // (contains the syncs that publish `row`)
     double Tm = first, vbar = 0.0;
     if (a.op == 1) {
       vbar = first;
       double acc1 = 0.0;
-#pragma unroll 4
+      double vi = vt;
+#pragma unroll 8
       for (int k = 0; k < M; ++k) {
         const int i = t + k * T;
-        const double d = vel(i) - vbar;
-        acc1 += wgt(i) * row[sk(i)] * d * d;
+        const double d = vi - vbar;
+        const double w = ((k == 0 && t == 0) || (k == M - 1 && t == T - 1)) ? hdv : a.dv;
+        acc1 += w * row[sk(i)] * d * d;
+        vi += vinc;
       }
       Tm = block_sum<T>(acc1, red);
     }
-    // diagonals: A_i = nudt(tdv + (v_{i-1} - vbar)/2/dv), C_i = nudt(tdv - (v_{i+1} - vbar)/2/dv)
+    // diagonals, affine in the cell index i:
+    //   A_i = nudt(tdv + (v_{i-1} - vbar)/2/dv) = A0 + i dA,  C_i = nudt(tdv - (v_{i+1} - vbar)/2/dv) = C0 - i dA
     const double nudt = a.nu * a.dt;
     const double tdv = -Tm / (a.dv * a.dv);
     const double bd = 1.0 + nudt * (2.0 * Tm / (a.dv * a.dv));
+    const double rbd = 1.0 / bd;
     const double hb = nudt / (2.0 * a.dv);
-    auto cA = [&](int i) { return nudt * tdv + hb * (vel(i - 1) - vbar); };
-    auto cC = [&](int i) { return nudt * tdv - hb * (vel(i + 1) - vbar); };
-
-    // ---------------- chunk interior [s, e-1], separator e
+    const double dA = hb * a.vstep;
     const int s = t * M, e = s + M - 1;
-    double rpv[M];                    // LU pivots' reciprocals of the interior
+    const double As0 = fma(hb, fma((double)(s - 1), a.vstep, a.v0) - vbar, nudt * tdv);   // A_s
+    const double Cs0 = fma(-hb, fma((double)(s + 1), a.vstep, a.v0) - vbar, nudt * tdv);  // C_s
+#define CA(i) fma(dA, (double)(i), As0)       /* A_{s+i} */
+#define CC(i) fma(-dA, (double)(i), Cs0)      /* C_{s+i} */
+
+    // ---------------- chunk interior [s, e-1] -> six spike end values (no per-cell storage)
     double u_first, u_last, w_first, w_last, y_first, y_last;
     {
-      // UL sweep up (reads the untouched right-hand side)
-      double rq = 1.0 / bd, tt = row[sk(e - 1)], h = 1.0;
-#pragma unroll
-      for (int i = M - 3; i >= 0; --i) {
-        const double rr = cC(s + i) * rq;
-        rq = 1.0 / (bd - rr * cA(s + i + 1));
-        tt = row[sk(s + i)] - rr * tt;
-        h = -rr * h;
+      double rq = rbd, tt = row[sk(e - 1)], h = 1.0;      // UL sweep up
+      {
+        double cc = CC(MI - 2), ca = CA(MI - 1);          // C_{s+i}, A_{s+i+1}, running down in i
+#pragma unroll 4
+        for (int i = MI - 2; i >= 0; --i) {
+          const double rr = cc * rq;
+          rq = rcp_near(fma(-rr, ca, bd), rq);
+          tt = fma(-rr, tt, row[sk(s + i)]);
+          h = -rr * h;
+          cc += dA; ca -= dA;
+        }
       }
       u_first = rq; w_first = h * rq; y_first = tt * rq;
-      // LU sweep down
-      double rp = 1.0 / bd, z = row[sk(s)], g = 1.0;
-      rpv[0] = rp;
-#pragma unroll
-      for (int i = 1; i <= M - 2; ++i) {
-        const double l = cA(s + i) * rp;
-        rp = 1.0 / (bd - l * cC(s + i - 1));
-        z = row[sk(s + i)] - l * z;
-        g = -l * g;
-        rpv[i] = rp;
+      double rp = rbd, z = row[sk(s)], g = 1.0;           // LU sweep down
+      {
+        double ca = CA(1), cc = CC(0);                    // A_{s+i}, C_{s+i-1}, running up in i
+#pragma unroll 4
+        for (int i = 1; i <= MI - 1; ++i) {
+          const double l = ca * rp;
+          rp = rcp_near(fma(-l, cc, bd), rp);
+          z = fma(-l, z, row[sk(s + i)]);
+          g = -l * g;
+          ca += dA; cc -= dA;
+        }
       }
       y_last = z * rp; w_last = rp; u_last = g * rp;
     }
     // ---------------- separator equation of this chunk (needs the next chunk's first-spikes)
-    const double As = (t > 0) ? cA(s) : 0.0;
-    const double Ce1 = cC(e - 1);
-    const double Ae = cA(e);
-    const double Ce = (t < T - 1) ? cC(e) : 0.0;
-    // neighbour chunk j+1: u_first, w_first, y_first, and its As, Ce1
+    const double As = (t > 0) ? CA(0) : 0.0;
+    const double Ce1 = CC(MI - 1);
+    const double Ae = CA(MI);
+    const double Ce = (t < T - 1) ? CC(MI) : 0.0;
     __syncthreads();
     X[t] = u_first; X[T + t] = w_first; X[2 * T + t] = y_first;
     __syncthreads();
     double ra, rb, rc, rd;
     {
-      const double As2 = cA(s + M);                    // A of next chunk's first row (= cA(e+1))
-      const double Ce12 = cC(e + M - 1);               // C of next chunk's last interior row
       ra = -Ae * As * u_last;
-      rb = bd - Ae * Ce1 * w_last;
+      rb = fma(-Ae * Ce1, w_last, bd);
       rc = 0.0;
-      rd = row[sk(e)] - Ae * y_last;
+      rd = fma(-Ae, y_last, row[sk(e)]);
       if (t < T - 1) {
-        rb -= Ce * As2 * X[t + 1];
-        rc = -Ce * Ce12 * X[T + t + 1];
-        rd -= Ce * X[2 * T + t + 1];
+        rb = fma(-Ce * CA(M), X[t + 1], rb);              // A of the next chunk's first row
+        rc = -Ce * CC(M + MI - 1) * X[T + t + 1];         // C of the next chunk's last interior row
+        rd = fma(-Ce, X[2 * T + t + 1], rd);
       }
     }
-    // ---------------- cyclic reduction over the T separators
-    // Shared-memory PCR (all steps): ping-pong between X[0,4T) and X[4T,8T)
+    // ---------------- cyclic reduction over the T separators (shared memory ping-pong)
     {
       double* cur = X;
       double* nxt = X + 4 * T;
@@ -160,14 +189,14 @@ __global__ void __launch_bounds__(T, 1) fp_kernel(const Args a) {
         if (im >= 0) {
           const double al = -a_ / cur[T + im];
           na = al * cur[im];
-          nb += al * cur[2 * T + im];
-          nd += al * cur[3 * T + im];
+          nb = fma(al, cur[2 * T + im], nb);
+          nd = fma(al, cur[3 * T + im], nd);
         }
         if (ip < T) {
           const double ga = -c_ / cur[T + ip];
           nc = ga * cur[2 * T + ip];
-          nb += ga * cur[ip];
-          nd += ga * cur[3 * T + ip];
+          nb = fma(ga, cur[ip], nb);
+          nd = fma(ga, cur[3 * T + ip], nd);
         }
         nxt[t] = na; nxt[T + t] = nb; nxt[2 * T + t] = nc; nxt[3 * T + t] = nd;
         __syncthreads();
@@ -178,30 +207,56 @@ __global__ void __launch_bounds__(T, 1) fp_kernel(const Args a) {
       X[t] = xe;
       __syncthreads();
     }
-    // ---------------- interior with known neighbours, in place
+    // ---------------- interior with known neighbours, in place.  Pivots of the upper half of the
+    // chunk are kept in registers during the sweep down; the lower half's are recomputed.
     {
       const double xe = X[t];
       const double xl = (t > 0) ? X[t - 1] : 0.0;
-      double z = row[sk(s)] - As * xl;
-      if (M == 2) z -= Ce1 * xe;
+      double rpv[MI - H];
+      double z = fma(-As, xl, row[sk(s)]);
+      if (MI == 1) z = fma(-Ce1, xe, z);
       row[sk(s)] = z;
+      double rp = rbd;
+      if (H == 0) rpv[0] = rp;
 #pragma unroll
-      for (int i = 1; i <= M - 2; ++i) {
-        const double l = cA(s + i) * rpv[i - 1];
+      for (int i = 1; i <= MI - 1; ++i) {
+        const double l = CA(i) * rp;
+        rp = rcp_near(fma(-l, CC(i - 1), bd), rp);
         double di = row[sk(s + i)];
-        if (i == M - 2) di -= Ce1 * xe;
-        z = di - l * z;
+        if (i == MI - 1) di = fma(-Ce1, xe, di);
+        z = fma(-l, z, di);
         row[sk(s + i)] = z;
+        if (i >= H) rpv[i - H] = rp;
+        if ((i & 3) == 3) asm volatile("" ::: "memory");
       }
-      double x = z * rpv[M - 2];
-      row[sk(e - 1)] = x;
+      double x = z * rp;
+      row[sk(s + MI - 1)] = x;
 #pragma unroll
-      for (int i = M - 3; i >= 0; --i) {
-        x = (row[sk(s + i)] - cC(s + i) * x) * rpv[i];
+      for (int i = MI - 2; i >= H; --i) {
+        x = fma(-CC(i), x, row[sk(s + i)]) * rpv[i - H];
         row[sk(s + i)] = x;
+        if ((i & 3) == 0) asm volatile("" ::: "memory");
+      }
+      if (H > 0) {
+        rp = rbd;
+        rpv[0] = rp;
+#pragma unroll
+        for (int i = 1; i <= H - 1; ++i) {
+          const double l = CA(i) * rp;
+          rp = rcp_near(fma(-l, CC(i - 1), bd), rp);
+          rpv[i] = rp;
+        }
+#pragma unroll
+        for (int i = H - 1; i >= 0; --i) {
+          x = fma(-CC(i), x, row[sk(s + i)]) * rpv[i];
+          row[sk(s + i)] = x;
+          if ((i & 3) == 0) asm volatile("" ::: "memory");
+        }
       }
       row[sk(e)] = xe;
     }
+#undef CA
+#undef CC
     __syncthreads();
     // ---------------- store + moments of the new row
     double* dst = a.fout + r * a.ld_out;
@@ -209,21 +264,22 @@ __global__ void __launch_bounds__(T, 1) fp_kernel(const Args a) {
       double acc[8];
 #pragma unroll
       for (int k = 0; k < 8; ++k) acc[k] = 0.0;
-#pragma unroll 2
-      for (int k = 0; k < M; ++k) {
+      double vi = vt;
+#pragma unroll 4
+      for (int k = 0; k < M; ++k, vi += vinc) {
         const int i = t + k * T;
         const double x = row[sk(i)];
         dst[i] = x;
-        const double vi = vel(i);
-        const double tw = wgt(i) * x;
+        const double w = ((k == 0 && t == 0) || (k == M - 1 && t == T - 1)) ? hdv : a.dv;
+        const double tw = w * x;
         acc[0] += tw;
         double p = tw * vi; acc[1] += p;
         p *= vi; acc[2] += p;
         p *= vi; acc[3] += p;
         p *= vi; acc[4] += p;
         p *= vi; acc[5] += p;
-        acc[6] += tw * x;
-        acc[7] += tw * log(x);
+        acc[6] = fma(tw, x, acc[6]);
+        acc[7] = fma(tw, log(x), acc[7]);
       }
 #pragma unroll
       for (int k = 0; k < 8; ++k) acc[k] = warp_sum(acc[k]);
@@ -238,7 +294,7 @@ __global__ void __launch_bounds__(T, 1) fp_kernel(const Args a) {
         if (lane == 0) a.mom_out[(long)k * a.mom_ld + r] = y;
       }
     } else {
-#pragma unroll 4
+#pragma unroll 8
       for (int k = 0; k < M; ++k) {
         const int i = t + k * T;
         dst[i] = row[sk(i)];
