@@ -103,6 +103,11 @@ int vpfp_fp_step_linspace(const double *f_in, long ld_in, double *f_out, long ld
 int vpfp_xmodes(const double *f, long ld, double *out, int nmodes, int batch, int nx, int ncols,
                 void *stream);
 
+/* The same sums over a slab of rows x_offset .. x_offset+nx-1 of a grid of nx_total cells
+ * (x-sharded multi-GPU layout); the partial results of all slabs add up to vpfp_xmodes. */
+int vpfp_xmodes_partial(const double *f, long ld, double *out, int nmodes, int batch, int nx,
+                        int ncols, int x_offset, int nx_total, void *stream);
+
 /* Ponderomotive driver E_d(x, t) summed over npulse pulses (vlapy/field_driver.py:24-50).
  * pulses: host array of 7 doubles per pulse {k0, w0, a0, t_L, t_R, t_wL, t_wR}. x, out: device. */
 int vpfp_driver(const double *x, double t, const double *pulses, int npulse, double *out, int nx,

@@ -137,6 +137,7 @@ int emul_fp_step(const double* f_in, long ld_in, double* f_out, long ld_out, con
 int emul_xmodes(const double* f, long ld, double* out, int nmodes, int batch, int nx, int ncols) {
   XmodesProg p;
   p.f = f; p.ld = ld; p.nmodes = nmodes; p.batch = batch; p.nx = nx; p.ncols = ncols;
+  p.x_offset = 0; p.nx_total = nx;
   const int threads = 128;
   p.cblocks = (ncols + threads - 1) / threads;
   int xch = nx / 64;

@@ -1,0 +1,65 @@
+"""Multi-GPU parity (-m gpu, needs >= 2 devices): the x/v-sharded step over NCCL against the
+reference output of the single-process run (golden nlepw_c2: C2, 40 collisional steps)."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+torch = pytest.importorskip("torch")
+import torch.distributed as dist  # noqa: E402
+import torch.multiprocessing as mp  # noqa: E402
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+pytestmark = pytest.mark.gpu
+
+
+def _worker(rank, world, port, op, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        from oracle import vpfp_oracle as O
+        from vlapy_b200 import dist as vd
+        cfg = O.nlepw_config()
+        topo = vd.Topology(cfg["nx"], cfg["nv"])
+        params = {"nu": cfg["nu"], "vlasov-poisson": {"time": "leapfrog"}, "fokker-planck": {"type": op}}
+        stuff = {k: cfg[k] for k in ("kx", "x", "one_over_kx", "v", "kv", "nv", "nx", "dv", "dt", "nu")}
+        stuff.update(pulse_dictionary=cfg["pulses"], driver_function=cfg["driver_function"])
+        step = vd.get_sharded_timestep(params, stuff, topo)
+        dev = torch.device("cuda", rank)
+        f0 = torch.from_numpy(cfg["f0"][topo.x0: topo.x0 + topo.nxl].copy()).to(dev)
+        state = {"e": torch.from_numpy(cfg["e0"].copy()).to(dev), "f": vd.Sharded(f0, "x")}
+        store = vd.make_store(topo, step.backend, 40)
+        for i in range(40):
+            t = cfg["dt"] * i
+            state = step(state, t, step.backend.driver(t), store)
+        series, modes = vd.finish_store(topo, store)
+        fx = vd.ops_to_x(state["f"], topo)
+        q.put((rank, fx.cpu().numpy(), state["e"].cpu().numpy(), series.cpu().numpy()))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 4])
+def test_sharded_c2_matches_reference(world):
+    if not torch.cuda.is_available() or torch.cuda.device_count() < world:
+        pytest.skip("needs %d GPUs" % world)
+    g = np.load(os.path.join(ROOT, "tests", "golden", "nlepw_c2.npz"))
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker, args=(r, world, 29620 + world, "lb", q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    outs = sorted([q.get(timeout=600) for _ in range(world)], key=lambda o: o[0])
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    f = np.concatenate([o[1] for o in outs], axis=0)
+    e = outs[0][2]
+    assert np.max(np.abs(e - g["e_lb"])) / np.max(np.abs(g["e_lb"])) < 1e-11
+    assert np.max(np.abs(f[::8, ::16] - g["f_sub_lb"])) / np.max(np.abs(g["f_sub_lb"])) < 1e-12
+    assert abs(f.sum() / float(g["f_sum_lb"]) - 1) < 1e-13
+    assert abs(outs[0][3][-1, 0] - 1.0) < 1e-12          # mean density after the all-reduce

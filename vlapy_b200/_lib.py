@@ -51,6 +51,7 @@ _SIGS = {
     "vpfp_fp_step": ([_P, _L, _P, _L, _P, _D, _D, _D, _I, _P, _L, _I, _I, _P], _I),
     "vpfp_fp_step_linspace": ([_P, _L, _P, _L, _D, _D, _D, _D, _D, _D, _I, _P, _L, _I, _I, _P], _I),
     "vpfp_xmodes": ([_P, _L, _P, _I, _I, _I, _I, _P], _I),
+    "vpfp_xmodes_partial": ([_P, _L, _P, _I, _I, _I, _I, _I, _I, _P], _I),
     "vpfp_driver": ([_P, _D, _P, _I, _P, _I, _P], _I),
     "vpfp_series": ([_P, _L, _P, _P, _P, _I, _P], _I),
 }

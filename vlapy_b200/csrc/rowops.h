@@ -368,6 +368,7 @@ struct XmodesProg {
   long ld;
   double* partial;  // [batch][xchunks][nmodes][ncols][2]
   int nmodes, batch, nx, ncols, xchunks, cblocks;
+  int x_offset, nx_total;  // rows are cells x_offset .. x_offset+nx-1 of a grid of nx_total (x-sharding)
 
   VPFP_HD int nphases() const { return 1; }
   VPFP_HD void phase(int, long blk, int tid, int nthr, unsigned char*) const {
@@ -379,11 +380,11 @@ struct XmodesProg {
     if (j >= ncols) return;
     int x0 = (int)((long)nx * xc / xchunks), x1 = (int)((long)nx * (xc + 1) / xchunks);
     for (int mth = 0; mth < nmodes; ++mth) {
-      const double ang = -2.0 * 3.14159265358979323846 * (double)mth / (double)nx;
+      const double ang = -2.0 * 3.14159265358979323846 * (double)mth / (double)nx_total;
       double sr = 0.0, si = 0.0;
       double wr = 1.0, wi = 0.0, cr = 1.0, ci = 0.0;
       if (mth > 0) {
-        sincos_hd(ang * x0, &wi, &wr);
+        sincos_hd(ang * (double)(x0 + x_offset), &wi, &wr);
         sincos_hd(ang, &ci, &cr);
       }
       for (int x = x0; x < x1; ++x) {

@@ -496,12 +496,21 @@ int vpfp_fp_step_linspace(const double* f_in, long ld_in, double* f_out, long ld
   }
 }
 
+int vpfp_xmodes_partial(const double* f, long ld, double* out, int nmodes, int batch, int nx, int ncols,
+                        int x_offset, int nx_total, void* stream);
+
 int vpfp_xmodes(const double* f, long ld, double* out, int nmodes, int batch, int nx, int ncols,
                 void* stream) {
-  if (!f || !out || nmodes < 1 || batch <= 0 || nx <= 0 || ncols <= 0)
+  return vpfp_xmodes_partial(f, ld, out, nmodes, batch, nx, ncols, 0, nx, stream);
+}
+
+int vpfp_xmodes_partial(const double* f, long ld, double* out, int nmodes, int batch, int nx, int ncols,
+                        int x_offset, int nx_total, void* stream) {
+  if (!f || !out || nmodes < 1 || batch <= 0 || nx <= 0 || ncols <= 0 || nx_total < nx || x_offset < 0)
     return fail(VPFP_ERR_ARG, "vpfp_xmodes: bad argument");
   XmodesProg p;
   p.f = f; p.ld = ld; p.nmodes = nmodes; p.batch = batch; p.nx = nx; p.ncols = ncols;
+  p.x_offset = x_offset; p.nx_total = nx_total;
   const int threads = 128;
   p.cblocks = (ncols + threads - 1) / threads;
   int xch = nx / 64;

@@ -1,0 +1,292 @@
+"""Multi-GPU VPFP step: one process per GPU, f sharded along x for the row operators and along v
+for the x-advection, torch.distributed all-to-all transposes between the two layouts.
+
+The reference is single-process; this is the sharding of SURVEY 8(e):
+
+    e df/dv, Fokker-Planck, v-moments   act on rows     -> x-sharded  f_x: (nx/P, nv)
+    v df/dx                             acts on columns -> v-sharded  f_v: (nx, nv/P)
+    density                             partial int over the local v-slice + all-reduce of nx doubles
+    Poisson                             solved redundantly on every rank (nx values)
+
+The orchestration is independent of where the operators run: ``backend`` supplies the per-shard
+operators (``DeviceBackend`` = the CUDA kernels of this package; the CPU tests plug the oracle in
+over gloo).  The operator closures built here accept and return ``Sharded`` handles, so the
+schedule mirrors of ``vlapy_b200.core.vlasov_poisson`` compose them unchanged.
+"""
+import numpy as np
+import torch
+import torch.distributed as dist
+
+
+class Sharded:
+    """A shard of f together with its layout: 'x' = rows [r*nx/P, (r+1)*nx/P) x all v,
+    'v' = all x  x  columns [r*nv/P, (r+1)*nv/P)."""
+    __slots__ = ("t", "layout")
+
+    def __init__(self, t, layout):
+        self.t, self.layout = t, layout
+
+
+class Topology:
+    def __init__(self, nx, nv, rank=None, world=None, group=None):
+        self.group = group
+        self.rank = dist.get_rank(group) if rank is None else rank
+        self.world = dist.get_world_size(group) if world is None else world
+        P = self.world
+        if nx % P or nv % P or (nv // P) % 2:
+            raise NotImplementedError("sharding needs nx and nv divisible by the number of ranks "
+                                      "(and an even number of v-columns per rank)")
+        self.nx, self.nv, self.nxl, self.nvl = nx, nv, nx // P, nv // P
+        self.x0, self.v0 = self.rank * self.nxl, self.rank * self.nvl
+
+    # ---- layout changes -------------------------------------------------------------------
+    def x_to_v(self, fx):
+        """(nx/P, nv) -> (nx, nv/P): rank r sends its rows of column block q to rank q."""
+        P, nxl, nvl = self.world, self.nxl, self.nvl
+        if P == 1:
+            return fx
+        send = fx.view(nxl, P, nvl).permute(1, 0, 2).contiguous()          # block q first
+        recv = torch.empty_like(send)
+        dist.all_to_all_single(recv, send, group=self.group)
+        return recv.view(P * nxl, nvl)                                      # blocks arrive ordered by source rank = x order
+
+    def v_to_x(self, fv):
+        """(nx, nv/P) -> (nx/P, nv): the row blocks of a v-shard are already contiguous."""
+        P, nxl, nvl = self.world, self.nxl, self.nvl
+        if P == 1:
+            return fv
+        send = fv.contiguous().view(P, nxl, nvl)
+        recv = torch.empty_like(send)
+        dist.all_to_all_single(recv, send, group=self.group)
+        return recv.permute(1, 0, 2).reshape(nxl, P * nvl)
+
+    def all_reduce_sum(self, t):
+        if self.world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group)
+        return t
+
+
+class DeviceBackend:
+    """Per-shard operators on the CUDA kernels (vlapy_b200.ops)."""
+
+    def __init__(self, topo, stuff, fp_type):
+        from . import ops
+        from ._util import const
+        from .core.vlasov import _phase_flags
+        self.ops, self.topo = ops, topo
+        s = stuff
+        self.kx, self.kv = const(s["kx"]), const(s["kv"])
+        self.v = const(s["v"])
+        self.v_loc = self.v[topo.v0: topo.v0 + topo.nvl].contiguous()
+        self.ook = const(s["one_over_kx"])
+        self.x = const(s["x"])
+        self.dv, self.dt, self.nu = float(s["dv"]), float(s["dt"]), float(s["nu"])
+        self.fp_type = fp_type
+        self.flags_x, self.flags_v = _phase_flags(s["kx"]), _phase_flags(s["kv"])
+        self.vgrid = ops.linspace_params(s["v"])
+        self.pulses = ops.pulses_to_array(s["pulse_dictionary"]) if s.get("pulse_dictionary") else None
+        self.driver_host = s.get("driver_function")
+        self.edge = (1 if topo.rank == 0 else 0) | (2 if topo.rank == topo.world - 1 else 0)
+
+    def edfdv(self, fx, e_loc, dt):
+        return self.ops.edfdv_exp(fx, e_loc, self.kv, dt, flags=self.flags_v)
+
+    def vdfdx(self, fv, dt):
+        return self.ops.vdfdx_exp(fv, self.kx, self.v_loc, dt, flags=self.flags_x)
+
+    def density_partial(self, fv):
+        return self.ops.moments(fv, self.v_loc, self.dv, nmom=1, edge_flags=self.edge)[0].contiguous()
+
+    def poisson(self, n, driver):
+        return self.ops.poisson(n, self.ook, driver)
+
+    def fp(self, fx, moments_out):
+        return self.ops.fp_step(fx, self.v, self.nu, self.dt, self.dv, self.fp_type, moments_out=moments_out,
+                                vgrid=self.vgrid)
+
+    def moments(self, fx, out):
+        return self.ops.moments(fx, self.v, self.dv, nmom=8, out=out)
+
+    def driver(self, t):
+        if self.pulses is not None:
+            return self.ops.driver(self.x, t, self.pulses)
+        return torch.as_tensor(np.asarray(self.driver_host(t))).to(self.x.device)
+
+    def xmodes_partial(self, fx, nmodes):
+        m = self.ops.xmodes(fx, nmodes, x_offset=self.topo.x0, nx_total=self.topo.nx)[0]
+        return torch.view_as_real(m).contiguous()
+
+    def zeros(self, shape):
+        return torch.zeros(shape, dtype=torch.float64, device=self.x.device)
+
+
+def make_sharded_operators(topo, backend):
+    """vdfdx / edfdv / field_solve / fp closures on Sharded handles (same call signatures as
+    vlapy/core/vlasov.py, field.py, step.py closures)."""
+
+    def to_x(f):
+        return f if f.layout == "x" else Sharded(topo.v_to_x(f.t), "x")
+
+    def to_v(f):
+        return f if f.layout == "v" else Sharded(topo.x_to_v(f.t), "v")
+
+    def vdfdx(f, dt):
+        return Sharded(backend.vdfdx(to_v(f).t, dt), "v")
+
+    def edfdv(f, e, dt):
+        e_loc = e[topo.x0: topo.x0 + topo.nxl].contiguous()
+        return Sharded(backend.edfdv(to_x(f).t, e_loc, dt), "x")
+
+    def field_solve(driver_field, f):
+        # density of a v-shard: partial integral over the local columns, then a sum over ranks
+        n = topo.all_reduce_sum(backend.density_partial(to_v(f).t))
+        return backend.poisson(n, driver_field)
+
+    def fp_step(f, moments_out=None):
+        return Sharded(backend.fp(to_x(f).t, moments_out), "x")
+
+    return dict(vdfdx=vdfdx, edfdv=edfdv, field_solve=field_solve, fp_step=fp_step, to_x=to_x, to_v=to_v)
+
+
+def get_sharded_timestep(all_params, stuff_for_time_loop, topo, backend=None):
+    """The sharded counterpart of vlapy/core/step.py:286-328.  Returns
+    timestep(state, t, de, store) -> state where state = {"e": full field, "f": Sharded};
+    ``store`` (optional) receives the per-step stored quantities of this rank's x-slab."""
+    from .core import vlasov_poisson
+    if backend is None:
+        backend = DeviceBackend(topo, stuff_for_time_loop, all_params["fokker-planck"]["type"])
+    ops_ = make_sharded_operators(topo, backend)
+    stuff = dict(stuff_for_time_loop)
+    stuff["driver_function"] = backend.driver
+    vp_step = vlasov_poisson.get_time_integrator(
+        all_params["vlasov-poisson"]["time"], ops_["vdfdx"], ops_["edfdv"], ops_["field_solve"], stuff)
+    collide = all_params["nu"] > 0.0
+    if all_params["nu"] < 0.0:
+        raise NotImplementedError
+    nmodes = 2
+
+    def timestep(state, t, de=None, store=None):
+        e, f = vp_step(e=state["e"], f=state["f"], t=t)
+        mom = store["moments"] if store is not None else None
+        if collide:
+            f = ops_["fp_step"](f, moments_out=mom)
+        else:
+            f = ops_["to_x"](f)
+            if mom is not None:
+                backend.moments(f.t, mom)
+        if store is not None:
+            i = store["i"]
+            sl = slice(topo.x0, topo.x0 + topo.nxl)
+            store["fields_e"][i] = e[sl]
+            if de is not None:
+                store["fields_driver"][i] = de[sl]
+            store["fields_mom"][i] = mom[:6]
+            # series: local sums over this rank's x cells (means are finished after an all-reduce)
+            el = e[sl]
+            store["series_sum"][i, 0:3] = mom[0:3].sum(dim=1)
+            store["series_sum"][i, 3] = (el * el).sum()
+            store["series_sum"][i, 4] = (de[sl] * de[sl]).sum() if de is not None else 0.0
+            store["series_sum"][i, 5:7] = mom[6:8].sum(dim=1)
+            store["modes_partial"][i] = backend.xmodes_partial(f.t, nmodes)
+            store["i"] = i + 1
+        return {"e": e, "f": f}
+
+    timestep.backend = backend
+    return timestep
+
+
+def make_store(topo, backend, nsteps):
+    return {
+        "i": 0,
+        "moments": backend.zeros((8, topo.nxl)),
+        "fields_e": backend.zeros((nsteps, topo.nxl)),
+        "fields_driver": backend.zeros((nsteps, topo.nxl)),
+        "fields_mom": backend.zeros((nsteps, 6, topo.nxl)),
+        "series_sum": backend.zeros((nsteps, 7)),
+        "modes_partial": backend.zeros((nsteps, 2, topo.nv, 2)),
+    }
+
+
+def finish_store(topo, store):
+    """storage cadence: turn local sums into global means / modes (two small all-reduces)"""
+    series = topo.all_reduce_sum(store["series_sum"].clone()) / topo.nx
+    modes = topo.all_reduce_sum(store["modes_partial"].clone())
+    return series, torch.view_as_complex(modes.contiguous())
+
+
+# ---------------------------------------------------------------------------------------------
+# bench.py --gpus N
+# ---------------------------------------------------------------------------------------------
+
+def bench_sharded(cfg, params, rules, K, W, dev, barrier):
+    """Strong scaling: the same nx x nv grid sharded over the ranks; K timed full timesteps."""
+    import bench as _bench
+    from . import ops
+    nx, nv = cfg["nx"], cfg["nv"]
+    topo = Topology(nx, nv)
+    stuff = {k: cfg[k] for k in ("kx", "x", "one_over_kx", "v", "kv", "nv", "nx", "dv", "dt", "nu")}
+    stuff.update(rules_to_store_f=rules, driver_function=_bench.host_driver(cfg), pulse_dictionary=cfg["pulses"])
+    step = get_sharded_timestep(params, stuff, topo)
+    backend = step.backend
+    # this rank's x-slab of the synthetic state, built on the host and uploaded
+    fv = np.exp(-cfg["v"] ** 2 / 2.0)
+    fv /= (cfg["dv"] * (fv[1:] + fv[:-1]) / 2.0).sum()
+    xs = cfg["x"][topo.x0: topo.x0 + topo.nxl]
+    f_host = torch.empty((topo.nxl, nv), dtype=torch.float64, pin_memory=True)
+    np.multiply((1.0 + 0.05 * np.sin(cfg["k0"] * xs))[:, None], fv[None, :], out=f_host.numpy())
+    e = torch.from_numpy(0.01 * np.cos(cfg["k0"] * cfg["x"])).to(dev)
+    state = {"e": e, "f": Sharded(f_host.to(dev), "x")}
+    total = W + K
+    drv = [backend.driver(cfg["dt"] * i) for i in range(total)]
+    store = make_store(topo, backend, total)
+    for i in range(W):
+        state = step(state, cfg["dt"] * i, drv[i], store)
+    barrier()
+    sampler = _bench.ClockSampler(dev.index)
+    sampler.start()
+    ops.launch_count = 0
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for i in range(W, W + K):
+        state = step(state, cfg["dt"] * i, drv[i], store)
+    ev1.record()
+    barrier()
+    ms = ev0.elapsed_time(ev1)
+    launches = ops.launch_count
+    clocks = sampler.summary()
+    series, modes = finish_store(topo, store)
+    mean_n = float(series[total - 1, 0])
+    # per-kernel durations
+    ops.profile_enable(True)
+    store["i"] = W
+    for i in range(W, W + K):
+        state = step(state, cfg["dt"] * i, drv[i], store)
+    prof = ops.profile_report()
+    ops.profile_enable(False)
+    # end to end: upload the slab from pinned host memory, K steps, download slab + stored rows
+    import time
+    barrier()
+    t0 = time.perf_counter()
+    st2 = {"e": e, "f": Sharded(f_host.to(dev, non_blocking=True), "x")}
+    store["i"] = 0
+    for i in range(K):
+        st2 = step(st2, cfg["dt"] * i, drv[i], store)
+    f_back = torch.empty((topo.nxl, nv), dtype=torch.float64, pin_memory=True)
+    f_back.copy_(ops_to_x(st2["f"], topo), non_blocking=True)
+    fields_back = store["fields_mom"][:K].cpu()
+    s2, m2 = finish_store(topo, store)
+    s2.cpu(); m2.cpu()
+    barrier()
+    sec = time.perf_counter() - t0
+    h2d = (topo.nxl * nv * 8) / K
+    d2h = (topo.nxl * nv * 8 + 8 * K * topo.nxl * 8 + 7 * K * 8 + K * 2 * nv * 16) / K
+    e2e = {"value": nx * nv * K / sec, "unit": "cell-updates/s", "h2d_bytes_per_step": h2d * topo.world,
+           "d2h_bytes_per_step": d2h * topo.world, "ms_per_step": sec * 1e3 / K,
+           "note": "every rank uploads its x-slab, runs %d steps, downloads slab + stored rows" % K}
+    P = topo.world
+    return dict(ms=ms, launches=launches, clocks=clocks, prof=prof, e2e=e2e, mean_n=mean_n, scaling="strong",
+                parallelism="x-sharded rows / v-sharded columns over %d GPUs, 2 NCCL all-to-all + 1 all-reduce per step" % P)
+
+
+def ops_to_x(f, topo):
+    return f.t if f.layout == "x" else topo.v_to_x(f.t)

@@ -168,14 +168,16 @@ def fp_step(f, v, nu, dt, dv, op="lb", out=None, moments_out=None, vgrid=None):
     return out
 
 
-def xmodes(f, nmodes=2, out=None):
-    """fft_x(f)[:nmodes] per v as (batch, nmodes, ncols) complex128 (vlapy/core/step.py:130-135)."""
+def xmodes(f, nmodes=2, out=None, x_offset=0, nx_total=None):
+    """fft_x(f)[:nmodes] per v as (batch, nmodes, ncols) complex128 (vlapy/core/step.py:130-135).
+    With x_offset / nx_total: the partial sums of an x-slab of a larger grid."""
     _, ld = _chk_f(f)
     nx, ncols = f.shape[-2], f.shape[-1]
     batch = int(np.prod(f.shape[:-2])) if f.dim() > 2 else 1
     if out is None:
         out = torch.empty((batch, nmodes, ncols, 2), dtype=f.dtype, device=f.device)
-    _lib.check(_lib.lib().vpfp_xmodes(f.data_ptr(), ld, out.data_ptr(), nmodes, batch, nx, ncols, _stream()))
+    _lib.check(_lib.lib().vpfp_xmodes_partial(f.data_ptr(), ld, out.data_ptr(), nmodes, batch, nx, ncols,
+                                              int(x_offset), int(nx_total or nx), _stream()))
     _count(2)
     return torch.view_as_complex(out)
 
