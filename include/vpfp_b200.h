@@ -63,6 +63,15 @@ int vpfp_vdfdx_exp(const double *f_in, long ld_in, double *f_out, long ld_out, c
                    const double *v, double dt, int batch, int nx, int ncols, int flags,
                    void *stream);
 
+/* v df/dx fused with the charge density of its result: n_out[b*nx + x] = trapz_v f_out[b, x, :]
+ * (vlapy/core/field.py:27-36), reduced in the epilogue of the last pass instead of a separate
+ * read of f.  Every field solve of the reference follows a v df/dx
+ * (vlapy/core/vlasov_poisson.py:54-55, 115-116, 205-206).  edge_flags as in vpfp_moments. */
+int vpfp_vdfdx_exp_density(const double *f_in, long ld_in, double *f_out, long ld_out,
+                           const double *kx, const double *v, double dt, int batch, int nx,
+                           int ncols, int flags, double *n_out, double dv, int edge_flags,
+                           void *stream);
+
 /* e df/dv, 2nd-order centred differences: f_out = f - e * gradient_v(f) * dt (edge_order=2).
  * Replaces vlapy/core/vlasov.py:143-165. */
 int vpfp_edfdv_cd2(const double *f_in, long ld_in, double *f_out, long ld_out, const double *e,

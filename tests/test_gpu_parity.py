@@ -139,6 +139,28 @@ def test_fast_and_generic_kernels_agree_with_oracle(dev, n, flags):
         assert rel_err(out[b].cpu().numpy(), O.vdfdx_exponential(g[b], 0.25, kxs[b], vv)) < TOL
 
 
+@pytest.mark.parametrize("nx,ncols,edge", [(4096, 36, 3), (16384, 66, 1), (8192, 32, 2), (256, 64, 3), (16384, 32, 0)])
+def test_vdfdx_fused_density(dev, nx, ncols, edge):
+    """charge density reduced in the epilogue of the last pass == trapz_v of the result, for
+    whole grids (edge = 3) and v-slices of a sharded grid (edge = 1, 2, 0)"""
+    from vlapy_b200 import ops
+    rng = np.random.default_rng(nx + ncols + edge)
+    f = rng.standard_normal((nx, ncols)) + 1.0
+    vv = np.linspace(-3.0, 3.0, ncols)
+    kx = O.spatial_grid(0.0, 17.0, nx)[2]
+    n = torch.empty(nx, dtype=torch.float64, device=dev)
+    out = ops.vdfdx_exp(torch.from_numpy(f).to(dev), torch.from_numpy(kx).to(dev), torch.from_numpy(vv).to(dev), 0.3,
+                        flags=1, density_out=n, dv=0.05, edge_flags=edge)
+    ref = O.vdfdx_exponential(f, 0.3, kx, vv)
+    assert rel_err(out.cpu().numpy(), ref) < TOL
+    w = np.full(ncols, 0.05)
+    if edge & 1:
+        w[0] *= 0.5
+    if edge & 2:
+        w[-1] *= 0.5
+    assert rel_err(n.cpu().numpy(), (ref * w).sum(axis=1)) < TOL
+
+
 def test_vdfdx_ensemble_with_per_simulation_kx(dev):
     from vlapy_b200.core import vlasov
     rng = np.random.default_rng(11)

@@ -45,6 +45,7 @@ _SIGS = {
     "vpfp_profile_report": ([_c.c_char_p, _I], _I),
     "vpfp_edfdv_exp": ([_P, _L, _P, _L, _P, _P, _D, _I, _I, _I, _P], _I),
     "vpfp_vdfdx_exp": ([_P, _L, _P, _L, _P, _P, _D, _I, _I, _I, _I, _P], _I),
+    "vpfp_vdfdx_exp_density": ([_P, _L, _P, _L, _P, _P, _D, _I, _I, _I, _I, _P, _D, _I, _P], _I),
     "vpfp_edfdv_cd2": ([_P, _L, _P, _L, _P, _D, _D, _I, _I, _P], _I),
     "vpfp_moments": ([_P, _L, _P, _D, _P, _L, _I, _I, _I, _I, _P], _I),
     "vpfp_poisson": ([_P, _P, _P, _P, _I, _I, _P], _I),

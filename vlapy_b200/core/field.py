@@ -29,7 +29,9 @@ def get_spectral_solver(dv, one_over_kx):
     def solve_total_electric_field(driver_field, f):
         f_d, host = to_dev(f)
         drv, _ = to_dev(driver_field)
-        n = compute_charges(f_d, dv)
+        n = getattr(f, "_vpfp_density", None)       # reduced by the v df/dx epilogue that produced f
+        if n is None:
+            n = compute_charges(f_d, dv)
         o = ook if ook.shape == n.shape else ook.expand_as(n).contiguous()
         return back(ops.poisson(n.contiguous(), o, drv.contiguous()), host)
 

@@ -41,17 +41,25 @@ def _phase_flags(k):
     return ops.PHASE_EXACT
 
 
-def get_vdfdx_exponential(kx, v):
+def get_vdfdx_exponential(kx, v, dv=None):
     """vlapy/core/vlasov.py:83-110 -- v df/dx exponential integrator.
 
-    kx may be (nx,) or (batch, nx) for ensembles of simulations with their own box length."""
+    kx may be (nx,) or (batch, nx) for ensembles of simulations with their own box length.
+    With ``dv`` the charge density of the result is reduced in the kernel's epilogue and attached
+    to the returned device tensor (``_vpfp_density``) for the field solve that always follows
+    (vlapy/core/vlasov_poisson.py:54-55); the tensor must not be modified in place in between."""
     kx_d = const(_check_wavenumbers(kx, "v df/dx"))
     v_d = const(v)
     flags = _phase_flags(kx)
 
     def step_vdfdx_exponential(f, dt):
         f_d, host = to_dev(f)
-        return back(ops.vdfdx_exp(f_d.contiguous(), kx_d, v_d, dt, flags=flags), host)
+        if dv is None or host:
+            return back(ops.vdfdx_exp(f_d.contiguous(), kx_d, v_d, dt, flags=flags), host)
+        n = f_d.new_empty(f_d.shape[:-1])
+        out = ops.vdfdx_exp(f_d.contiguous(), kx_d, v_d, dt, flags=flags, density_out=n, dv=dv)
+        out._vpfp_density = n
+        return out
 
     return step_vdfdx_exponential
 
@@ -83,7 +91,8 @@ def get_edfdv_center_differenced(dv):
 def get_vdfdx(stuff_for_time_loop, vdfdx_implementation="exponential"):
     """vlapy/core/vlasov.py:213-235."""
     if vdfdx_implementation == "exponential":
-        vdfdx = get_vdfdx_exponential(kx=stuff_for_time_loop["kx"], v=stuff_for_time_loop["v"])
+        vdfdx = get_vdfdx_exponential(kx=stuff_for_time_loop["kx"], v=stuff_for_time_loop["v"],
+                                      dv=stuff_for_time_loop.get("dv"))
     else:
         raise NotImplementedError(
             "v df/dx: <" + vdfdx_implementation + "> has not yet been implemented on the b200 backend")

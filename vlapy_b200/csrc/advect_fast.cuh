@@ -46,6 +46,11 @@ struct FastArgs {
   const cplx* twN;  // exp(-2 pi i m/N)
   const cplx* twL1; // exp(-2 pi i m/N1), N1 entries
   const cplx* twL2; // exp(-2 pi i m/N2), N2 entries
+  // optional fused charge density (COLS pass 3 epilogue): partial[tile_b][sim*N + x] = sum over the
+  // tile's columns of w_j f[x][j] (np.trapz weights: dv, dv/2 on a global end column)
+  double* dens_partial;
+  double dv;
+  int edge_flags;
 };
 
 __device__ __forceinline__ cplx ldg_c(const cplx* p) {
@@ -176,8 +181,33 @@ __global__ void __launch_bounds__(CB* Geo<L>::TPC) pass13_kernel(const FastArgs 
 #pragma unroll
       for (int j = 0; j < R1; ++j)
         if (valid) gstore<MODE>(a, sim, seq, (long)(r + 8 * j) * N2 + n2, x[q * R1 + j], true);
+      if (MODE == ADV_COLS && a.dens_partial != nullptr) {
+        // charge density of the new f (vlapy/core/field.py:27-36): weighted sum over this tile's
+        // 2*CB real columns, reduced across the CB lanes that share x; one partial row per column tile
+        const int ncols = 2 * a.nseq;
+        const double wa = (valid ? ((2 * seq == 0 && (a.edge_flags & 1)) ? 0.5 * a.dv : a.dv) : 0.0);
+        const double wb = (valid ? ((2 * seq + 1 == ncols - 1 && (a.edge_flags & 2)) ? 0.5 * a.dv : a.dv) : 0.0);
+        const int tiles_b = (a.nseq + CB - 1) / CB;
+        const int bt = blockIdx.x % tiles_b;
+#pragma unroll
+        for (int j = 0; j < R1; ++j) {
+          double d = wa * x[q * R1 + j].x + wb * x[q * R1 + j].y;
+#pragma unroll
+          for (int o = (CB < 32 ? CB : 32) / 2; o > 0; o >>= 1) d += __shfl_xor_sync(0xffffffffu, d, o);
+          if (b == 0) a.dens_partial[((long)bt * a.nsim + sim) * a.N + (long)(r + 8 * j) * N2 + n2] = d;
+        }
+      }
     }
   }
+}
+
+// second stage of the fused density: n[x] = sum over column tiles (fixed order, deterministic)
+__global__ void dens_reduce_kernel(const double* __restrict__ partial, int ntiles, long n, double* __restrict__ out) {
+  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double s = 0.0;
+  for (int t = 0; t < ntiles; ++t) s += partial[(long)t * n + i];
+  out[i] = s;
 }
 
 // ------------------------------------------------------------------------------------------

@@ -26,6 +26,7 @@ struct Args {
   int op;                    // 0 lb, 1 dg
   double* mom_out; long mom_ld;
   int rows, nv;
+  const double2* logtab;     // 128 x (1/c_i, ln c_i), c_i = 1 + (i + 1/2)/128
 };
 
 __device__ __forceinline__ double warp_sum(double x) {
@@ -51,13 +52,30 @@ __device__ __forceinline__ double block_sum(double x, double* red) {
 // tridiagonal matrix with slowly varying coefficients converge geometrically): two Newton steps
 // when the first residual is below 2^-14 (then the result is good to < 1 ulp), else a division.
 __device__ __forceinline__ double rcp_near(double p, double r) {
-  const double e = fma(-p, r, 1.0);
-  if (fabs(e) < 6.0e-5) {
-    const double r1 = fma(r, e, r);
-    const double e1 = fma(-p, r1, 1.0);
-    return fma(r1, e1, r1);
-  }
+  const double e = fma(-p, r, 1.0);                    // 1/p = r (1 + e + e^2 + ...)
+  if (fabs(e) < 3.0e-6) return fma(r, fma(e, e, e), r);  // truncation e^3 < 3e-17
   return 1.0 / p;
+}
+
+// natural logarithm for the f ln f moment: x = 2^e m, m in [1,2) split by its top 7 mantissa bits
+// into c_i (1 + r); ln x = e ln2 + ln c_i + log1p(r), |r| < 2^-8, degree-6 series.  Absolute error
+// ~1e-16 (what a sum of f ln f needs); non-positive, subnormal or non-finite arguments take the
+// library path so that NaN / -inf semantics match numpy (vlapy/core/step.py:222-224).
+__device__ __forceinline__ double log_sum(double x, const double2* __restrict__ tab) {
+  const long long bits = __double_as_longlong(x);
+  const int ex = (int)((bits >> 52) & 0x7ff);
+  if (bits <= 0 || ex == 0 || ex == 0x7ff) return log(x);
+  const double m = __longlong_as_double((bits & 0x000fffffffffffffLL) | 0x3ff0000000000000LL);
+  const int idx = (int)((bits >> 45) & 127);
+  const double2 t = tab[idx];                          // (1/c_i, ln c_i)
+  const double r = fma(m, t.x, -1.0);
+  double p = fma(r, -1.0 / 6.0, 0.2);
+  p = fma(r, p, -0.25);
+  p = fma(r, p, 1.0 / 3.0);
+  p = fma(r, p, -0.5);
+  p = fma(r * r, p, r);
+  const double e = (double)(ex - 1023);
+  return fma(e, 6.93147180369123816490e-01, fma(e, 1.90821492927058770002e-10, t.y + p));
 }
 
 template <int M, int T>
@@ -70,8 +88,10 @@ __global__ void __launch_bounds__(T, 1) fp_kernel(const Args a) {
   double* row = reinterpret_cast<double*>(smem_raw);  // NV + T (one pad per chunk)
   double* red = row + NV + T;                          // 64
   double* X = red + 64;                                // 8 * T scratch (separator system / moments)
+  double2* LT = reinterpret_cast<double2*>(X + 8 * T); // 128 entries of the log table
   const int t = threadIdx.x;
   const int lane = t & 31, warp = t >> 5;
+  for (int i = t; i < 128; i += T) LT[i] = a.logtab[i];
   auto sk = [](int i) { return i + i / M; };           // skewed index
   // velocity of cell t + k*T (row-order loops) -- affine in k; the reference grid is np.linspace
   const double vt = fma((double)t, a.vstep, a.v0);
@@ -174,37 +194,42 @@ __global__ void __launch_bounds__(T, 1) fp_kernel(const Args a) {
         rd = fma(-Ce, X[2 * T + t + 1], rd);
       }
     }
-    // ---------------- cyclic reduction over the T separators (shared memory ping-pong)
+    // ---------------- cyclic reduction over the T separators (shared memory ping-pong).
+    // Rows are kept normalised (unit diagonal: a, c, d divided by b), so a step needs one
+    // reciprocal.  The matrix is diagonally dominant, the couplings shrink quadratically per
+    // step; once every |a| + |c| is below 1e-18 the rows are decoupled and x = d.
     {
       double* cur = X;
       double* nxt = X + 4 * T;
+      {
+        const double ib = 1.0 / rb;
+        ra *= ib; rc *= ib; rd *= ib;
+      }
       __syncthreads();
-      cur[t] = ra; cur[T + t] = rb; cur[2 * T + t] = rc; cur[3 * T + t] = rd;
-      __syncthreads();
+      cur[t] = ra; cur[T + t] = rc; cur[2 * T + t] = rd;
+      int more = __syncthreads_or((fabs(ra) + fabs(rc)) > 1e-18);
 #pragma unroll 1
-      for (int st = 1; st < T; st <<= 1) {
-        double na = 0.0, nc = 0.0, nb = cur[T + t], nd = cur[3 * T + t];
-        const double a_ = cur[t], c_ = cur[2 * T + t];
+      for (int st = 1; st < T && more; st <<= 1) {
+        double nb = 1.0, na = 0.0, nc = 0.0;
         const int im = t - st, ip = t + st;
         if (im >= 0) {
-          const double al = -a_ / cur[T + im];
-          na = al * cur[im];
-          nb = fma(al, cur[2 * T + im], nb);
-          nd = fma(al, cur[3 * T + im], nd);
+          na = -ra * cur[im];
+          nb = fma(-ra, cur[T + im], nb);
+          rd = fma(-ra, cur[2 * T + im], rd);
         }
         if (ip < T) {
-          const double ga = -c_ / cur[T + ip];
-          nc = ga * cur[2 * T + ip];
-          nb = fma(ga, cur[ip], nb);
-          nd = fma(ga, cur[3 * T + ip], nd);
+          nc = -rc * cur[T + ip];
+          nb = fma(-rc, cur[ip], nb);
+          rd = fma(-rc, cur[2 * T + ip], rd);
         }
-        nxt[t] = na; nxt[T + t] = nb; nxt[2 * T + t] = nc; nxt[3 * T + t] = nd;
-        __syncthreads();
+        const double ib = 1.0 / nb;
+        ra = na * ib; rc = nc * ib; rd *= ib;
+        nxt[t] = ra; nxt[T + t] = rc; nxt[2 * T + t] = rd;
+        more = __syncthreads_or((fabs(ra) + fabs(rc)) > 1e-18);
         double* tmp = cur; cur = nxt; nxt = tmp;
       }
-      const double xe = cur[3 * T + t] / cur[T + t];
       __syncthreads();
-      X[t] = xe;
+      X[t] = rd;
       __syncthreads();
     }
     // ---------------- interior with known neighbours, in place.  Pivots of the upper half of the
@@ -279,7 +304,7 @@ __global__ void __launch_bounds__(T, 1) fp_kernel(const Args a) {
         p *= vi; acc[4] += p;
         p *= vi; acc[5] += p;
         acc[6] = fma(tw, x, acc[6]);
-        acc[7] = fma(tw, log(x), acc[7]);
+        acc[7] = fma(tw, log_sum(x, LT), acc[7]);
       }
 #pragma unroll
       for (int k = 0; k < 8; ++k) acc[k] = warp_sum(acc[k]);
@@ -306,7 +331,7 @@ __global__ void __launch_bounds__(T, 1) fp_kernel(const Args a) {
 
 template <int M, int T>
 constexpr size_t smem_bytes() {
-  return sizeof(double) * (size_t)(M * T + T + 64 + 8 * T);
+  return sizeof(double) * (size_t)(M * T + T + 64 + 8 * T + 256);
 }
 
 }  // namespace fpfast

@@ -101,7 +101,7 @@ struct DeviceCache {
   void* scratch[4] = {nullptr, nullptr, nullptr, nullptr};   // grow-only, one per purpose
   size_t scratch_bytes[4] = {0, 0, 0, 0};
 };
-enum { SCR_XMODES = 0, SCR_PHANTOM = 1 };
+enum { SCR_XMODES = 0, SCR_PHANTOM = 1, SCR_DENSITY = 2 };
 static std::map<int, DeviceCache> g_cache;
 static std::mutex g_cache_mu;
 
@@ -218,7 +218,14 @@ static bool fast_eligible(const AdvectProg& a, const AdvectPlan& pl) {
   return true;
 }
 
-static int run_advect(AdvectProg a, cudaStream_t st, int flags = VPFP_PHASE_EXACT) {
+struct DensityReq {   // fused charge density request (vdfdx only)
+  double* out = nullptr;
+  double dv = 0.0;
+  int edge_flags = 3;
+};
+
+static int run_advect(AdvectProg a, cudaStream_t st, int flags = VPFP_PHASE_EXACT,
+                      const DensityReq* dens = nullptr, bool* dens_done = nullptr) {
   const AdvectPlan pl = make_advect_plan(a.mode, a.N, 2048, 2048);
   int rc = get_twiddles(a.N, &a.tw);
   if (rc) return rc;
@@ -241,11 +248,32 @@ static int run_advect(AdvectProg a, cudaStream_t st, int flags = VPFP_PHASE_EXAC
     fa.fin = a.fin; fa.ld_in = a.ld_in; fa.fout = a.fout; fa.ld_out = a.ld_out;
     fa.kvec = a.kvec; fa.cvec = a.cvec; fa.dt = a.dt; fa.phantom = a.phantom;
     fa.twN = a.tw;
+    fa.dens_partial = nullptr; fa.dv = 0.0; fa.edge_flags = 3;
+    int dens_tiles = 0;
+    if (dens && dens->out && a.mode == ADV_COLS) {
+      const int CB = (pl.N1 == 128) ? 16 : 32;
+      dens_tiles = (a.nseq + CB - 1) / CB;
+      void* scr = nullptr;
+      rc = get_scratch(SCR_DENSITY, sizeof(double) * (size_t)dens_tiles * a.nsim * a.N, &scr);
+      if (rc) return rc;
+      fa.dens_partial = (double*)scr; fa.dv = dens->dv; fa.edge_flags = dens->edge_flags;
+    }
     rc = get_twiddles(pl.N1, &fa.twL1);
     if (rc) return rc;
     rc = get_twiddles(pl.N2, &fa.twL2);
     if (rc) return rc;
-    return (a.mode == ADV_COLS) ? run_fast_mode<ADV_COLS>(fa, st) : run_fast_mode<ADV_ROWS>(fa, st);
+    rc = (a.mode == ADV_COLS) ? run_fast_mode<ADV_COLS>(fa, st) : run_fast_mode<ADV_ROWS>(fa, st);
+    if (rc) return rc;
+    if (fa.dens_partial) {
+      const long n = (long)a.nsim * a.N;
+      {
+        ProfScope ps("vdfdx.density_reduce", st);
+        fast::dens_reduce_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(fa.dens_partial, dens_tiles, n, dens->out);
+      }
+      CUDA_TRY(cudaGetLastError());
+      if (dens_done) *dens_done = true;
+    }
+    return VPFP_OK;
   }
   for (int pass = 1; pass <= 3; ++pass) {
     advect_set_pass(a, pl, pass);
@@ -304,6 +332,28 @@ struct PoissonDftProg {
   }
 };
 
+// table of the f ln f logarithm (fp_fast.cuh log_sum): 128 x (1/c_i, ln c_i), cached per device
+static std::map<int, double2*> g_logtab;
+static int get_logtab(const double2** out) {
+  int dev = 0;
+  CUDA_TRY(cudaGetDevice(&dev));
+  std::lock_guard<std::mutex> lk(g_cache_mu);
+  auto it = g_logtab.find(dev);
+  if (it != g_logtab.end()) { *out = it->second; return VPFP_OK; }
+  std::vector<double2> h(128);
+  for (int i = 0; i < 128; ++i) {
+    const long double c = 1.0L + ((long double)i + 0.5L) / 128.0L;
+    h[i].x = (double)(1.0L / c);
+    h[i].y = (double)(-logl((long double)h[i].x));     // consistent with the rounded reciprocal
+  }
+  double2* d = nullptr;
+  CUDA_TRY(cudaMalloc(&d, sizeof(double2) * 128));
+  CUDA_TRY(cudaMemcpy(d, h.data(), sizeof(double2) * 128, cudaMemcpyHostToDevice));
+  g_logtab[dev] = d;
+  *out = d;
+  return VPFP_OK;
+}
+
 template <int M, int T>
 static int launch_fp_fast(const fpfast::Args& a, cudaStream_t st) {
   const size_t smem = fpfast::smem_bytes<M, T>();
@@ -331,6 +381,9 @@ static int launch_fp_fast(const fpfast::Args& a, cudaStream_t st) {
 // ------------------------------------------------------------------------------------------
 extern "C" {
 
+int vpfp_moments(const double* f, long ld, const double* v, double dv, double* out, long out_ld,
+                 int nmom, int rows, int ncols, int edge_flags, void* stream);
+
 int vpfp_abi_version(void) { return VPFP_ABI_VERSION; }
 const char* vpfp_last_error(void) { return g_err.c_str(); }
 
@@ -339,6 +392,7 @@ int vpfp_shutdown(void) {
   for (auto& kv : g_cache) {
     cudaSetDevice(kv.first);
     for (auto& t : kv.second.tw) cudaFree(t.second);
+    if (g_logtab.count(kv.first)) { cudaFree(g_logtab[kv.first]); g_logtab.erase(kv.first); }
     for (int i = 0; i < 4; ++i)
       if (kv.second.scratch[i]) cudaFree(kv.second.scratch[i]);
   }
@@ -407,6 +461,33 @@ int vpfp_vdfdx_exp(const double* f_in, long ld_in, double* f_out, long ld_out, c
   a.fin = f_in; a.ld_in = ld_in; a.fout = f_out; a.ld_out = ld_out;
   a.kvec = kx; a.cvec = v; a.addv = nullptr; a.dt = dt;
   return run_advect(a, (cudaStream_t)stream, flags);
+}
+
+int vpfp_vdfdx_exp_density(const double* f_in, long ld_in, double* f_out, long ld_out, const double* kx,
+                           const double* v, double dt, int batch, int nx, int ncols, int flags,
+                           double* n_out, double dv, int edge_flags, void* stream) {
+  if (!f_in || !f_out || !kx || !v || !n_out || batch <= 0 || nx <= 0 || ncols <= 0 || ld_in < ncols ||
+      ld_out < ncols)
+    return fail(VPFP_ERR_ARG, "vpfp_vdfdx_exp_density: bad argument");
+  if (!is_pow2(nx) || nx < 2 || nx > (1 << 24))
+    return fail(VPFP_ERR_UNSUPPORTED, "v df/dx: <exponential> needs nx = 2^k >= 2 on the b200 backend");
+  if ((ncols & 1) || (ld_in & 1) || (ld_out & 1) || ((uintptr_t)f_in & 15) || ((uintptr_t)f_out & 15))
+    return fail(VPFP_ERR_UNSUPPORTED, "v df/dx: column count and row pitch must be even, f 16-byte aligned");
+  AdvectProg a;
+  memset(&a, 0, sizeof(a));
+  a.mode = ADV_COLS; a.op = OP_PHASE; a.N = nx;
+  a.nsim = batch; a.nrows = nx; a.nseq = ncols / 2;
+  a.fin = f_in; a.ld_in = ld_in; a.fout = f_out; a.ld_out = ld_out;
+  a.kvec = kx; a.cvec = v; a.addv = nullptr; a.dt = dt;
+  DensityReq dr; dr.out = n_out; dr.dv = dv; dr.edge_flags = edge_flags;
+  bool done = false;
+  int rc = run_advect(a, (cudaStream_t)stream, flags, &dr, &done);
+  if (rc) return rc;
+  if (!done) {
+    // sizes served by the generic kernels: density as a separate row reduction of the result
+    return vpfp_moments(f_out, ld_out, v, dv, n_out, (long)batch * nx, 1, batch * nx, ncols, edge_flags, stream);
+  }
+  return VPFP_OK;
 }
 
 int vpfp_edfdv_cd2(const double* f_in, long ld_in, double* f_out, long ld_out, const double* e,
@@ -482,6 +563,8 @@ int vpfp_fp_step_linspace(const double* f_in, long ld_in, double* f_out, long ld
   a.fin = f_in; a.ld_in = ld_in; a.fout = f_out; a.ld_out = ld_out;
   a.v0 = v0; a.vstep = vstep; a.vlast = vlast; a.nu = nu; a.dt = dt; a.dv = dv; a.op = op;
   a.mom_out = moments_out; a.mom_ld = mom_ld; a.rows = rows; a.nv = nv;
+  int rc = get_logtab(&a.logtab);
+  if (rc) return rc;
   cudaStream_t st = (cudaStream_t)stream;
   switch (nv) {
     case 16384: return launch_fp_fast<32, 512>(a, st);

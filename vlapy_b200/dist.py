@@ -92,9 +92,16 @@ class DeviceBackend:
         return self.ops.edfdv_exp(fx, e_loc, self.kv, dt, flags=self.flags_v)
 
     def vdfdx(self, fv, dt):
-        return self.ops.vdfdx_exp(fv, self.kx, self.v_loc, dt, flags=self.flags_x)
+        n = fv.new_empty(fv.shape[0])            # partial density over the local columns, fused epilogue
+        out = self.ops.vdfdx_exp(fv, self.kx, self.v_loc, dt, flags=self.flags_x, density_out=n, dv=self.dv,
+                                 edge_flags=self.edge)
+        out._vpfp_density = n
+        return out
 
     def density_partial(self, fv):
+        n = getattr(fv, "_vpfp_density", None)
+        if n is not None:
+            return n
         return self.ops.moments(fv, self.v_loc, self.dv, nmom=1, edge_flags=self.edge)[0].contiguous()
 
     def poisson(self, n, driver):

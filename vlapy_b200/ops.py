@@ -73,8 +73,9 @@ def edfdv_exp(f, e, kv, dt, out=None, flags=PHASE_EXACT):
     return out
 
 
-def vdfdx_exp(f, kx, v, dt, out=None, flags=PHASE_EXACT):
-    """vlapy/core/vlasov.py:94-108 on device. f: (batch, nx, ncols) or (nx, ncols); kx: (batch, nx)."""
+def vdfdx_exp(f, kx, v, dt, out=None, flags=PHASE_EXACT, density_out=None, dv=None, edge_flags=3):
+    """vlapy/core/vlasov.py:94-108 on device. f: (batch, nx, ncols) or (nx, ncols); kx: (batch, nx).
+    density_out (batch*nx doubles) + dv: also return trapz_v of the result (fused epilogue)."""
     _, ld = _chk_f(f)
     nx, ncols = f.shape[-2], f.shape[-1]
     batch = int(np.prod(f.shape[:-2])) if f.dim() > 2 else 1
@@ -82,6 +83,13 @@ def vdfdx_exp(f, kx, v, dt, out=None, flags=PHASE_EXACT):
         out = torch.empty(f.shape, dtype=f.dtype, device=f.device)
     _, ldo = _chk_f(out, "out")
     _vec(kx, batch * nx, "kx"); _vec(v, ncols, "v")
+    if density_out is not None:
+        _vec(density_out, batch * nx, "density_out")
+        _lib.check(_lib.lib().vpfp_vdfdx_exp_density(f.data_ptr(), ld, out.data_ptr(), ldo, kx.data_ptr(),
+                                                     v.data_ptr(), float(dt), batch, nx, ncols, flags,
+                                                     density_out.data_ptr(), float(dv), edge_flags, _stream()))
+        _count(adv_launches("cols", nx) + 1)
+        return out
     _lib.check(_lib.lib().vpfp_vdfdx_exp(f.data_ptr(), ld, out.data_ptr(), ldo, kx.data_ptr(), v.data_ptr(),
                                          float(dt), batch, nx, ncols, flags, _stream()))
     _count(adv_launches("cols", nx))
