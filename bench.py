@@ -247,8 +247,26 @@ def gpu_arm(args):
             "series": {"_rows": torch.zeros((total, 7), dtype=torch.float64, device=dev)},
             "_moment_scratch": torch.zeros((8, nx), dtype=torch.float64, device=dev),
         }
+        use_graph = nx * nv <= outer_loop.GRAPH_MAX_CELLS
+        if use_graph:
+            # launch-bound grids: the product path replays one captured step (vlapy_b200/outer_loop.py)
+            gs = outer_loop._GraphStep(params, stuff, nx, nv, (2, nv), True, dev)
+            gs.e.copy_(work["e"]); gs.f.copy_(work["f"])
+            gs.capture()
+            inputs = torch.cat([torch.from_numpy(times)[:, None].to(dev), drv_rows], dim=1).contiguous()
+            rows = torch.empty((total, gs.stage.numel()), dtype=torch.float64, device=dev)
+
+            def run_step(i):
+                gs.inp.copy_(inputs[i])
+                gs.graph.replay()
+                rows[i].copy_(gs.stage)
+            n_launch_per_step = None
+        else:
+            def run_step(i):
+                nonlocal work
+                work, _ = one_step(work, i)
         for i in range(W):
-            work, _ = one_step(work, i)
+            run_step(i)
         barrier()
         sampler = ClockSampler(local_rank)
         sampler.start()
@@ -256,7 +274,7 @@ def gpu_arm(args):
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         ev0.record()
         for i in range(W, W + K):
-            work, _ = one_step(work, i)
+            run_step(i)
         ev1.record()
         barrier()
         ms = ev0.elapsed_time(ev1)
@@ -264,11 +282,16 @@ def gpu_arm(args):
         clocks = sampler.summary()
         # ---- per-kernel durations (second pass over the same steps, events around every launch)
         ops.profile_enable(True)
+        ops.launch_count = 0
         for i in range(W, W + K):
-            work, _ = one_step(work, i)
+            work, _ = one_step(work, i)      # eager, so that every launch is bracketed by events
         prof = ops.profile_report()
         ops.profile_enable(False)
-        mean_n = float(work["series"]["_rows"][W + K - 1, 0])
+        if use_graph:
+            launches = ops.launch_count      # kernels per step are the same in the captured graph
+            mean_n = float(rows[W + K - 1, 8 * nx])
+        else:
+            mean_n = float(work["series"]["_rows"][W + K - 1, 0])
         del work, drv_rows
         torch.cuda.empty_cache()
         # ---- end to end through the public inner-loop API with host buffers
@@ -294,7 +317,7 @@ def gpu_arm(args):
                    "note": "one inner-loop call of %d steps: uploads f,e,driver rows; downloads fields, series, "
                            "stored modes, f, e (storage cadence of vlapy/manager.py:138-150)" % K}
         result = dict(ms=ms, launches=launches, clocks=clocks, prof=prof, e2e=e2e, mean_n=mean_n, scaling="strong",
-                      parallelism="1 GPU")
+                      parallelism="1 GPU", graph=use_graph)
 
     if world > 1:
         t = torch.tensor([result["ms"]], dtype=torch.float64, device=dev)
@@ -326,7 +349,8 @@ def gpu_arm(args):
                        "per_step": "edfdv(dt/2), vdfdx(dt), density+Poisson, edfdv(dt/2), FP solve + 8 moments, "
                                    "series, 2 x-modes",
                        "l2": "state (%.2f GB) exceeds the 126 MB L2; no flush needed" % (nx * nv * 8 / 1e9),
-                       "parallelism": result["parallelism"], "phase_factors": "geometric tables (VPFP_PHASE_TABLE)"},
+                       "parallelism": result["parallelism"], "phase_factors": "geometric tables (VPFP_PHASE_TABLE)",
+                       "cuda_graph": bool(result.get("graph", False))},
             "clocks": result["clocks"], "gpu_launches": result["launches"],
             "roofline": {"bound": "hbm", "kernel": dom_label, "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": None, "peak_source": peak_src,

@@ -122,6 +122,12 @@ int vpfp_xmodes_partial(const double *f, long ld, double *out, int nmodes, int b
 int vpfp_driver(const double *x, double t, const double *pulses, int npulse, double *out, int nx,
                 void *stream);
 
+/* The same driver with the time read on the device: t = (((*t_dev + incs[0]) + incs[1]) + ...),
+ * summed in the reference's order (vlapy/core/vlasov_poisson.py:116-148).  Lets a whole timestep
+ * be captured in a CUDA graph and replayed with a new time.  incs: host array, ninc <= 6. */
+int vpfp_driver_dev(const double *x, const double *t_dev, const double *incs, int ninc,
+                    const double *pulses, int npulse, double *out, int nx, void *stream);
+
 /* Series reductions of one stored step (vlapy/core/step.py:202-224): out[0..6] =
  * mean_x of moments rows n, j, T, mean(e^2), mean(de^2), mean_x of rows f2, flogf. */
 int vpfp_series(const double *moments, long mom_ld, const double *e, const double *de,

@@ -156,7 +156,7 @@ int emul_xmodes(const double* f, long ld, double* out, int nmodes, int batch, in
 
 int emul_driver(const double* x, double t, const double* pulses, int npulse, double* out, int nx) {
   DriverProg p;
-  p.x = x; p.out = out; p.t = t; p.nx = nx; p.npulse = npulse;
+  p.x = x; p.out = out; p.t = t; p.t_dev = nullptr; p.ninc = 0; p.nx = nx; p.npulse = npulse;
   for (int i = 0; i < npulse * 7; ++i) p.pulses[i] = pulses[i];
   run_prog(p, (nx + 255) / 256, 256, 0, 1);
   return 0;

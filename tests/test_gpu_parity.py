@@ -400,6 +400,35 @@ def test_small_collisional_run_through_inner_loop(dev):
         assert rel_err(o["e"], g["small_e_%d" % li]) < 1e-11
 
 
+def test_cuda_graph_inner_loop_equals_eager(dev):
+    """the captured-step inner loop (default for small grids) and the eager one give the same
+    stored quantities and final state, for a schedule with several driver sub-step times"""
+    from vlapy_b200 import outer_loop
+    cfg = O.nlepw_config(nx=32, nv=256, k0=0.35, log_nu=-2)
+    res = {}
+    for mode in (True, False):
+        params = make_params(cfg, "pefrl", "dg")
+        params["backend"]["cuda_graph"] = mode
+        stuff = make_stuff(cfg, RULES)
+        sim, inner = outer_loop.get_sim_config_and_inner_loop_step(params, stuff, 12, RULES)
+        for li in range(2):
+            t = cfg["dt"] * np.arange(li * 12, (li + 1) * 12)
+            drv = np.stack([cfg["driver_function"](ti) for ti in t])
+            sim = inner(time_array=t, driver_array=drv, temp_storage=sim)
+        res[mode] = {"f": sim["f"].copy(), "e": sim["e"].copy(), "T": sim["fields"]["T"].copy(),
+                     "series": {k: np.array(v).copy() for k, v in sim["series"].items()},
+                     "stored_f": sim["stored_f"].copy()}
+    g, e = res[True], res[False]
+    assert rel_err(g["f"], e["f"]) < 1e-14 and rel_err(g["e"], e["e"]) < 1e-13
+    np.testing.assert_allclose(g["T"], e["T"], rtol=1e-13)
+    for k in e["series"]:
+        np.testing.assert_allclose(g["series"][k], e["series"][k], rtol=1e-12, atol=1e-16, err_msg=k)
+    np.testing.assert_allclose(g["stored_f"], e["stored_f"], rtol=1e-6, atol=1e-9)
+    # and both agree with the oracle
+    e_ref, f_ref = O.run_steps(cfg, 24, "pefrl", "dg")
+    assert rel_err(g["f"], f_ref) < TOL
+
+
 def test_smoke_entry(dev):
     import __graft_entry__ as ge
     assert ge.smoke()

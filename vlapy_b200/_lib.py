@@ -54,6 +54,7 @@ _SIGS = {
     "vpfp_xmodes": ([_P, _L, _P, _I, _I, _I, _I, _P], _I),
     "vpfp_xmodes_partial": ([_P, _L, _P, _I, _I, _I, _I, _I, _I, _P], _I),
     "vpfp_driver": ([_P, _D, _P, _I, _P, _I, _P], _I),
+    "vpfp_driver_dev": ([_P, _P, _P, _I, _P, _I, _P, _I, _P], _I),
     "vpfp_series": ([_P, _L, _P, _P, _P, _I, _P], _I),
 }
 

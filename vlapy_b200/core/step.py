@@ -28,8 +28,11 @@ def get_device_driver_function(stuff_for_time_loop):
     x_d = const(stuff_for_time_loop["x"])
 
     def driver_function(current_time):
+        if isinstance(current_time, ops.DevTime):
+            return ops.driver_dev(x_d, current_time, arr)
         return ops.driver(x_d, current_time, arr)
 
+    driver_function.on_device = True
     return driver_function
 
 
@@ -145,6 +148,15 @@ def get_storage_step(stuff_for_time_loop):
         return temp_storage
 
     return storage_step
+
+
+def get_step_parts(all_params, stuff_for_time_loop):
+    """The pieces of a timestep for callers that compose them differently (the CUDA-graph inner loop
+    of vlapy_b200/outer_loop.py): (vp_step, fp_step, fp_fuses_moments, store_f_function)."""
+    vp_step = get_vlasov_poisson_step(all_params=all_params, stuff_for_time_loop=stuff_for_time_loop)
+    fp_step = get_collision_step(all_params=all_params, stuff_for_time_loop=stuff_for_time_loop)
+    store_f = get_f_update(store_f_rule=stuff_for_time_loop["rules_to_store_f"])
+    return vp_step, fp_step, getattr(fp_step, "fuses_moments", False), store_f
 
 
 def get_timestep(all_params, stuff_for_time_loop):

@@ -37,6 +37,7 @@ struct FastArgs {
   int mode, exact;
   int N, N1, N2;
   int nsim, nseq, nrows;
+  int seq_off, seq_cnt;     // this launch handles packed sequences [seq_off, seq_off + seq_cnt) (L2 slab)
   const double* fin; long ld_in;
   double* fout; long ld_out;
   const double* kvec;  // [nsim][N] (COLS) or [N] (ROWS)
@@ -103,17 +104,17 @@ __global__ void __launch_bounds__(CB* Geo<L>::TPC) pass13_kernel(const FastArgs 
   int sim = 0, seq, n2;
   bool valid;
   if (MODE == ADV_COLS) {
-    const int tiles_b = (a.nseq + CB - 1) / CB;
+    const int tiles_b = (a.seq_cnt + CB - 1) / CB;
     const int bt = blockIdx.x % tiles_b;
     const long r = blockIdx.x / tiles_b;
     n2 = (int)(r % a.N2);
     sim = (int)(r / a.N2);
-    seq = bt * CB + b;
-    valid = seq < a.nseq;
+    seq = a.seq_off + bt * CB + b;
+    valid = seq < a.seq_off + a.seq_cnt;
   } else {
     const int tiles_b = a.N2 / CB;
     const int bt = blockIdx.x % tiles_b;
-    seq = blockIdx.x / tiles_b;
+    seq = a.seq_off + blockIdx.x / tiles_b;
     n2 = bt * CB + b;
     valid = true;
   }
@@ -187,8 +188,8 @@ __global__ void __launch_bounds__(CB* Geo<L>::TPC) pass13_kernel(const FastArgs 
         const int ncols = 2 * a.nseq;
         const double wa = (valid ? ((2 * seq == 0 && (a.edge_flags & 1)) ? 0.5 * a.dv : a.dv) : 0.0);
         const double wb = (valid ? ((2 * seq + 1 == ncols - 1 && (a.edge_flags & 2)) ? 0.5 * a.dv : a.dv) : 0.0);
-        const int tiles_b = (a.nseq + CB - 1) / CB;
-        const int bt = blockIdx.x % tiles_b;
+        const int tiles_b = (a.seq_cnt + CB - 1) / CB;
+        const int bt = a.seq_off / CB + blockIdx.x % tiles_b;      // global column-tile index
 #pragma unroll
         for (int j = 0; j < R1; ++j) {
           double d = wa * x[q * R1 + j].x + wb * x[q * R1 + j].y;
@@ -246,22 +247,23 @@ struct P2Layout {
   static constexpr int T_ELEMS = 2 * L * CB;
 };
 
-template <int L, int MODE, int CB>
-__global__ void __launch_bounds__(CB * 2 * Geo<L>::TPC, 2) pass2_kernel(const FastArgs a, const int t1_chunk) {
+template <int L, int MODE, int CB, bool PF>
+__global__ void __launch_bounds__(CB * 2 * Geo<L>::TPC, PF ? 2 : 4) pass2_kernel(const FastArgs a, const int t1_chunk) {
   using G = Geo<L>;
   using LY = P2Layout<L, MODE, CB>;
   constexpr int R1 = G::R1, TPC = G::TPC, NA = G::NA;
   constexpr int NT = CB * 2 * TPC;
   constexpr int HALF = L / 2;
   extern __shared__ __align__(16) unsigned char smem_raw[];
+  constexpr int NPT = 8 + HALF / 8 + 1;               // Lo[0..7] = G^j, Hi[0..HALF/8] = G^(8j)
   cplx* S = reinterpret_cast<cplx*>(smem_raw);        // exchange
-  cplx* STG = S + LY::S_ELEMS;                        // staging (prefetched tile)
-  cplx* PT = STG + LY::T_ELEMS;                       // [2 chan][CB][HALF+1]  G^j
-  cplx* BASE = PT + 2 * CB * (HALF + 1);              // [2 groups][2 chan][CB]
+  cplx* STG = S + LY::S_ELEMS;                        // staging (prefetched tile), PF only
+  cplx* PT = STG + (PF ? LY::T_ELEMS : 0);            // [2 chan][CB][NPT]
+  cplx* BASE = PT + 2 * CB * NPT;                     // [2 groups][2 chan][CB]
   cplx* TWL = BASE + 4 * CB;                          // [L]     exp(-2 pi i m / L)
   cplx* TWT = TWL + L;                                // [2][L]  four-step twiddles W_N^(n2 k1) of the staged tile
-  cplx* TWC = TWT + 2 * L;                            // [2][L]  the same for the tile being transformed
-  double* PHI = reinterpret_cast<double*>(TWC + 2 * L);    // [2 chan][CB]
+  cplx* TWC = TWT + 2 * L;                            // [2][L]  the same for the tile being transformed (PF only)
+  double* PHI = reinterpret_cast<double*>(TWC + (PF ? 2 * L : 0));    // [2 chan][CB]
 
   // thread roles: b = packed sequence, u = 0..R1-1 (step A: group u / TPC, r-slot u % TPC)
   int b, u;
@@ -269,14 +271,16 @@ __global__ void __launch_bounds__(CB * 2 * Geo<L>::TPC, 2) pass2_kernel(const Fa
   else { const int ta = threadIdx.x % TPC; b = (threadIdx.x / TPC) % CB; u = (threadIdx.x / (TPC * CB)) * TPC + ta; }
   const int T1 = a.N1 / 2;
   const int nchunks = (T1 + t1_chunk - 1) / t1_chunk;
-  const int tiles_b = (a.nseq + CB - 1) / CB;
+  const int tiles_b = (a.seq_cnt + CB - 1) / CB;
   int sim = 0;
   const int chunk = blockIdx.x % nchunks;
   const long rest = blockIdx.x / nchunks;
   const int bt = (int)(rest % tiles_b);
   if (MODE == ADV_COLS) sim = (int)(rest / tiles_b);
-  const int seq = bt * CB + b;
-  const bool valid = seq < a.nseq;
+  const int seq0 = a.seq_off + bt * CB;                  // first packed sequence of this CTA
+  const int seq_end = a.seq_off + a.seq_cnt;
+  const int seq = seq0 + b;
+  const bool valid = seq < seq_end;
   const long N = a.N, N1 = a.N1;
   const double inv_n = 1.0 / (double)N;
 
@@ -294,19 +298,19 @@ __global__ void __launch_bounds__(CB * 2 * Geo<L>::TPC, 2) pass2_kernel(const Fa
     if (MODE == ADV_COLS) {
       for (int w = threadIdx.x; w < 2 * L * CB; w += NT) {
         const int bb = w % CB, l = (w / CB) % L, gg = w / (CB * L);
-        const int sq = bt * CB + bb;
+        const int sq = seq0 + bb;
         cplx* dst = STG + LY::tidx(gg, l, bb);
-        if (sq < a.nseq)
+        if (sq < seq_end)
           cp_async16(dst, a.fout + ((long)sim * N + (long)(gg ? k1g1 : k1g0) * L + l) * a.ld_out + 2 * (long)sq);
         else *dst = cmake(0.0, 0.0);
       }
     } else {
       for (int w = threadIdx.x; w < 2 * L * CB; w += NT) {
         const int l = w % L, bb = (w / L) % CB, gg = w / (L * CB);
-        const int sq = bt * CB + bb;
+        const int sq = seq0 + bb;
         cplx* dst = STG + LY::tidx(gg, l, bb);
         const long n = (long)(gg ? k1g1 : k1g0) * L + l;
-        if (sq < a.nseq) {
+        if (sq < seq_end) {
           const long ra = 2 * (long)sq, rb = ra + 1;
           cp_async8(&dst->x, a.fout + ra * a.ld_out + n);
           if (rb < a.nrows) cp_async8(&dst->y, a.fout + rb * a.ld_out + n);
@@ -323,33 +327,28 @@ __global__ void __launch_bounds__(CB * 2 * Geo<L>::TPC, 2) pass2_kernel(const Fa
 
   for (int w = threadIdx.x; w < L; w += NT) TWL[w] = ldg_c(a.twL2 + w);
   const int t1_begin = chunk * t1_chunk, t1_end = min(T1, (chunk + 1) * t1_chunk);
-  prefetch(t1_begin);
+  if (PF) prefetch(t1_begin);
 
   if (!a.exact) {
     // phi = (K[1] dt) c ; G = exp(-i N1 phi); PT[j] = G^j = H[j>>3] * Lo[j&7]
     for (int w = threadIdx.x; w < 2 * CB; w += NT) {
       const int ch = w / CB, bb = w % CB;
-      const int sq = bt * CB + bb;
+      const int sq = seq0 + bb;
       double c = 0.0;
-      if (sq < a.nseq) {
+      if (sq < seq_end) {
         const long rr = 2 * (long)sq + ch;
         c = (MODE == ADV_COLS || rr < a.nrows) ? a.cvec[rr] : 0.0;
       }
       PHI[w] = mul_rn(mul_rn(K[1], a.dt), c);
     }
     __syncthreads();
-    for (int w = threadIdx.x; w < 2 * CB * (8 + HALF / 8); w += NT) {
-      const int sq = w / (8 + HALF / 8), i = w % (8 + HALF / 8);
-      const int j = (i < 8) ? i : 8 * (i - 7);
+    for (int w = threadIdx.x; w < 2 * CB * NPT; w += NT) {
+      const int sq = w / NPT, i = w % NPT;
+      const int j = (i < 8) ? i : 8 * (i - 8);          // Lo: j = 0..7, Hi: j = 0, 8, .., HALF
       const double th = (double)N1 * PHI[sq] * (double)j;
       double sn, cs;
       sincos(th, &sn, &cs);
-      PT[sq * (HALF + 1) + j] = cmake(cs, -sn);
-    }
-    __syncthreads();
-    for (int w = threadIdx.x; w < 2 * CB * (HALF + 1); w += NT) {
-      const int sq = w / (HALF + 1), j = w % (HALF + 1);
-      if (j >= 8 && (j & 7)) PT[sq * (HALF + 1) + j] = cmul(PT[sq * (HALF + 1) + (j & ~7)], PT[sq * (HALF + 1) + (j & 7)]);
+      PT[sq * NPT + i] = cmake(cs, -sn);
     }
   }
 
@@ -357,6 +356,7 @@ __global__ void __launch_bounds__(CB * 2 * Geo<L>::TPC, 2) pass2_kernel(const Fa
     const bool self = (t1 == 0);
     const int k1g0 = self ? 0 : t1, k1g1 = self ? (int)(N1 / 2) : (int)(N1 - t1);
 #define K1G(g) ((g) ? k1g1 : k1g0)
+    if (!PF) __syncthreads();                          // previous tile's pointwise is done with BASE
     if (!a.exact) {
       for (int w = threadIdx.x; w < 4 * CB; w += NT) {     // base(k1) per group/channel, scaled by 1/(2N)
         const int bb = w % CB, gc = w / CB, g = gc >> 1, ch = gc & 1;
@@ -367,19 +367,42 @@ __global__ void __launch_bounds__(CB * 2 * Geo<L>::TPC, 2) pass2_kernel(const Fa
     }
     cplx x[16];
     const int g = u / TPC, ta = u % TPC;
-    cp_async_wait_all();
-    __syncthreads();                                   // tile t1 is in STG
-    // ---------------- step A: staged tile -> registers, four-step twiddle, radix-R1
+    const cplx* TWI;                                   // twiddles for the inverse at the end of this tile
+    if (PF) {
+      cp_async_wait_all();
+      __syncthreads();                                 // tile t1 is in STG
+      // ---------------- step A: staged tile -> registers, four-step twiddle, radix-R1
 #pragma unroll
-    for (int q = 0; q < NA; ++q)
+      for (int q = 0; q < NA; ++q)
 #pragma unroll
-      for (int j = 0; j < R1; ++j) {
-        const int n2 = (ta + TPC * q) + 8 * j;
-        x[q * R1 + j] = cmul(STG[LY::tidx(g, n2, b)], TWT[g * L + n2]);
-      }
-    for (int w = threadIdx.x; w < 2 * L; w += NT) TWC[w] = TWT[w];   // keep for the inverse (TWT gets the next tile's)
-    __syncthreads();                                   // STG consumed, S free (previous tile's readers done)
-    if (t1 + 1 < t1_end) prefetch(t1 + 1);
+        for (int j = 0; j < R1; ++j) {
+          const int n2 = (ta + TPC * q) + 8 * j;
+          x[q * R1 + j] = cmul(STG[LY::tidx(g, n2, b)], TWT[g * L + n2]);
+        }
+      for (int w = threadIdx.x; w < 2 * L; w += NT) TWC[w] = TWT[w];   // keep for the inverse (TWT gets the next tile's)
+      TWI = TWC;
+      __syncthreads();                                 // STG consumed, S free (previous tile's readers done)
+      if (t1 + 1 < t1_end) prefetch(t1 + 1);
+    } else {
+      // direct loads (4 CTAs per SM hide the latency); twiddles of this tile into shared memory
+#pragma unroll
+      for (int q = 0; q < NA; ++q)
+#pragma unroll
+        for (int j = 0; j < R1; ++j)
+          x[q * R1 + j] = valid ? gload<MODE>(a, a.fout, a.ld_out, sim, seq, (long)K1G(g) * L + (ta + TPC * q) + 8 * j, false)
+                                : cmake(0.0, 0.0);
+      __syncthreads();                                 // previous tile done with S, TWT, BASE
+      for (int w = threadIdx.x; w < 2 * L; w += NT) TWT[w] = ldg_c(a.twN + (long)(w % L) * K1G(w / L));
+      TWI = TWT;
+      __syncthreads();
+#pragma unroll
+      for (int q = 0; q < NA; ++q)
+#pragma unroll
+        for (int j = 0; j < R1; ++j) {
+          const int n2 = (ta + TPC * q) + 8 * j;
+          x[q * R1 + j] = cmul(x[q * R1 + j], TWT[g * L + n2]);
+        }
+    }
 #pragma unroll
     for (int q = 0; q < NA; ++q) {
       const int r = ta + TPC * q;
@@ -412,6 +435,15 @@ __global__ void __launch_bounds__(CB * 2 * Geo<L>::TPC, 2) pass2_kernel(const Fa
     // ---------------- pointwise: pairs (Z at bin k, Zp at bin N - k), both in this thread
     {
       const long k1A = K1G(gA);
+      // table phases: P = base(k1) * Hi[j >> 3] * Lo[j & 7]; within a thread j & 7 takes one value for
+      // the bins below Nyquist and one above (k2 = m + R1 k', R1 a multiple of 8), base one per group
+      cplx baseA_a, baseA_b, loP_a, loP_b, loN_a, loN_b;
+      if (!a.exact) {
+        baseA_a = BASE[(gA * 2 + 0) * CB + b]; baseA_b = BASE[(gA * 2 + 1) * CB + b];
+        const int mlo = (special ? 0 : mA) & 7;
+        loP_a = PT[b * NPT + mlo]; loP_b = PT[(CB + b) * NPT + mlo];
+        loN_a = PT[b * NPT + ((8 - mlo) & 7)]; loN_b = PT[(CB + b) * NPT + ((8 - mlo) & 7)];
+      }
       auto pair_op = [&](cplx& Zr, cplx& Zpr, const long kbin, const long k1, const int gsel, const bool selfpair) {
         const bool neg = (2 * kbin > N);
         const bool nyq = (2 * kbin == N);
@@ -427,10 +459,15 @@ __global__ void __launch_bounds__(CB * 2 * Geo<L>::TPC, 2) pass2_kernel(const Fa
         } else {
           const int k2 = (int)((kbin - k1) / N1);           // 0..L-1
           const int j = neg ? (L - k2) : k2;                // |signed k2| in 0..HALF
-          cplx ta_ = PT[b * (HALF + 1) + j], tb_ = PT[(CB + b) * (HALF + 1) + j];
+          const bool hoisted = (!special) || (k1 == 0 && ((k2 & 7) == 0));
+          cplx la = hoisted ? (neg ? loN_a : loP_a) : PT[b * NPT + (j & 7)];
+          cplx lb = hoisted ? (neg ? loN_b : loP_b) : PT[(CB + b) * NPT + (j & 7)];
+          cplx ta_ = cmul(PT[b * NPT + 8 + (j >> 3)], la);
+          cplx tb_ = cmul(PT[(CB + b) * NPT + 8 + (j >> 3)], lb);
           if (neg) { ta_ = cconj(ta_); tb_ = cconj(tb_); }
-          Pa = cmul(BASE[(gsel * 2 + 0) * CB + b], ta_);
-          Pb = cmul(BASE[(gsel * 2 + 1) * CB + b], tb_);
+          (void)gsel;
+          Pa = cmul(baseA_a, ta_);
+          Pb = cmul(baseA_b, tb_);
           if (nyq) { Pa.y = 0.0; Pb.y = 0.0; }
         }
         const cplx Z = Zr, Zp = Zpr;
@@ -476,7 +513,7 @@ __global__ void __launch_bounds__(CB * 2 * Geo<L>::TPC, 2) pass2_kernel(const Fa
 #pragma unroll
       for (int j = 0; j < R1; ++j) {
         const int n2 = r + 8 * j;
-        const cplx val = cmulc(x[q * R1 + j], TWC[g * L + n2]);
+        const cplx val = cmulc(x[q * R1 + j], TWI[g * L + n2]);
         if (valid) gstore<MODE>(a, sim, seq, (long)K1G(g) * L + n2, val, false);
       }
     }
@@ -485,9 +522,9 @@ __global__ void __launch_bounds__(CB * 2 * Geo<L>::TPC, 2) pass2_kernel(const Fa
 }
 
 template <int L, int CB>
-constexpr size_t pass2_smem(int mode) {
-  return sizeof(cplx) * (size_t)(((mode == ADV_ROWS) ? CB * 2 * (L / 8) * 9 : 2 * L * CB) + 2 * L * CB +
-                                 2 * CB * (L / 2 + 1) + 4 * CB + 5 * L) +
+constexpr size_t pass2_smem(int mode, bool pf) {
+  return sizeof(cplx) * (size_t)(((mode == ADV_ROWS) ? CB * 2 * (L / 8) * 9 : 2 * L * CB) + (pf ? 2 * L * CB : 0) +
+                                 2 * CB * (8 + L / 16 + 1) + 4 * CB + 3 * L + (pf ? 2 * L : 0)) +
          sizeof(double) * 2 * CB;
 }
 

@@ -426,6 +426,9 @@ struct DriverProg {
   const double* x;
   double* out;
   double t;
+  const double* t_dev;   // optional: time base read on the device (CUDA-graph replay), then the
+  int ninc;              // increments are added one by one in the reference's order
+  double inc[6];
   int nx, npulse;
   double pulses[DRIVER_MAX_PULSES * 7];  // k0, w0, a0, t_L, t_R, t_wL, t_wR
 
@@ -433,6 +436,11 @@ struct DriverProg {
   VPFP_HD void phase(int, long blk, int tid, int nthr, unsigned char*) const {
     long i = blk * nthr + tid;
     if (i >= nx) return;
+    double t = this->t;
+    if (t_dev) {
+      t = t_dev[0];
+      for (int k = 0; k < ninc; ++k) t = t + inc[k];
+    }
     double total = 0.0;
     for (int p = 0; p < npulse; ++p) {
       const double* q = pulses + 7 * p;

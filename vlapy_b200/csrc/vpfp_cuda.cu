@@ -6,6 +6,7 @@
 #include <cuda_runtime.h>
 
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <mutex>
@@ -166,8 +167,8 @@ static int launch_pass13(const fast::FastArgs& fa, cudaStream_t st) {
   constexpr int threads = CB * fast::Geo<L>::TPC;
   const size_t smem = sizeof(cplx) * L * CB;
   long grid;
-  if (MODE == ADV_COLS) grid = (long)fa.nsim * fa.N2 * ((fa.nseq + CB - 1) / CB);
-  else grid = (long)fa.nseq * (fa.N2 / CB);
+  if (MODE == ADV_COLS) grid = (long)fa.nsim * fa.N2 * ((fa.seq_cnt + CB - 1) / CB);
+  else grid = (long)fa.seq_cnt * (fa.N2 / CB);
   if (grid > 2147483647L) return fail(VPFP_ERR_UNSUPPORTED, "grid too large");
   {
     ProfScope ps(MODE == ADV_COLS ? (INV ? "vdfdx.pass3" : "vdfdx.pass1") : (INV ? "edfdv.pass3" : "edfdv.pass1"), st);
@@ -177,32 +178,45 @@ static int launch_pass13(const fast::FastArgs& fa, cudaStream_t st) {
   return VPFP_OK;
 }
 
-template <int L, int MODE>
-static int launch_pass2(const fast::FastArgs& fa, cudaStream_t st) {
+static int g_pass2_prefetch = 0;   // 0: direct loads, 4 CTAs/SM; 1: cp.async staging, 2 CTAs/SM (VPFP_PASS2_PREFETCH)
+
+template <int L, int MODE, bool PF>
+static int launch_pass2_pf(const fast::FastArgs& fa, cudaStream_t st) {
   constexpr int CB = (L == 128) ? 8 : 16;
   constexpr int threads = CB * 2 * fast::Geo<L>::TPC;
-  const size_t smem = fast::pass2_smem<L, CB>(MODE);
+  const size_t smem = fast::pass2_smem<L, CB>(MODE, PF);
   static bool configured = false;
   if (!configured) {
-    int rc = opt_in_smem(fast::pass2_kernel<L, MODE, CB>, smem);
+    int rc = opt_in_smem(fast::pass2_kernel<L, MODE, CB, PF>, smem);
     if (rc) return rc;
     configured = true;
   }
   const int T1 = fa.N1 / 2;
   const int t1_chunk = 8;
   const int nchunks = (T1 + t1_chunk - 1) / t1_chunk;
-  const long grid = (long)(MODE == ADV_COLS ? fa.nsim : 1) * ((fa.nseq + CB - 1) / CB) * nchunks;
+  const long grid = (long)(MODE == ADV_COLS ? fa.nsim : 1) * ((fa.seq_cnt + CB - 1) / CB) * nchunks;
   if (grid > 2147483647L) return fail(VPFP_ERR_UNSUPPORTED, "grid too large");
   {
     ProfScope ps(MODE == ADV_COLS ? "vdfdx.pass2" : "edfdv.pass2", st);
-    fast::pass2_kernel<L, MODE, CB><<<(unsigned)grid, threads, smem, st>>>(fa, t1_chunk);
+    fast::pass2_kernel<L, MODE, CB, PF><<<(unsigned)grid, threads, smem, st>>>(fa, t1_chunk);
   }
   CUDA_TRY(cudaGetLastError());
   return VPFP_OK;
 }
 
+template <int L, int MODE>
+static int launch_pass2(const fast::FastArgs& fa, cudaStream_t st) {
+  static int init = 0;
+  if (!init) {
+    const char* e = getenv("VPFP_PASS2_PREFETCH");
+    if (e) g_pass2_prefetch = atoi(e);
+    init = 1;
+  }
+  return g_pass2_prefetch ? launch_pass2_pf<L, MODE, true>(fa, st) : launch_pass2_pf<L, MODE, false>(fa, st);
+}
+
 template <int MODE>
-static int run_fast_mode(const fast::FastArgs& fa, cudaStream_t st) {
+static int run_three_passes(const fast::FastArgs& fa, cudaStream_t st) {
   int rc;
   if (fa.N1 == 64) rc = launch_pass13<64, MODE, 0>(fa, st); else rc = launch_pass13<128, MODE, 0>(fa, st);
   if (rc) return rc;
@@ -210,6 +224,62 @@ static int run_fast_mode(const fast::FastArgs& fa, cudaStream_t st) {
   if (rc) return rc;
   if (fa.N1 == 64) rc = launch_pass13<64, MODE, 1>(fa, st); else rc = launch_pass13<128, MODE, 1>(fa, st);
   return rc;
+}
+
+// L2-slab execution: the three passes run slab by slab (a slab = a range of packed sequences
+// whose footprint fits the 126 MB L2 several times over), slabs round-robin over a few internal
+// streams, so passes 2 and 3 find their input in L2 and only one read and one write of f reach HBM.
+struct SlabStreams {
+  static const int MAXS = 4;
+  cudaStream_t s[MAXS];
+  cudaEvent_t fork, join[MAXS];
+  bool ready = false;
+};
+static std::map<int, SlabStreams> g_slab_streams;
+static long g_slab_bytes = -1;
+static int g_slab_nstreams = 3;
+
+template <int MODE>
+static int run_fast_mode(fast::FastArgs fa, cudaStream_t st) {
+  if (g_slab_bytes < 0) {
+    const char* e = getenv("VPFP_SLAB_MB");
+    g_slab_bytes = e ? atol(e) * (1L << 20) : 0;
+    const char* n = getenv("VPFP_SLAB_STREAMS");
+    if (n) g_slab_nstreams = atoi(n);
+    if (g_slab_nstreams < 1) g_slab_nstreams = 1;
+    if (g_slab_nstreams > SlabStreams::MAXS) g_slab_nstreams = SlabStreams::MAXS;
+  }
+  const long per_seq = (long)(MODE == ADV_COLS ? fa.nsim : 1) * fa.N * 16;
+  long seqs = g_slab_bytes > 0 ? (g_slab_bytes / per_seq) / 32 * 32 : 0;
+  if (seqs < 32) seqs = (g_slab_bytes > 0) ? 32 : 0;
+  fa.seq_off = 0; fa.seq_cnt = fa.nseq;
+  if (seqs == 0 || seqs >= fa.nseq) return run_three_passes<MODE>(fa, st);
+  int dev = 0;
+  CUDA_TRY(cudaGetDevice(&dev));
+  SlabStreams& ss = g_slab_streams[dev];
+  if (!ss.ready) {
+    for (int i = 0; i < SlabStreams::MAXS; ++i) {
+      CUDA_TRY(cudaStreamCreateWithFlags(&ss.s[i], cudaStreamNonBlocking));
+      CUDA_TRY(cudaEventCreateWithFlags(&ss.join[i], cudaEventDisableTiming));
+    }
+    CUDA_TRY(cudaEventCreateWithFlags(&ss.fork, cudaEventDisableTiming));
+    ss.ready = true;
+  }
+  const int ns = g_slab_nstreams;
+  CUDA_TRY(cudaEventRecord(ss.fork, st));
+  for (int i = 0; i < ns; ++i) CUDA_TRY(cudaStreamWaitEvent(ss.s[i], ss.fork, 0));
+  int k = 0;
+  for (long off = 0; off < fa.nseq; off += seqs, ++k) {
+    fa.seq_off = (int)off;
+    fa.seq_cnt = (int)((off + seqs <= fa.nseq) ? seqs : fa.nseq - off);
+    int rc = run_three_passes<MODE>(fa, ss.s[k % ns]);
+    if (rc) return rc;
+  }
+  for (int i = 0; i < ns; ++i) {
+    CUDA_TRY(cudaEventRecord(ss.join[i], ss.s[i]));
+    CUDA_TRY(cudaStreamWaitEvent(st, ss.join[i], 0));
+  }
+  return VPFP_OK;
 }
 
 static bool fast_eligible(const AdvectProg& a, const AdvectPlan& pl) {
@@ -245,6 +315,7 @@ static int run_advect(AdvectProg a, cudaStream_t st, int flags = VPFP_PHASE_EXAC
     fa.mode = a.mode; fa.exact = (flags & VPFP_PHASE_TABLE) ? 0 : 1;
     fa.N = a.N; fa.N1 = pl.N1; fa.N2 = pl.N2;
     fa.nsim = a.nsim; fa.nseq = a.nseq; fa.nrows = a.nrows;
+    fa.seq_off = 0; fa.seq_cnt = a.nseq;
     fa.fin = a.fin; fa.ld_in = a.ld_in; fa.fout = a.fout; fa.ld_out = a.ld_out;
     fa.kvec = a.kvec; fa.cvec = a.cvec; fa.dt = a.dt; fa.phantom = a.phantom;
     fa.twN = a.tw;
@@ -619,7 +690,19 @@ int vpfp_driver(const double* x, double t, const double* pulses, int npulse, dou
     return fail(VPFP_ERR_ARG, "vpfp_driver: bad argument");
   if (npulse > DRIVER_MAX_PULSES) return fail(VPFP_ERR_UNSUPPORTED, "vpfp_driver: too many pulses");
   DriverProg p;
-  p.x = x; p.out = out; p.t = t; p.nx = nx; p.npulse = npulse;
+  p.x = x; p.out = out; p.t = t; p.t_dev = nullptr; p.ninc = 0; p.nx = nx; p.npulse = npulse;
+  for (int i = 0; i < npulse * 7; ++i) p.pulses[i] = pulses[i];
+  return launch_prog(p, (nx + 255) / 256, 256, 0, 1, (cudaStream_t)stream, "driver");
+}
+
+int vpfp_driver_dev(const double* x, const double* t_dev, const double* incs, int ninc, const double* pulses,
+                    int npulse, double* out, int nx, void* stream) {
+  if (!x || !out || !t_dev || nx <= 0 || npulse < 0 || ninc < 0 || ninc > 6 || (npulse > 0 && !pulses))
+    return fail(VPFP_ERR_ARG, "vpfp_driver_dev: bad argument");
+  if (npulse > DRIVER_MAX_PULSES) return fail(VPFP_ERR_UNSUPPORTED, "vpfp_driver: too many pulses");
+  DriverProg p;
+  p.x = x; p.out = out; p.t = 0.0; p.t_dev = t_dev; p.ninc = ninc; p.nx = nx; p.npulse = npulse;
+  for (int i = 0; i < ninc; ++i) p.inc[i] = incs[i];
   for (int i = 0; i < npulse * 7; ++i) p.pulses[i] = pulses[i];
   return launch_prog(p, (nx + 255) / 256, 256, 0, 1, (cudaStream_t)stream, "driver");
 }

@@ -201,6 +201,34 @@ def driver(x, t, pulses, out=None):
     return out
 
 
+class DevTime:
+    """A time whose base lives in a device scalar (so that a captured CUDA graph can be replayed
+    with a new time); ``+ float`` appends an increment, applied one by one on the device in the
+    order the schedule wrote them (vlapy/core/vlasov_poisson.py:116-148 sums left to right)."""
+    __slots__ = ("base", "incs")
+
+    def __init__(self, base, incs=()):
+        self.base, self.incs = base, tuple(incs)
+
+    def __add__(self, other):
+        return DevTime(self.base, self.incs + (float(other),))
+
+    __radd__ = __add__
+
+
+def driver_dev(x, t, pulses, out=None):
+    """driver(x, t) with t a DevTime"""
+    pulses = np.ascontiguousarray(pulses, dtype=np.float64).reshape(-1, 7)
+    incs = np.asarray(t.incs, dtype=np.float64)
+    if out is None:
+        out = torch.empty_like(x)
+    _lib.check(_lib.lib().vpfp_driver_dev(x.data_ptr(), t.base.data_ptr(), incs.ctypes.data_as(ctypes.c_void_p),
+                                          incs.size, pulses.ctypes.data_as(ctypes.c_void_p), pulses.shape[0],
+                                          out.data_ptr(), x.numel(), _stream()))
+    _count(1)
+    return out
+
+
 def series(mom, e, de, out=None):
     """vlapy/core/step.py:202-224 on device: 7 x-means of one stored step."""
     if out is None:

@@ -9,8 +9,9 @@ the device copies of e and f are kept under private keys for the next call.
 import numpy as np
 import torch
 
+from . import ops
 from .core import step
-from ._util import device
+from ._util import const, device
 
 BACKEND = "b200"
 
@@ -94,12 +95,110 @@ def _device_storage(temp_storage, nt, nx, nv, dev):
     return d, p
 
 
+class _GraphStep:
+    """One timestep captured in a CUDA graph.  Small grids are launch bound: a step
+    is ~25 kernels of a few microseconds, so the Python/launch overhead dominates.  The captured
+    step reads its time and driver row from a small device input buffer and writes everything the
+    storage step records into one staging row, so a replay costs three launches from Python
+    (input copy, graph, staging copy).  Needs the device-side driver (``pulse_dictionary``)."""
+
+    def __init__(self, all_params, stuff, nx, nv, nmodes_shape, modes_complex, dev):
+        self.vp_step, self.fp_step, self.fused, self.store_f = step.get_step_parts(all_params, stuff)
+        self.v_d, self.dv = const(stuff["v"]), float(stuff["dv"])
+        self.nx, self.nv = nx, nv
+        self.inp = torch.zeros(1 + nx, dtype=torch.float64, device=dev)            # [t, driver row]
+        self.e = torch.zeros(nx, dtype=torch.float64, device=dev)
+        self.f = torch.zeros((nx, nv), dtype=torch.float64, device=dev)
+        self.mom = torch.zeros((8, nx), dtype=torch.float64, device=dev)
+        self.n_modes = int(np.prod(nmodes_shape))
+        self.modes_complex = bool(modes_complex)
+        nstage = 8 * nx + 7 + (2 * self.n_modes if self.modes_complex else self.n_modes)
+        self.stage = torch.zeros(nstage, dtype=torch.float64, device=dev)
+        self.graph = None
+
+    def _body(self):
+        nx = self.nx
+        t = ops.DevTime(self.inp[:1])
+        de = self.inp[1:]
+        e, f = self.vp_step(e=self.e, f=self.f, t=t)
+        if self.fused:
+            f = self.fp_step(f, moments_out=self.mom)
+        else:
+            f = self.fp_step(f=f)
+            ops.moments(f, self.v_d, self.dv, nmom=8, out=self.mom)
+        st = self.stage
+        st[0:nx] = e
+        st[nx:2 * nx] = de
+        st[2 * nx:8 * nx] = self.mom[:6].reshape(-1)
+        ops.series(self.mom, e, de, out=st[8 * nx:8 * nx + 7])
+        m = self.store_f(f)
+        tail = st[8 * nx + 7:]
+        tail.copy_(torch.view_as_real(m).reshape(-1) if self.modes_complex else m.reshape(-1))
+        self.e.copy_(e)
+        self.f.copy_(f)
+
+    def capture(self):
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        e0, f0 = self.e.clone(), self.f.clone()
+        with torch.cuda.stream(side):
+            self._body()                        # warm-up: library caches, allocator pools
+        torch.cuda.current_stream().wait_stream(side)
+        self.e.copy_(e0)
+        self.f.copy_(f0)
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self._body()
+        self.e.copy_(e0)
+        self.f.copy_(f0)
+
+
+GRAPH_MAX_CELLS = 1 << 22      # above this a step is no longer launch bound (and the extra copy of f would cost)
+
+
 def get_inner_loop_stepper(all_params, stuff_for_time_loop, steps_in_loop):
-    """vlapy/outer_loop.py:248-281: inner_loop(time_array, driver_array, temp_storage)."""
+    """vlapy/outer_loop.py:248-281: inner_loop(time_array, driver_array, temp_storage).
+
+    ``all_params["backend"]["cuda_graph"]``: "auto" (default: graphs for grids up to 2^22 cells when
+    the device-side driver is available), True or False."""
     if all_params["backend"]["core"] != BACKEND:
         raise NotImplementedError(
             "The backend: <" + all_params["backend"]["core"] + "> has not yet been implemented")
     one_step = step.get_timestep(all_params=all_params, stuff_for_time_loop=stuff_for_time_loop)
+    graph_opt = all_params["backend"].get("cuda_graph", "auto")
+    graph_state = {}
+
+    def want_graph(nx, nv):
+        if graph_opt is False or stuff_for_time_loop.get("pulse_dictionary") is None:
+            return False
+        return graph_opt is True or nx * nv <= GRAPH_MAX_CELLS
+
+    def run_graph(time_array, drv, d, nx, nv):
+        gs = graph_state.get("gs")
+        if gs is None:
+            gs = _GraphStep(all_params, stuff_for_time_loop, nx, nv, tuple(d["stored_f"].shape[1:]),
+                            d["stored_f"].is_complex(), drv.device)
+            gs.e.copy_(d["e"]); gs.f.copy_(d["f"])
+            gs.capture()
+            graph_state["gs"] = gs
+        gs.e.copy_(d["e"]); gs.f.copy_(d["f"])
+        nt = steps_in_loop
+        inputs = torch.empty((nt, 1 + nx), dtype=torch.float64, device=drv.device)
+        inputs[:, 0] = torch.as_tensor(np.asarray(time_array, dtype=np.float64)).to(drv.device)
+        inputs[:, 1:] = drv
+        rows = torch.empty((nt, gs.stage.numel()), dtype=torch.float64, device=drv.device)
+        for it in range(nt):
+            gs.inp.copy_(inputs[it])
+            gs.graph.replay()
+            rows[it].copy_(gs.stage)
+        d["e"], d["f"] = gs.e.clone(), gs.f.clone()
+        d["fields"].copy_(rows[:, :8 * nx].reshape(nt, 8, nx).permute(1, 0, 2))
+        d["series_rows"].copy_(rows[:, 8 * nx:8 * nx + 7])
+        tail = rows[:, 8 * nx + 7:]
+        if gs.modes_complex:
+            d["stored_f"].copy_(torch.view_as_complex(tail.reshape(nt, -1, 2).contiguous()).reshape(d["stored_f"].shape))
+        else:
+            d["stored_f"].copy_(tail.reshape(d["stored_f"].shape))
 
     def inner_loop(time_array, driver_array, temp_storage):
         dev = device()
@@ -107,18 +206,21 @@ def get_inner_loop_stepper(all_params, stuff_for_time_loop, steps_in_loop):
         d, pin = _device_storage(temp_storage, steps_in_loop, nx, nv, dev)
         # host -> device: the driver rows of this loop (asynchronous when the caller pinned them)
         drv = torch.as_tensor(np.ascontiguousarray(driver_array, dtype=np.float64)).to(dev, non_blocking=True)
-        work = {
-            "time_batch": np.asarray(time_array, dtype=np.float64),
-            "driver_array_batch": drv,
-            "e": d["e"], "f": d["f"],
-            "stored_f": d["stored_f"],
-            "fields": {k: d["fields"][j] for j, k in enumerate(step.FIELD_KEYS)},
-            "series": {"_rows": d["series_rows"]},
-            "_moment_scratch": d["moments"],
-        }
-        for it in range(steps_in_loop):
-            work, _ = one_step(work, it)
-        d["e"], d["f"] = work["e"], work["f"]
+        if want_graph(nx, nv):
+            run_graph(time_array, drv, d, nx, nv)
+        else:
+            work = {
+                "time_batch": np.asarray(time_array, dtype=np.float64),
+                "driver_array_batch": drv,
+                "e": d["e"], "f": d["f"],
+                "stored_f": d["stored_f"],
+                "fields": {k: d["fields"][j] for j, k in enumerate(step.FIELD_KEYS)},
+                "series": {"_rows": d["series_rows"]},
+                "_moment_scratch": d["moments"],
+            }
+            for it in range(steps_in_loop):
+                work, _ = one_step(work, it)
+            d["e"], d["f"] = work["e"], work["f"]
         # device -> host once per inner loop (the storage cadence of vlapy/manager.py:138-150),
         # into pinned mirrors; the returned arrays are views that the next call overwrites, as the
         # reference's in-place temp_storage arrays are.
