@@ -38,7 +38,10 @@ WORKLOADS = {
     "c3": (4096, 4096, "C3: collisional NLEPW (k0=0.35, leapfrog+LB) 4096x4096 fp64"),
     "c2": (256, 2048, "C2: NLEPW as run_nlepw.py (k0=0.35, leapfrog+LB) 256x2048 fp64"),
     "c1": (32, 512, "C1: Landau damping (tests/test_landau_damping.py grid, collisionless leapfrog) 32x512 fp64"),
+    "c4": (256, 512, "C4: k-sweep ensemble of 1024 independent Landau-damping simulations, 256x512 fp64 each, "
+                     "sharded by simulation"),
 }
+C4_BATCH = 1024
 EPW = {0.3: (1.1598464805919155, -0.012620368421117013), 0.35: (1.220953506161683, -0.03431805085829906)}
 
 
@@ -67,6 +70,112 @@ def make_config(workload, nx=None, nv=None):
     nu = 0.0 if landau else abs(nu_ld) * 1e-4
     return dict(nx=nx, nv=nv, k0=k0, x=x, kx=kx, one_over_kx=ook, v=v, dv=dv, kv=kv, dt=dt, nu=nu,
                 pulses=pulses, desc=desc, vmax=vmax)
+
+
+def epw_root(k0):
+    """EPW dispersion root as vlapy/diagnostics/z_function.py:26-50 (setup only)."""
+    from scipy import optimize, special
+    zp = lambda x: -2.0 * (1.0 + x * (1j * np.sqrt(np.pi) * special.wofz(x)))   # noqa: E731
+    chi = (1.0 / k0) ** 2.0 / 2.0
+    r = optimize.newton(lambda x: 1.0 - chi * zp(x), np.sqrt(1.0 + 3 * k0 ** 2.0))
+    return r * k0 * np.sqrt(2.0)
+
+
+def ensemble_arm(args):
+    """C4: batch of independent simulations, sharded by simulation over the ranks (no collective)."""
+    import torch
+    import torch.distributed as dist
+    from vlapy_b200 import ensemble, ops
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    nx, nv, desc = WORKLOADS["c4"]
+    nx, nv = args.nx or nx, args.nv or nv
+    lo, hi = ensemble.shard(C4_BATCH, rank, world)
+    k0s = np.linspace(0.25, 0.45, C4_BATCH)[lo:hi]
+    B = hi - lo
+    vmax = 6.4
+    dv = 2 * vmax / nv
+    v = np.linspace(-vmax + dv / 2.0, vmax - dv / 2.0, nv)
+    kv = np.fft.fftfreq(nv, d=dv) * 2.0 * np.pi
+    dt = np.linspace(0, 80, 500)[1]
+    xs, kxs, ooks, pulses = [], [], [], []
+    for k0 in k0s:
+        xmax = 2.0 * np.pi / k0
+        dx = xmax / nx
+        xs.append(np.linspace(dx / 2.0, xmax - dx / 2.0, nx))
+        kx = np.fft.fftfreq(nx, d=dx) * 2.0 * np.pi
+        ook = np.zeros_like(kx); ook[1:] = 1.0 / kx[1:]
+        kxs.append(kx); ooks.append(ook)
+        w0 = float(np.real(epw_root(k0)))
+        pulses.append({"p": {"k0": k0, "w0": w0, "a0": 1e-7, "t_L": 6, "t_R": 20, "t_wL": 2.5, "t_wR": 2.5}})
+    stuff = dict(kx=np.stack(kxs), one_over_kx=np.stack(ooks), x=np.stack(xs), v=v, kv=kv, dv=dv, dt=dt, nu=0.0,
+                 pulses=pulses)
+    params = {"nu": 0.0, "vlasov-poisson": {"time": "leapfrog", "vdfdx": "exponential", "edfdv": "exponential",
+                                            "poisson": "spectral"}, "fokker-planck": {"type": "lb"}}
+    step_fn = ensemble.get_ensemble_timestep(params, stuff)
+    fv = np.exp(-v ** 2 / 2.0); fv /= (dv * (fv[1:] + fv[:-1]) / 2.0).sum()
+    f_host = torch.empty((B, nx, nv), dtype=torch.float64, pin_memory=True)
+    f_host.numpy()[:] = fv[None, None, :]
+    state = {"e": torch.zeros((B, nx), dtype=torch.float64, device=dev), "f": f_host.to(dev)}
+    K, W = args.steps, args.warmup
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+    for i in range(W):
+        state = step_fn(state, dt * i)
+    barrier()
+    sampler = ClockSampler(local_rank); sampler.start()
+    ops.launch_count = 0
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for i in range(W, W + K):
+        state = step_fn(state, dt * i)
+    ev1.record()
+    barrier()
+    ms = ev0.elapsed_time(ev1)
+    launches = ops.launch_count
+    clocks = sampler.summary()
+    mean_n = float(state["series"][:, 0].mean())
+    # end to end: upload the shard's state, K steps, download state + series
+    barrier()
+    t0 = time.perf_counter()
+    st = {"e": torch.zeros((B, nx), dtype=torch.float64, device=dev), "f": f_host.to(dev, non_blocking=True)}
+    for i in range(K):
+        st = step_fn(st, dt * i)
+    back = torch.empty((B, nx, nv), dtype=torch.float64, pin_memory=True)
+    back.copy_(st["f"], non_blocking=True)
+    st["series"].cpu(); st["e"].cpu()
+    barrier()
+    sec = time.perf_counter() - t0
+    tms = torch.tensor([ms, sec], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+    if rank == 0:
+        ms, sec = float(tms[0]), float(tms[1])
+        cells = C4_BATCH * nx * nv
+        peak, peak_src = peaks()
+        line = {"metric": "phase-space cell-updates/s (full VPFP timestep)", "value": cells * K / (ms * 1e-3),
+                "unit": "cell-updates/s", "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms / K,
+                "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": {"workload": desc, "nx": nx, "nv": nv, "batch": C4_BATCH, "integrator": "leapfrog",
+                           "collisions": "none", "parallelism": "%d simulations per GPU, no collective" % B},
+                "clocks": clocks, "gpu_launches": launches,
+                "roofline": {"bound": "hbm", "kernel": "whole step", "achieved": 48.0 * cells / world / (ms / K * 1e-3) / 1e9,
+                             "peak": peak, "unit": "GB/s", "frac": 48.0 * cells / world / (ms / K * 1e-3) / 1e9 / peak,
+                             "traffic": None, "peak_source": peak_src},
+                "e2e": {"value": cells * K / sec, "unit": "cell-updates/s",
+                        "h2d_bytes_per_step": C4_BATCH * nx * nv * 8 / K, "d2h_bytes_per_step": C4_BATCH * nx * nv * 8 / K},
+                "mean_n_last_step": mean_n}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
 
 
 def host_driver(cfg):
@@ -388,6 +497,8 @@ def main():
     args = ap.parse_args()
     if args.impl == "reference":
         reference_arm(args)
+    elif args.workload == "c4":
+        ensemble_arm(args)
     else:
         gpu_arm(args)
 

@@ -133,6 +133,16 @@ int vpfp_driver_dev(const double *x, const double *t_dev, const double *incs, in
 int vpfp_series(const double *moments, long mom_ld, const double *e, const double *de,
                 double *out, int nx, void *stream);
 
+/* Ensembles of independent simulations (BASELINE config 4): simulation b owns rows
+ * b*nx .. b*nx+nx-1 of every per-x array.  vpfp_series_batch writes out[b*7 + k];
+ * vpfp_driver_batch evaluates the driver with per-simulation grids x[batch][nx] and pulse
+ * parameters pulses_dev[batch][npulse][7] (device memory); t_dev may be NULL (then t is used). */
+int vpfp_series_batch(const double *moments, long mom_ld, const double *e, const double *de,
+                      double *out, int nx, int batch, void *stream);
+int vpfp_driver_batch(const double *x, double t, const double *t_dev, const double *incs, int ninc,
+                      const double *pulses_dev, int npulse, double *out, int nx, int batch,
+                      void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -429,6 +429,37 @@ def test_cuda_graph_inner_loop_equals_eager(dev):
     assert rel_err(g["f"], f_ref) < TOL
 
 
+@pytest.mark.parametrize("integ,nu_log", [("leapfrog", None), ("pefrl", -2)])
+def test_ensemble_matches_independent_oracle_runs(dev, integ, nu_log):
+    """BASELINE config 4 in miniature: a k-sweep of independent simulations in one batch; every
+    member must follow the reference's timestep exactly as if it ran alone."""
+    from vlapy_b200 import ensemble
+    k0s = [0.27, 0.3, 0.35, 0.41, 0.44]
+    cfgs = [O.make_config(32, 128, k0, tmax=80, nt=500, a0=1e-3, t_R=20, log_nu_over_nu_ld=nu_log) for k0 in k0s]
+    nu = cfgs[1]["nu"]
+    for c in cfgs:
+        c["nu"] = nu                      # one collision frequency for the whole batch
+    stuff = dict(kx=np.stack([c["kx"] for c in cfgs]), one_over_kx=np.stack([c["one_over_kx"] for c in cfgs]),
+                 x=np.stack([c["x"] for c in cfgs]), v=cfgs[0]["v"], kv=cfgs[0]["kv"], dv=cfgs[0]["dv"],
+                 dt=cfgs[0]["dt"], nu=nu, pulses=[c["pulses"] for c in cfgs])
+    params = make_params(cfgs[0], integ, "lb")
+    step_fn = ensemble.get_ensemble_timestep(params, stuff)
+    state = {"e": torch.from_numpy(np.stack([c["e0"] for c in cfgs])).to(dev),
+             "f": torch.from_numpy(np.stack([c["f0"] for c in cfgs])).to(dev)}
+    nsteps = 6
+    for i in range(nsteps):
+        state = step_fn(state, cfgs[0]["dt"] * i)
+    f, e = state["f"].cpu().numpy(), state["e"].cpu().numpy()
+    mom, ser = state["moments"].cpu().numpy(), state["series"].cpu().numpy()
+    for b, c in enumerate(cfgs):
+        e_ref, f_ref, hist = O.run_steps(c, nsteps, integ, "lb", collect=True)
+        assert rel_err(f[b], f_ref) < TOL
+        assert np.max(np.abs(e[b] - e_ref)) < 1e-13
+        assert rel_err(mom[:3, b], hist["mom"][-1][:3]) < TOL
+        np.testing.assert_allclose(ser[b, :6], hist["series"][-1][:6], rtol=1e-9, atol=1e-13)
+    assert ensemble.shard(1024, 3, 8) == (384, 512) and ensemble.shard(10, 3, 4) == (9, 10)
+
+
 def test_smoke_entry(dev):
     import __graft_entry__ as ge
     assert ge.smoke()

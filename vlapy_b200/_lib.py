@@ -55,6 +55,8 @@ _SIGS = {
     "vpfp_xmodes_partial": ([_P, _L, _P, _I, _I, _I, _I, _I, _I, _P], _I),
     "vpfp_driver": ([_P, _D, _P, _I, _P, _I, _P], _I),
     "vpfp_driver_dev": ([_P, _P, _P, _I, _P, _I, _P, _I, _P], _I),
+    "vpfp_series_batch": ([_P, _L, _P, _P, _P, _I, _I, _P], _I),
+    "vpfp_driver_batch": ([_P, _D, _P, _P, _I, _P, _I, _P, _I, _I, _P], _I),
     "vpfp_series": ([_P, _L, _P, _P, _P, _I, _P], _I),
 }
 

@@ -451,6 +451,38 @@ struct DriverProg {
   }
 };
 
+// Ensemble driver: simulation b has its own grid row x[b*nx ...] and pulse parameters
+// pulses[b][npulse][7] (device memory); one time for all.
+struct DriverBatchProg {
+  const double* x;
+  const double* pulses;
+  double* out;
+  double t;
+  const double* t_dev;
+  int ninc;
+  double inc[6];
+  int nx, npulse, batch;
+
+  VPFP_HD int nphases() const { return 1; }
+  VPFP_HD void phase(int, long blk, int tid, int nthr, unsigned char*) const {
+    long i = blk * nthr + tid;
+    if (i >= (long)nx * batch) return;
+    double t = this->t;
+    if (t_dev) {
+      t = t_dev[0];
+      for (int k = 0; k < ninc; ++k) t = t + inc[k];
+    }
+    const double* q0 = pulses + (i / nx) * npulse * 7;
+    double total = 0.0;
+    for (int p = 0; p < npulse; ++p) {
+      const double* q = q0 + 7 * p;
+      double env = 0.5 * (tanh((t - q[3]) / q[5]) - tanh((t - q[4]) / q[6]));
+      total += env * q[0] * q[2] * sin(q[0] * x[i] - q[1] * t);
+    }
+    out[i] = total;
+  }
+};
+
 // ---------------------------------------------------------------------------------------------
 // Series means of one step (vlapy/core/step.py:202-224): single CTA.
 // out = [mean n, mean j, mean T, mean e^2, mean de^2, mean int f^2, mean int f ln f]
@@ -464,25 +496,27 @@ struct SeriesProg {
   int nx;
   VPFP_HD int nphases(int nthr) const { return 2 + tree_phases(nthr); }
   VPFP_HD long smem_bytes(int nthr) const { return (long)7 * nthr * sizeof(double); }
-  VPFP_HD void phase(int ph, long, int tid, int nthr, unsigned char* smem) const {
+  // blk = simulation index of an ensemble (rows blk*nx .. blk*nx + nx - 1 of the moment arrays)
+  VPFP_HD void phase(int ph, long blk, int tid, int nthr, unsigned char* smem) const {
     double* part = reinterpret_cast<double*>(smem);
     const int nt = tree_phases(nthr);
+    const long o = blk * nx;
     if (ph == 0) {
       double a[7] = {0, 0, 0, 0, 0, 0, 0};
       for (int i = tid; i < nx; i += nthr) {
-        a[0] += mom[0 * mom_ld + i];
-        a[1] += mom[1 * mom_ld + i];
-        a[2] += mom[2 * mom_ld + i];
-        a[3] += e[i] * e[i];
-        a[4] += de ? de[i] * de[i] : 0.0;
-        a[5] += mom[6 * mom_ld + i];
-        a[6] += mom[7 * mom_ld + i];
+        a[0] += mom[0 * mom_ld + o + i];
+        a[1] += mom[1 * mom_ld + o + i];
+        a[2] += mom[2 * mom_ld + o + i];
+        a[3] += e[o + i] * e[o + i];
+        a[4] += de ? de[o + i] * de[o + i] : 0.0;
+        a[5] += mom[6 * mom_ld + o + i];
+        a[6] += mom[7 * mom_ld + o + i];
       }
       for (int k = 0; k < 7; ++k) part[(long)k * nthr + tid] = a[k];
     } else if (ph <= nt) {
       tree_step(ph - 1, nthr, 7, tid, nthr, part);
     } else if (tid < 7) {
-      out[tid] = part[(long)tid * nthr] / (double)nx;
+      out[blk * 7 + tid] = part[(long)tid * nthr] / (double)nx;
     }
   }
 };

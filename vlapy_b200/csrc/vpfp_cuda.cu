@@ -707,14 +707,31 @@ int vpfp_driver_dev(const double* x, const double* t_dev, const double* incs, in
   return launch_prog(p, (nx + 255) / 256, 256, 0, 1, (cudaStream_t)stream, "driver");
 }
 
-int vpfp_series(const double* moments, long mom_ld, const double* e, const double* de, double* out,
-                int nx, void* stream) {
-  if (!moments || !e || !out || nx <= 0) return fail(VPFP_ERR_ARG, "vpfp_series: bad argument");
+int vpfp_series_batch(const double* moments, long mom_ld, const double* e, const double* de, double* out,
+                      int nx, int batch, void* stream) {
+  if (!moments || !e || !out || nx <= 0 || batch <= 0) return fail(VPFP_ERR_ARG, "vpfp_series: bad argument");
   SeriesProg p;
   p.mom = moments; p.mom_ld = mom_ld; p.e = e; p.de = de; p.out = out; p.nx = nx;
   int threads = 256;
   while (threads > 32 && threads > nx) threads >>= 1;
-  return launch_prog(p, 1, threads, p.smem_bytes(threads), p.nphases(threads), (cudaStream_t)stream, "series");
+  return launch_prog(p, batch, threads, p.smem_bytes(threads), p.nphases(threads), (cudaStream_t)stream, "series");
+}
+
+int vpfp_series(const double* moments, long mom_ld, const double* e, const double* de, double* out,
+                int nx, void* stream) {
+  return vpfp_series_batch(moments, mom_ld, e, de, out, nx, 1, stream);
+}
+
+int vpfp_driver_batch(const double* x, double t, const double* t_dev, const double* incs, int ninc,
+                      const double* pulses_dev, int npulse, double* out, int nx, int batch, void* stream) {
+  if (!x || !out || !pulses_dev || nx <= 0 || batch <= 0 || npulse < 1 || ninc < 0 || ninc > 6)
+    return fail(VPFP_ERR_ARG, "vpfp_driver_batch: bad argument");
+  DriverBatchProg p;
+  p.x = x; p.pulses = pulses_dev; p.out = out; p.t = t; p.t_dev = t_dev; p.ninc = t_dev ? ninc : 0;
+  for (int i = 0; i < p.ninc; ++i) p.inc[i] = incs[i];
+  p.nx = nx; p.npulse = npulse; p.batch = batch;
+  const long n = (long)nx * batch;
+  return launch_prog(p, (n + 255) / 256, 256, 0, 1, (cudaStream_t)stream, "driver");
 }
 
 }  // extern "C"
