@@ -30,7 +30,7 @@ extern "C" {
 /* flags for the advection operators */
 #define VPFP_PHASE_EXACT 0   /* per-bin sincos of theta = (k*dt)*c, the reference's own rounding */
 #define VPFP_PHASE_TABLE 1   /* geometric phase tables (needs a uniform fftfreq wavenumber grid);
-                              * honoured by the register-resident kernels (4096 <= N <= 16384),
+                              * honoured by the register-resident kernels (256 <= N <= 16384),
                               * the generic kernels always use the exact phases */
 #define VPFP_FORCE_GENERIC 2 /* testing: skip the register-resident kernels */
 

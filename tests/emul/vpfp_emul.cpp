@@ -140,9 +140,9 @@ int emul_xmodes(const double* f, long ld, double* out, int nmodes, int batch, in
   p.x_offset = 0; p.nx_total = nx;
   const int threads = 128;
   p.cblocks = (ncols + threads - 1) / threads;
-  int xch = nx / 64;
+  int xch = nx / 128;
   if (xch < 1) xch = 1;
-  if (xch > 64) xch = 64;
+  if (xch > 32) xch = 32;
   p.xchunks = xch;
   std::vector<double> partial((size_t)batch * xch * nmodes * ncols * 2);
   p.partial = partial.data();

@@ -116,23 +116,26 @@ def test_vdfdx_sizes_vs_oracle(dev, shape):
 
 
 @pytest.mark.parametrize("flags", [0, 1, 2])
-@pytest.mark.parametrize("n", [4096, 8192, 16384])
+@pytest.mark.parametrize("n", [256, 512, 1024, 2048, 4096, 8192, 16384])
 def test_fast_and_generic_kernels_agree_with_oracle(dev, n, flags):
     """register-resident kernels with exact phases (0) and geometric tables (1), and the generic
     phase program (2), on white-noise-dominated input at the sizes the fast path serves."""
     from vlapy_b200 import ops
     rng = np.random.default_rng(n + flags)
-    # e df/dv: 5 rows (odd: phantom partner) of length n
+    # e df/dv: an odd number of rows (phantom partner) of length n; enough cells (> 2^22) for the
+    # three-pass kernels to be chosen at every n
     dv, v, kv = O.velocity_grid(6.4, n)
-    f = rng.standard_normal((5, n))
-    e = 0.3 * rng.standard_normal(5)
+    nrows = max(5, (1 << 22) // n + 1)
+    f = rng.standard_normal((nrows, n))
+    e = 0.3 * rng.standard_normal(nrows)
     out = ops.edfdv_exp(torch.from_numpy(f).to(dev), torch.from_numpy(e).to(dev), torch.from_numpy(kv).to(dev),
                         0.125, flags=flags)
     assert rel_err(out.cpu().numpy(), O.edfdv_exponential(f, e, 0.125, kv)) < TOL
-    # v df/dx: n rows, 36 columns (ragged tile), two simulations with their own kx
-    vv = np.linspace(-6.4, 6.4, 36)
+    # v df/dx: n rows, a ragged number of columns, two simulations with their own kx
+    ncols = max(36, 2 * (((1 << 21) // n) // 2) + 4)
+    vv = np.linspace(-6.4, 6.4, ncols)
     kxs = np.stack([O.spatial_grid(0.0, 2 * np.pi / k0, n)[2] for k0 in (0.3, 0.41)])
-    g = rng.standard_normal((2, n, 36))
+    g = rng.standard_normal((2, n, ncols))
     out = ops.vdfdx_exp(torch.from_numpy(g).to(dev), torch.from_numpy(kxs).to(dev), torch.from_numpy(vv).to(dev),
                         0.25, flags=flags)
     for b in range(2):

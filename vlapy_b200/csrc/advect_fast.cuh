@@ -112,11 +112,10 @@ __global__ void __launch_bounds__(CB* Geo<L>::TPC) pass13_kernel(const FastArgs 
     seq = a.seq_off + bt * CB + b;
     valid = seq < a.seq_off + a.seq_cnt;
   } else {
-    const int tiles_b = a.N2 / CB;
-    const int bt = blockIdx.x % tiles_b;
-    seq = a.seq_off + blockIdx.x / tiles_b;
-    n2 = bt * CB + b;
-    valid = true;
+    const long gl = (long)blockIdx.x * CB + b;        // lanes enumerate (sequence, n2)
+    seq = a.seq_off + (int)(gl / a.N2);
+    n2 = (int)(gl % a.N2);
+    valid = seq < a.seq_off + a.seq_cnt;
   }
   const long N2 = a.N2;
   cplx x[16];
@@ -188,14 +187,16 @@ __global__ void __launch_bounds__(CB* Geo<L>::TPC) pass13_kernel(const FastArgs 
         const int ncols = 2 * a.nseq;
         const double wa = (valid ? ((2 * seq == 0 && (a.edge_flags & 1)) ? 0.5 * a.dv : a.dv) : 0.0);
         const double wb = (valid ? ((2 * seq + 1 == ncols - 1 && (a.edge_flags & 2)) ? 0.5 * a.dv : a.dv) : 0.0);
+        constexpr int NSUB = (CB > 32) ? CB / 32 : 1;               // warps per column tile
         const int tiles_b = (a.seq_cnt + CB - 1) / CB;
-        const int bt = a.seq_off / CB + blockIdx.x % tiles_b;      // global column-tile index
+        const int bt = (a.seq_off / CB + blockIdx.x % tiles_b) * NSUB + (CB > 32 ? b / 32 : 0);
 #pragma unroll
         for (int j = 0; j < R1; ++j) {
           double d = wa * x[q * R1 + j].x + wb * x[q * R1 + j].y;
 #pragma unroll
           for (int o = (CB < 32 ? CB : 32) / 2; o > 0; o >>= 1) d += __shfl_xor_sync(0xffffffffu, d, o);
-          if (b == 0) a.dens_partial[((long)bt * a.nsim + sim) * a.N + (long)(r + 8 * j) * N2 + n2] = d;
+          if ((b & 31) == 0 || (CB < 32 && b == 0))
+            a.dens_partial[((long)bt * a.nsim + sim) * a.N + (long)(r + 8 * j) * N2 + n2] = d;
         }
       }
     }
@@ -459,7 +460,7 @@ __global__ void __launch_bounds__(CB * 2 * Geo<L>::TPC, PF ? 2 : 4) pass2_kernel
         } else {
           const int k2 = (int)((kbin - k1) / N1);           // 0..L-1
           const int j = neg ? (L - k2) : k2;                // |signed k2| in 0..HALF
-          const bool hoisted = (!special) || (k1 == 0 && ((k2 & 7) == 0));
+          const bool hoisted = (R1 % 8 == 0) && ((!special) || (k1 == 0 && ((k2 & 7) == 0)));
           cplx la = hoisted ? (neg ? loN_a : loP_a) : PT[b * NPT + (j & 7)];
           cplx lb = hoisted ? (neg ? loN_b : loP_b) : PT[(CB + b) * NPT + (j & 7)];
           cplx ta_ = cmul(PT[b * NPT + 8 + (j >> 3)], la);

@@ -81,8 +81,17 @@ VPFP_HD void fft16(cplx* x) {
 
 template <int R, int DIR>
 VPFP_HD void fftR(cplx* x) {
-  if (R == 8) fft8<DIR>(x);
-  else fft16<DIR>(x);
+  if (R == 2) {
+    const cplx a = x[0], b = x[1];
+    x[0] = cadd(a, b);
+    x[1] = csub(a, b);
+  } else if (R == 4) {
+    fft4<DIR>(x[0], x[1], x[2], x[3]);
+  } else if (R == 8) {
+    fft8<DIR>(x);
+  } else {
+    fft16<DIR>(x);
+  }
 }
 
 }  // namespace fast

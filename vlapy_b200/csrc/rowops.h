@@ -379,25 +379,54 @@ struct XmodesProg {
     int j = cb * nthr + tid;
     if (j >= ncols) return;
     int x0 = (int)((long)nx * xc / xchunks), x1 = (int)((long)nx * (xc + 1) / xchunks);
-    for (int mth = 0; mth < nmodes; ++mth) {
-      const double ang = -2.0 * 3.14159265358979323846 * (double)mth / (double)nx_total;
-      double sr = 0.0, si = 0.0;
-      double wr = 1.0, wi = 0.0, cr = 1.0, ci = 0.0;
-      if (mth > 0) {
-        sincos_hd(ang * (double)(x0 + x_offset), &wi, &wr);
-        sincos_hd(ang, &ci, &cr);
+    const double* col = f + ((long)b * nx) * ld + j;
+    // mode 0 and modes 1.. in one sweep over the rows; four rows in flight per iteration
+    double s0 = 0.0;
+    double sr[4], si[4];
+    double wr[4], wi[4], cr[4], ci[4];
+    const int nm = nmodes < 5 ? nmodes : 5;
+    for (int m = 1; m < nm; ++m) {
+      const double ang = -2.0 * 3.14159265358979323846 * (double)m / (double)nx_total;
+      sincos_hd(ang * (double)(x0 + x_offset), &wi[m - 1], &wr[m - 1]);
+      sincos_hd(ang, &ci[m - 1], &cr[m - 1]);
+      sr[m - 1] = 0.0; si[m - 1] = 0.0;
+    }
+    int x = x0;
+    for (; x + 4 <= x1; x += 4) {
+      double v0 = col[(long)x * ld], v1 = col[(long)(x + 1) * ld], v2 = col[(long)(x + 2) * ld],
+             v3 = col[(long)(x + 3) * ld];
+      double vv[4] = {v0, v1, v2, v3};
+      s0 += (v0 + v1) + (v2 + v3);
+      for (int m = 1; m < nm; ++m) {
+        double a = wr[m - 1], bb = wi[m - 1];
+        for (int q = 0; q < 4; ++q) {
+          sr[m - 1] += vv[q] * a;
+          si[m - 1] += vv[q] * bb;
+          double na = a * cr[m - 1] - bb * ci[m - 1];
+          bb = a * ci[m - 1] + bb * cr[m - 1];
+          a = na;
+        }
+        wr[m - 1] = a; wi[m - 1] = bb;
       }
-      for (int x = x0; x < x1; ++x) {
-        double val = f[((long)b * nx + x) * ld + j];
-        sr += val * wr;
-        si += val * wi;
-        double nr = wr * cr - wi * ci;
-        wi = wr * ci + wi * cr;
-        wr = nr;
+    }
+    for (; x < x1; ++x) {
+      double val = col[(long)x * ld];
+      s0 += val;
+      for (int m = 1; m < nm; ++m) {
+        sr[m - 1] += val * wr[m - 1];
+        si[m - 1] += val * wi[m - 1];
+        double na = wr[m - 1] * cr[m - 1] - wi[m - 1] * ci[m - 1];
+        wi[m - 1] = wr[m - 1] * ci[m - 1] + wi[m - 1] * cr[m - 1];
+        wr[m - 1] = na;
       }
-      long o = ((((long)b * xchunks + xc) * nmodes + mth) * ncols + j) * 2;
-      partial[o] = sr;
-      partial[o + 1] = si;
+    }
+    long o = ((((long)b * xchunks + xc) * nmodes + 0) * ncols + j) * 2;
+    partial[o] = s0;
+    partial[o + 1] = 0.0;
+    for (int m = 1; m < nm; ++m) {
+      o = ((((long)b * xchunks + xc) * nmodes + m) * ncols + j) * 2;
+      partial[o] = sr[m - 1];
+      partial[o + 1] = si[m - 1];
     }
   }
 };

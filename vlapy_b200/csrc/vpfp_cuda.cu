@@ -163,12 +163,12 @@ static int opt_in_smem(Kern kern, size_t smem) {
 
 template <int L, int MODE, int INV>
 static int launch_pass13(const fast::FastArgs& fa, cudaStream_t st) {
-  constexpr int CB = (L == 128) ? 16 : 32;
+  constexpr int CB = (L == 128) ? 16 : (L == 64 ? 32 : 64);
   constexpr int threads = CB * fast::Geo<L>::TPC;
   const size_t smem = sizeof(cplx) * L * CB;
   long grid;
   if (MODE == ADV_COLS) grid = (long)fa.nsim * fa.N2 * ((fa.seq_cnt + CB - 1) / CB);
-  else grid = (long)fa.seq_cnt * (fa.N2 / CB);
+  else grid = ((long)fa.seq_cnt * fa.N2 + CB - 1) / CB;
   if (grid > 2147483647L) return fail(VPFP_ERR_UNSUPPORTED, "grid too large");
   {
     ProfScope ps(MODE == ADV_COLS ? (INV ? "vdfdx.pass3" : "vdfdx.pass1") : (INV ? "edfdv.pass3" : "edfdv.pass1"), st);
@@ -182,7 +182,7 @@ static int g_pass2_prefetch = 0;   // 0: direct loads, 4 CTAs/SM; 1: cp.async st
 
 template <int L, int MODE, bool PF>
 static int launch_pass2_pf(const fast::FastArgs& fa, cudaStream_t st) {
-  constexpr int CB = (L == 128) ? 8 : 16;
+  constexpr int CB = (L == 128) ? 8 : (L == 64 ? 16 : 32);
   constexpr int threads = CB * 2 * fast::Geo<L>::TPC;
   const size_t smem = fast::pass2_smem<L, CB>(MODE, PF);
   static bool configured = false;
@@ -218,11 +218,26 @@ static int launch_pass2(const fast::FastArgs& fa, cudaStream_t st) {
 template <int MODE>
 static int run_three_passes(const fast::FastArgs& fa, cudaStream_t st) {
   int rc;
-  if (fa.N1 == 64) rc = launch_pass13<64, MODE, 0>(fa, st); else rc = launch_pass13<128, MODE, 0>(fa, st);
+  switch (fa.N1) {
+    case 16: rc = launch_pass13<16, MODE, 0>(fa, st); break;
+    case 32: rc = launch_pass13<32, MODE, 0>(fa, st); break;
+    case 64: rc = launch_pass13<64, MODE, 0>(fa, st); break;
+    default: rc = launch_pass13<128, MODE, 0>(fa, st); break;
+  }
   if (rc) return rc;
-  if (fa.N2 == 64) rc = launch_pass2<64, MODE>(fa, st); else rc = launch_pass2<128, MODE>(fa, st);
+  switch (fa.N2) {
+    case 16: rc = launch_pass2<16, MODE>(fa, st); break;
+    case 32: rc = launch_pass2<32, MODE>(fa, st); break;
+    case 64: rc = launch_pass2<64, MODE>(fa, st); break;
+    default: rc = launch_pass2<128, MODE>(fa, st); break;
+  }
   if (rc) return rc;
-  if (fa.N1 == 64) rc = launch_pass13<64, MODE, 1>(fa, st); else rc = launch_pass13<128, MODE, 1>(fa, st);
+  switch (fa.N1) {
+    case 16: rc = launch_pass13<16, MODE, 1>(fa, st); break;
+    case 32: rc = launch_pass13<32, MODE, 1>(fa, st); break;
+    case 64: rc = launch_pass13<64, MODE, 1>(fa, st); break;
+    default: rc = launch_pass13<128, MODE, 1>(fa, st); break;
+  }
   return rc;
 }
 
@@ -284,8 +299,8 @@ static int run_fast_mode(fast::FastArgs fa, cudaStream_t st) {
 
 static bool fast_eligible(const AdvectProg& a, const AdvectPlan& pl) {
   if (a.op != OP_PHASE || pl.N1 == 1) return false;
-  if (!((pl.N1 == 64 || pl.N1 == 128) && (pl.N2 == 64 || pl.N2 == 128))) return false;
-  return true;
+  auto ok = [](int n) { return n == 16 || n == 32 || n == 64 || n == 128; };
+  return ok(pl.N1) && ok(pl.N2);
 }
 
 struct DensityReq {   // fused charge density request (vdfdx only)
@@ -296,7 +311,13 @@ struct DensityReq {   // fused charge density request (vdfdx only)
 
 static int run_advect(AdvectProg a, cudaStream_t st, int flags = VPFP_PHASE_EXACT,
                       const DensityReq* dens = nullptr, bool* dens_done = nullptr) {
-  const AdvectPlan pl = make_advect_plan(a.mode, a.N, 2048, 2048);
+  // Small problems (< 4M cells) are latency bound: one generic kernel with the whole sequence in
+  // shared memory beats three dependent launches.  Otherwise 256 <= N <= 16384 take the
+  // register-resident three passes.
+  const long cells = (long)a.N * 2 * a.nseq * (a.mode == ADV_COLS ? a.nsim : 1);
+  const bool small = cells < (1L << 22) && a.N <= 2048;
+  const AdvectPlan pl = ((flags & VPFP_FORCE_GENERIC) || small) ? make_advect_plan(a.mode, a.N, 2048, 2048)
+                                                                : make_advect_plan(a.mode, a.N, 128, 128);
   int rc = get_twiddles(a.N, &a.tw);
   if (rc) return rc;
   if (pl.N1 == 1) {
@@ -322,8 +343,8 @@ static int run_advect(AdvectProg a, cudaStream_t st, int flags = VPFP_PHASE_EXAC
     fa.dens_partial = nullptr; fa.dv = 0.0; fa.edge_flags = 3;
     int dens_tiles = 0;
     if (dens && dens->out && a.mode == ADV_COLS) {
-      const int CB = (pl.N1 == 128) ? 16 : 32;
-      dens_tiles = (a.nseq + CB - 1) / CB;
+      const int CB = (pl.N1 == 128) ? 16 : (pl.N1 == 64 ? 32 : 64);
+      dens_tiles = ((a.nseq + CB - 1) / CB) * (CB > 32 ? CB / 32 : 1);
       void* scr = nullptr;
       rc = get_scratch(SCR_DENSITY, sizeof(double) * (size_t)dens_tiles * a.nsim * a.N, &scr);
       if (rc) return rc;
@@ -660,16 +681,16 @@ int vpfp_xmodes(const double* f, long ld, double* out, int nmodes, int batch, in
 
 int vpfp_xmodes_partial(const double* f, long ld, double* out, int nmodes, int batch, int nx, int ncols,
                         int x_offset, int nx_total, void* stream) {
-  if (!f || !out || nmodes < 1 || batch <= 0 || nx <= 0 || ncols <= 0 || nx_total < nx || x_offset < 0)
-    return fail(VPFP_ERR_ARG, "vpfp_xmodes: bad argument");
+  if (!f || !out || nmodes < 1 || nmodes > 5 || batch <= 0 || nx <= 0 || ncols <= 0 || nx_total < nx || x_offset < 0)
+    return fail(VPFP_ERR_ARG, "vpfp_xmodes: bad argument (1 <= nmodes <= 5)");
   XmodesProg p;
   p.f = f; p.ld = ld; p.nmodes = nmodes; p.batch = batch; p.nx = nx; p.ncols = ncols;
   p.x_offset = x_offset; p.nx_total = nx_total;
   const int threads = 128;
   p.cblocks = (ncols + threads - 1) / threads;
-  int xch = nx / 64;
+  int xch = nx / 128;
   if (xch < 1) xch = 1;
-  if (xch > 64) xch = 64;
+  if (xch > 32) xch = 32;
   p.xchunks = xch;
   void* scratch = nullptr;
   size_t bytes = (size_t)batch * xch * nmodes * ncols * 2 * sizeof(double);

@@ -54,9 +54,10 @@ def _is_pow2(n):
     return n > 0 and (n & (n - 1)) == 0
 
 
-def adv_launches(mode, n):
-    """kernels per advection call: one when the sequence fits a CTA, else the three passes"""
-    return 1 if n <= 2048 else 3
+def adv_launches(mode, n, cells=1 << 30):
+    """kernels per advection call: one when the sequence fits a CTA (short sequences, or small
+    problems of up to 2048 points), else the three passes"""
+    return 1 if (n <= 128 or (cells < (1 << 22) and n <= 2048)) else 3
 
 
 def edfdv_exp(f, e, kv, dt, out=None, flags=PHASE_EXACT):
@@ -69,7 +70,7 @@ def edfdv_exp(f, e, kv, dt, out=None, flags=PHASE_EXACT):
     _vec(e, rows, "e"); _vec(kv, nv, "kv")
     _lib.check(_lib.lib().vpfp_edfdv_exp(f.data_ptr(), ld, out.data_ptr(), ldo, e.data_ptr(), kv.data_ptr(),
                                          float(dt), rows, nv, flags, _stream()))
-    _count(adv_launches("rows", nv))
+    _count(adv_launches("rows", nv, rows * nv))
     return out
 
 
@@ -88,11 +89,11 @@ def vdfdx_exp(f, kx, v, dt, out=None, flags=PHASE_EXACT, density_out=None, dv=No
         _lib.check(_lib.lib().vpfp_vdfdx_exp_density(f.data_ptr(), ld, out.data_ptr(), ldo, kx.data_ptr(),
                                                      v.data_ptr(), float(dt), batch, nx, ncols, flags,
                                                      density_out.data_ptr(), float(dv), edge_flags, _stream()))
-        _count(adv_launches("cols", nx) + 1)
+        _count(adv_launches("cols", nx, batch * nx * ncols) + 1)
         return out
     _lib.check(_lib.lib().vpfp_vdfdx_exp(f.data_ptr(), ld, out.data_ptr(), ldo, kx.data_ptr(), v.data_ptr(),
                                          float(dt), batch, nx, ncols, flags, _stream()))
-    _count(adv_launches("cols", nx))
+    _count(adv_launches("cols", nx, batch * nx * ncols))
     return out
 
 
