@@ -206,38 +206,57 @@ def initial_state(cfg, pinned=False):
 
 
 class ClockSampler(threading.Thread):
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe):
+    one streaming nvidia-smi process sampling every 50 ms."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
         super().__init__(daemon=True)
-        self.index, self.rows, self.stop_flag = index, [], False
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "50"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.proc = None
+        super().start()
+        time.sleep(0.15)          # let the first sample land before the timed region starts
 
     def run(self):
-        while not self.stop_flag:
-            try:
-                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5)
-                if out.returncode == 0 and out.stdout.strip():
-                    self.rows.append([c.strip() for c in out.stdout.strip().split(",")])
-            except Exception:
-                pass
-            time.sleep(0.1)
+        if self.proc is None:
+            return
+        for line in self.proc.stdout:
+            cells = [c.strip() for c in line.strip().split(",")]
+            if len(cells) >= 7:
+                self.rows.append(cells)
 
     def summary(self):
-        self.stop_flag = True
+        if self.proc is not None:
+            time.sleep(0.06)
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=3)
+            except Exception:
+                self.proc.kill()
         self.join(timeout=3)
         if not self.rows:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
-        sm = [float(r[0]) for r in self.rows if r[0].replace(".", "").isdigit()]
+
+        def num(s):
+            try:
+                return float(s)
+            except ValueError:
+                return None
+        sm = [num(r[0]) for r in self.rows if num(r[0]) is not None]
+        pw = [num(r[2]) for r in self.rows if num(r[2]) is not None]
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         reasons = [n for j, n in enumerate(names) if any(r[3 + j].lower().startswith("active") for r in self.rows)]
-        return {"sm_mhz": float(np.median(sm)) if sm else None,
-                "sm_max_mhz": float(self.rows[0][1]) if self.rows[0][1].replace(".", "").isdigit() else None,
-                "power_w_max": max(float(r[2]) for r in self.rows if r[2].replace(".", "").isdigit()),
-                "reasons": reasons, "samples": len(self.rows)}
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": num(self.rows[0][1]),
+                "power_w_max": max(pw) if pw else None, "reasons": reasons, "samples": len(self.rows)}
 
 
 def peaks():
@@ -499,6 +518,15 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
+    # stdout carries exactly ONE JSON line: anything libraries print there (NCCL's version banner)
+    # goes to stderr instead -- fd 1 is pointed at fd 2 and the line is written to the saved fd
+    sys.stdout.flush()
+    saved = os.dup(1)
+    os.dup2(2, 1)
+    global print
+
+    def print(*a, **k):          # noqa: A001  (only json lines are printed by this module)
+        os.write(saved, (" ".join(str(x) for x in a) + "\n").encode())
     if args.impl == "reference":
         reference_arm(args)
     elif args.workload == "c4":

@@ -133,6 +133,30 @@ int vpfp_driver_dev(const double *x, const double *t_dev, const double *incs, in
 int vpfp_series(const double *moments, long mom_ld, const double *e, const double *de,
                 double *out, int nx, void *stream);
 
+/* Multi-GPU (one process per GPU): shards that peers can address, and the two advections with the
+ * x<->v layout change fused into the stores of their last pass -- the result is written over
+ * NVLink straight into the target ranks' shards instead of a local array + all-to-all.
+ *   vpfp_ipc_alloc / open / close / free: cudaMalloc + CUDA IPC handle (64 bytes) exchange.
+ *   vpfp_edfdv_exp_scatter: f_in is the local x-shard (rows, nv); scratch (rows, nv) holds the
+ *     intermediate passes; the result column block q lands in peer_fv[q] (the v-shard of rank q,
+ *     shape (rows*nparts, nv/nparts)) at rows [my_rank*rows, (my_rank+1)*rows).
+ *   vpfp_vdfdx_exp_scatter: f_in is the local v-shard (nx, ncols); the result row block q lands in
+ *     peer_fx[q] (the x-shard of rank q, shape (nx/nparts, ncols*nparts)) at columns
+ *     [my_rank*ncols, (my_rank+1)*ncols); n_out (nullable) receives the partial charge density.
+ * The caller orders the ranks (a barrier on the stream) before a shard is read.  Both need the
+ * register-resident kernels (256 <= N <= 16384 and >= 4M cells per rank). */
+int vpfp_ipc_alloc(unsigned long bytes, void **ptr, unsigned char *handle64);
+int vpfp_ipc_open(const unsigned char *handle64, void **ptr);
+int vpfp_ipc_close(void *ptr);
+int vpfp_ipc_free(void *ptr);
+int vpfp_edfdv_exp_scatter(const double *f_in, long ld_in, double *scratch, long ld_scratch,
+                           const double *e, const double *kv, double dt, int rows, int nv, int flags,
+                           void *const *peer_fv, int nparts, int my_rank, void *stream);
+int vpfp_vdfdx_exp_scatter(const double *f_in, long ld_in, double *scratch, long ld_scratch,
+                           const double *kx, const double *v, double dt, int nx, int ncols,
+                           int flags, double *n_out, double dv, int edge_flags,
+                           void *const *peer_fx, int nparts, int my_rank, void *stream);
+
 /* Ensembles of independent simulations (BASELINE config 4): simulation b owns rows
  * b*nx .. b*nx+nx-1 of every per-x array.  vpfp_series_batch writes out[b*7 + k];
  * vpfp_driver_batch evaluates the driver with per-simulation grids x[batch][nx] and pulse

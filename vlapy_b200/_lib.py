@@ -55,6 +55,12 @@ _SIGS = {
     "vpfp_xmodes_partial": ([_P, _L, _P, _I, _I, _I, _I, _I, _I, _P], _I),
     "vpfp_driver": ([_P, _D, _P, _I, _P, _I, _P], _I),
     "vpfp_driver_dev": ([_P, _P, _P, _I, _P, _I, _P, _I, _P], _I),
+    "vpfp_ipc_alloc": ([_c.c_size_t, _c.POINTER(_P), _c.c_char_p], _I),
+    "vpfp_ipc_open": ([_c.c_char_p, _c.POINTER(_P)], _I),
+    "vpfp_ipc_close": ([_P], _I),
+    "vpfp_ipc_free": ([_P], _I),
+    "vpfp_edfdv_exp_scatter": ([_P, _L, _P, _L, _P, _P, _D, _I, _I, _I, _c.POINTER(_P), _I, _I, _P], _I),
+    "vpfp_vdfdx_exp_scatter": ([_P, _L, _P, _L, _P, _P, _D, _I, _I, _I, _P, _D, _I, _c.POINTER(_P), _I, _I, _P], _I),
     "vpfp_series_batch": ([_P, _L, _P, _P, _P, _I, _I, _P], _I),
     "vpfp_driver_batch": ([_P, _D, _P, _P, _I, _P, _I, _P, _I, _I, _P], _I),
     "vpfp_series": ([_P, _L, _P, _P, _P, _I, _P], _I),

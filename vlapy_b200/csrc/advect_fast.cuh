@@ -35,7 +35,7 @@ struct Geo {
 
 struct FastArgs {
   int mode, exact;
-  int N, N1, N2;
+  int N, N1, N2, lN2;       // N2 = 1 << lN2
   int nsim, nseq, nrows;
   int seq_off, seq_cnt;     // this launch handles packed sequences [seq_off, seq_off + seq_cnt) (L2 slab)
   const double* fin; long ld_in;
@@ -52,6 +52,13 @@ struct FastArgs {
   double* dens_partial;
   double dv;
   int edge_flags;
+  // optional scatter of the LAST pass to peer GPUs (multi-GPU layout change fused into the store):
+  //  peer_mode 1 (ROWS, e df/dv of an x-shard): element (row, n) goes to the v-shard of rank
+  //    q = n / part, at [my_rank * nrows + row][n % part], pitch part          (part = nv / P)
+  //  peer_mode 2 (COLS, v df/dx of a v-shard): element (x, col) goes to the x-shard of rank
+  //    q = x / part, at [x % part][my_rank * ncols + col], pitch ncols * P     (part = nx / P)
+  int peer_mode, nparts, my_rank, lpart;   // part = 1 << lpart
+  double* peer[8];
 };
 
 __device__ __forceinline__ cplx ldg_c(const cplx* p) {
@@ -75,6 +82,25 @@ __device__ __forceinline__ cplx gload(const FastArgs& a, const double* base, lon
 
 template <int MODE>
 __device__ __forceinline__ void gstore(const FastArgs& a, int sim, int seq, long n, cplx val, bool last_pass) {
+  if (last_pass && a.peer_mode) {
+    // stores over NVLink straight into the target rank's shard (P2P-mapped pointers)
+    if (MODE == ADV_COLS) {
+      const int q = (int)(n >> a.lpart);
+      const long xl = n & ((1L << a.lpart) - 1);
+      const long ncols = 2L * a.nseq;
+      double* dst = a.peer[q] + xl * (ncols * a.nparts) + (long)a.my_rank * ncols + 2 * (long)seq;
+      *reinterpret_cast<double2*>(dst) = make_double2(val.x, val.y);
+    } else {
+      const int q = (int)(n >> a.lpart);
+      const long part = 1L << a.lpart;
+      const long c = n & (part - 1);
+      const long ra = 2 * (long)seq, rb = ra + 1;
+      double* base = a.peer[q] + ((long)a.my_rank * a.nrows) * part + c;
+      base[ra * part] = val.x;
+      if (rb < a.nrows) base[rb * part] = val.y;
+    }
+    return;
+  }
   if (MODE == ADV_COLS) {
     *reinterpret_cast<double2*>(a.fout + ((long)sim * a.N + n) * a.ld_out + 2 * (long)seq) = make_double2(val.x, val.y);
     return;
@@ -113,8 +139,8 @@ __global__ void __launch_bounds__(CB* Geo<L>::TPC) pass13_kernel(const FastArgs 
     valid = seq < a.seq_off + a.seq_cnt;
   } else {
     const long gl = (long)blockIdx.x * CB + b;        // lanes enumerate (sequence, n2)
-    seq = a.seq_off + (int)(gl / a.N2);
-    n2 = (int)(gl % a.N2);
+    seq = a.seq_off + (int)(gl >> a.lN2);
+    n2 = (int)(gl & (a.N2 - 1));
     valid = seq < a.seq_off + a.seq_cnt;
   }
   const long N2 = a.N2;

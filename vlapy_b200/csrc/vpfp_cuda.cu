@@ -309,8 +309,14 @@ struct DensityReq {   // fused charge density request (vdfdx only)
   int edge_flags = 3;
 };
 
+struct ScatterReq {   // last pass stores into peer shards (multi-GPU), see advect_fast.cuh FastArgs
+  int mode = 0, nparts = 1, my_rank = 0;
+  double* peer[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+};
+
 static int run_advect(AdvectProg a, cudaStream_t st, int flags = VPFP_PHASE_EXACT,
-                      const DensityReq* dens = nullptr, bool* dens_done = nullptr) {
+                      const DensityReq* dens = nullptr, bool* dens_done = nullptr,
+                      const ScatterReq* scat = nullptr) {
   // Small problems (< 4M cells) are latency bound: one generic kernel with the whole sequence in
   // shared memory beats three dependent launches.  Otherwise 256 <= N <= 16384 take the
   // register-resident three passes.
@@ -320,6 +326,8 @@ static int run_advect(AdvectProg a, cudaStream_t st, int flags = VPFP_PHASE_EXAC
                                                                 : make_advect_plan(a.mode, a.N, 128, 128);
   int rc = get_twiddles(a.N, &a.tw);
   if (rc) return rc;
+  if (scat && scat->mode && !(fast_eligible(a, pl) && !(flags & VPFP_FORCE_GENERIC)))
+    return fail(VPFP_ERR_UNSUPPORTED, "peer scatter needs the register-resident kernels (256 <= N <= 16384, >= 4M cells)");
   if (pl.N1 == 1) {
     advect_set_pass(a, pl, 0);
     return launch_prog(a, a.ntiles(), pl.threads[0], a.smem_bytes(), a.nphases(), st,
@@ -334,13 +342,20 @@ static int run_advect(AdvectProg a, cudaStream_t st, int flags = VPFP_PHASE_EXAC
   if (fast_eligible(a, pl) && !(flags & VPFP_FORCE_GENERIC)) {
     fast::FastArgs fa;
     fa.mode = a.mode; fa.exact = (flags & VPFP_PHASE_TABLE) ? 0 : 1;
-    fa.N = a.N; fa.N1 = pl.N1; fa.N2 = pl.N2;
+    fa.N = a.N; fa.N1 = pl.N1; fa.N2 = pl.N2; fa.lN2 = ilog2(pl.N2);
     fa.nsim = a.nsim; fa.nseq = a.nseq; fa.nrows = a.nrows;
     fa.seq_off = 0; fa.seq_cnt = a.nseq;
     fa.fin = a.fin; fa.ld_in = a.ld_in; fa.fout = a.fout; fa.ld_out = a.ld_out;
     fa.kvec = a.kvec; fa.cvec = a.cvec; fa.dt = a.dt; fa.phantom = a.phantom;
     fa.twN = a.tw;
     fa.dens_partial = nullptr; fa.dv = 0.0; fa.edge_flags = 3;
+    fa.peer_mode = 0; fa.nparts = 1; fa.my_rank = 0; fa.lpart = 0;
+    for (int i = 0; i < 8; ++i) fa.peer[i] = nullptr;
+    if (scat && scat->mode) {
+      fa.peer_mode = scat->mode; fa.nparts = scat->nparts; fa.my_rank = scat->my_rank;
+      fa.lpart = ilog2(a.N / scat->nparts);
+      for (int i = 0; i < scat->nparts; ++i) fa.peer[i] = scat->peer[i];
+    }
     int dens_tiles = 0;
     if (dens && dens->out && a.mode == ADV_COLS) {
       const int CB = (pl.N1 == 128) ? 16 : (pl.N1 == 64 ? 32 : 64);
@@ -579,6 +594,78 @@ int vpfp_vdfdx_exp_density(const double* f_in, long ld_in, double* f_out, long l
     // sizes served by the generic kernels: density as a separate row reduction of the result
     return vpfp_moments(f_out, ld_out, v, dv, n_out, (long)batch * nx, 1, batch * nx, ncols, edge_flags, stream);
   }
+  return VPFP_OK;
+}
+
+// ---- multi-GPU: peer-mapped shards and advection with the layout change fused into the last store
+int vpfp_ipc_alloc(size_t bytes, void** ptr, unsigned char* handle64) {
+  if (!ptr || !handle64 || bytes == 0) return fail(VPFP_ERR_ARG, "vpfp_ipc_alloc: bad argument");
+  CUDA_TRY(cudaMalloc(ptr, bytes));
+  cudaIpcMemHandle_t h;
+  CUDA_TRY(cudaIpcGetMemHandle(&h, *ptr));
+  static_assert(sizeof(h) == 64, "cudaIpcMemHandle_t is 64 bytes");
+  memcpy(handle64, &h, 64);
+  return VPFP_OK;
+}
+
+int vpfp_ipc_open(const unsigned char* handle64, void** ptr) {
+  if (!ptr || !handle64) return fail(VPFP_ERR_ARG, "vpfp_ipc_open: bad argument");
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle64, 64);
+  CUDA_TRY(cudaIpcOpenMemHandle(ptr, h, cudaIpcMemLazyEnablePeerAccess));
+  return VPFP_OK;
+}
+
+int vpfp_ipc_close(void* ptr) {
+  CUDA_TRY(cudaIpcCloseMemHandle(ptr));
+  return VPFP_OK;
+}
+
+int vpfp_ipc_free(void* ptr) {
+  CUDA_TRY(cudaFree(ptr));
+  return VPFP_OK;
+}
+
+int vpfp_edfdv_exp_scatter(const double* f_in, long ld_in, double* scratch, long ld_scratch, const double* e,
+                           const double* kv, double dt, int rows, int nv, int flags, void* const* peer_fv,
+                           int nparts, int my_rank, void* stream) {
+  if (!f_in || !scratch || !e || !kv || !peer_fv || rows <= 0 || nv <= 0 || nparts < 1 || nparts > 8 ||
+      my_rank < 0 || my_rank >= nparts || nv % nparts)
+    return fail(VPFP_ERR_ARG, "vpfp_edfdv_exp_scatter: bad argument");
+  if (!is_pow2(nv) || !is_pow2(nparts))
+    return fail(VPFP_ERR_UNSUPPORTED, "e df/dv scatter: nv and the number of ranks must be powers of two");
+  AdvectProg a;
+  memset(&a, 0, sizeof(a));
+  a.mode = ADV_ROWS; a.op = OP_PHASE; a.N = nv;
+  a.nsim = 1; a.nrows = rows; a.nseq = (rows + 1) / 2;
+  a.fin = f_in; a.ld_in = ld_in; a.fout = scratch; a.ld_out = ld_scratch;
+  a.kvec = kv; a.cvec = e; a.addv = nullptr; a.dt = dt;
+  ScatterReq sr; sr.mode = 1; sr.nparts = nparts; sr.my_rank = my_rank;
+  for (int i = 0; i < nparts; ++i) sr.peer[i] = (double*)peer_fv[i];
+  return run_advect(a, (cudaStream_t)stream, flags, nullptr, nullptr, &sr);
+}
+
+int vpfp_vdfdx_exp_scatter(const double* f_in, long ld_in, double* scratch, long ld_scratch, const double* kx,
+                           const double* v, double dt, int nx, int ncols, int flags, double* n_out, double dv,
+                           int edge_flags, void* const* peer_fx, int nparts, int my_rank, void* stream) {
+  if (!f_in || !scratch || !kx || !v || !peer_fx || nx <= 0 || ncols <= 0 || nparts < 1 || nparts > 8 ||
+      my_rank < 0 || my_rank >= nparts || nx % nparts)
+    return fail(VPFP_ERR_ARG, "vpfp_vdfdx_exp_scatter: bad argument");
+  if (!is_pow2(nx) || !is_pow2(nparts) || (ncols & 1) || (ld_in & 1) || (ld_scratch & 1))
+    return fail(VPFP_ERR_UNSUPPORTED, "v df/dx scatter: nx and ranks powers of two, even column counts");
+  AdvectProg a;
+  memset(&a, 0, sizeof(a));
+  a.mode = ADV_COLS; a.op = OP_PHASE; a.N = nx;
+  a.nsim = 1; a.nrows = nx; a.nseq = ncols / 2;
+  a.fin = f_in; a.ld_in = ld_in; a.fout = scratch; a.ld_out = ld_scratch;
+  a.kvec = kx; a.cvec = v; a.addv = nullptr; a.dt = dt;
+  ScatterReq sr; sr.mode = 2; sr.nparts = nparts; sr.my_rank = my_rank;
+  for (int i = 0; i < nparts; ++i) sr.peer[i] = (double*)peer_fx[i];
+  DensityReq dr; dr.out = n_out; dr.dv = dv; dr.edge_flags = edge_flags;
+  bool done = false;
+  int rc = run_advect(a, (cudaStream_t)stream, flags, n_out ? &dr : nullptr, &done, &sr);
+  if (rc) return rc;
+  if (n_out && !done) return fail(VPFP_ERR_UNSUPPORTED, "v df/dx scatter: fused density unavailable at this size");
   return VPFP_OK;
 }
 

@@ -20,11 +20,15 @@ import torch.distributed as dist
 
 class Sharded:
     """A shard of f together with its layout: 'x' = rows [r*nx/P, (r+1)*nx/P) x all v,
-    'v' = all x  x  columns [r*nv/P, (r+1)*nv/P)."""
-    __slots__ = ("t", "layout")
+    'v' = all x  x  columns [r*nv/P, (r+1)*nv/P).
+    ``density``: the (globally reduced) charge density of this f when the producing operator already
+    computed it.  ``pending`` = (f_x, e_local, dt): the shard is e df/dv of f_x, not evaluated yet --
+    whoever consumes it decides where the result is stored (locally in x layout, or scattered over
+    NVLink into the peers' v-shards)."""
+    __slots__ = ("t", "layout", "density", "pending")
 
-    def __init__(self, t, layout):
-        self.t, self.layout = t, layout
+    def __init__(self, t, layout, density=None, pending=None):
+        self.t, self.layout, self.density, self.pending = t, layout, density, pending
 
 
 class Topology:
@@ -65,6 +69,39 @@ class Topology:
             dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group)
         return t
 
+    def stream_barrier(self, token):
+        """order the ranks on the device (no host synchronisation): a one-element all-reduce"""
+        return self.all_reduce_sum(token)
+
+
+class PeerShards:
+    """Receive buffers of this rank that the peers can address (CUDA IPC over NVLink), and the
+    mapped pointers of every peer's: ``fx`` (nx/P, nv) receives the scattered result of v df/dx,
+    ``fv`` (nx, nv/P) the scattered result of e df/dv."""
+
+    def __init__(self, topo, device):
+        from . import ops
+        nbytes = 8 * topo.nxl * topo.nv
+        self.bx, self.bv = ops.PeerBuffer(nbytes), ops.PeerBuffer(nbytes)
+        self.fx = self.bx.tensor((topo.nxl, topo.nv), device)
+        self.fv = self.bv.tensor((topo.nx, topo.nvl), device)
+        mine = torch.tensor(list(self.bx.handle + self.bv.handle), dtype=torch.uint8, device=device)
+        every = [torch.empty_like(mine) for _ in range(topo.world)]
+        dist.all_gather(every, mine, group=topo.group)
+        self.px, self.pv = [], []
+        for q, h in enumerate(every):
+            if q == topo.rank:
+                self.px.append(self.bx.ptr); self.pv.append(self.bv.ptr)
+            else:
+                raw = bytes(h.cpu().numpy().tobytes())
+                self.px.append(self.bx.open_peer(raw[:64])); self.pv.append(self.bv.open_peer(raw[64:]))
+        self.token = torch.zeros(1, dtype=torch.float32, device=device)
+
+    def close(self):
+        torch.cuda.synchronize()
+        self.fx = self.fv = None
+        self.bx.close(); self.bv.close()
+
 
 class DeviceBackend:
     """Per-shard operators on the CUDA kernels (vlapy_b200.ops)."""
@@ -87,9 +124,47 @@ class DeviceBackend:
         self.pulses = ops.pulses_to_array(s["pulse_dictionary"]) if s.get("pulse_dictionary") else None
         self.driver_host = s.get("driver_function")
         self.edge = (1 if topo.rank == 0 else 0) | (2 if topo.rank == topo.world - 1 else 0)
+        # layout changes fused into the operators' last pass (stores over NVLink into the peers'
+        # shards) when the register-resident kernels apply; otherwise NCCL all-to-all transposes
+        import os
+
+        def pow2(n):
+            return n > 0 and (n & (n - 1)) == 0
+        P = topo.world
+        self.can_scatter = (P > 1 and P <= 8 and pow2(P) and pow2(topo.nx) and pow2(topo.nv)
+                            and 256 <= topo.nx <= 16384 and 256 <= topo.nv <= 16384
+                            and topo.nxl * topo.nv >= (1 << 22) and os.environ.get("VPFP_NO_SCATTER", "0") == "0")
+        self.peers = PeerShards(topo, self.x.device) if self.can_scatter else None
+        self.scratch_x = self.scratch_v = None
+
+    def close(self):
+        if self.peers is not None:
+            self.peers.close()
+            self.peers, self.can_scatter = None, False
 
     def edfdv(self, fx, e_loc, dt):
         return self.ops.edfdv_exp(fx, e_loc, self.kv, dt, flags=self.flags_v)
+
+    def edfdv_scatter(self, fx, e_loc, dt):
+        """e df/dv of the local x-shard, result delivered as everybody's v-shard"""
+        topo, pr = self.topo, self.peers
+        if self.scratch_x is None:
+            self.scratch_x = torch.empty((topo.nxl, topo.nv), dtype=torch.float64, device=fx.device)
+        self.ops.edfdv_exp_scatter(fx, e_loc, self.kv, dt, self.scratch_x, pr.pv, topo.rank, flags=self.flags_v)
+        topo.stream_barrier(pr.token)            # every rank's block has landed in every v-shard
+        return pr.fv
+
+    def vdfdx_scatter(self, fv, dt):
+        """v df/dx of the local v-shard, result delivered as everybody's x-shard; returns it with the
+        all-reduced charge density (the all-reduce also orders the ranks)"""
+        topo, pr = self.topo, self.peers
+        if self.scratch_v is None:
+            self.scratch_v = torch.empty((topo.nx, topo.nvl), dtype=torch.float64, device=fv.device)
+        n = fv.new_empty(topo.nx)
+        self.ops.vdfdx_exp_scatter(fv, self.kx, self.v_loc, dt, self.scratch_v, pr.px, topo.rank,
+                                   flags=self.flags_x, density_out=n, dv=self.dv, edge_flags=self.edge)
+        topo.all_reduce_sum(n)
+        return pr.fx, n
 
     def vdfdx(self, fv, dt):
         n = fv.new_empty(fv.shape[0])            # partial density over the local columns, fused epilogue
@@ -131,20 +206,37 @@ def make_sharded_operators(topo, backend):
     """vdfdx / edfdv / field_solve / fp closures on Sharded handles (same call signatures as
     vlapy/core/vlasov.py, field.py, step.py closures)."""
 
+    scatter = bool(getattr(backend, "can_scatter", False))
+
     def to_x(f):
+        if f.pending is not None:
+            return Sharded(backend.edfdv(*f.pending), "x")
         return f if f.layout == "x" else Sharded(topo.v_to_x(f.t), "x")
 
     def to_v(f):
+        if f.pending is not None:
+            if scatter:
+                return Sharded(backend.edfdv_scatter(*f.pending), "v")
+            f = to_x(f)
         return f if f.layout == "v" else Sharded(topo.x_to_v(f.t), "v")
 
     def vdfdx(f, dt):
-        return Sharded(backend.vdfdx(to_v(f).t, dt), "v")
+        fv = to_v(f)
+        if scatter:
+            fx, n = backend.vdfdx_scatter(fv.t, dt)
+            return Sharded(fx, "x", density=n)
+        return Sharded(backend.vdfdx(fv.t, dt), "v")
 
     def edfdv(f, e, dt):
         e_loc = e[topo.x0: topo.x0 + topo.nxl].contiguous()
-        return Sharded(backend.edfdv(to_x(f).t, e_loc, dt), "x")
+        fx = to_x(f)
+        if scatter:
+            return Sharded(None, "x", pending=(fx.t, e_loc, dt))     # evaluated by its consumer
+        return Sharded(backend.edfdv(fx.t, e_loc, dt), "x")
 
     def field_solve(driver_field, f):
+        if f.density is not None:
+            return backend.poisson(f.density, driver_field)
         # density of a v-shard: partial integral over the local columns, then a sum over ranks
         n = topo.all_reduce_sum(backend.density_partial(to_v(f).t))
         return backend.poisson(n, driver_field)
@@ -181,6 +273,9 @@ def get_sharded_timestep(all_params, stuff_for_time_loop, topo, backend=None):
             f = ops_["to_x"](f)
             if mom is not None:
                 backend.moments(f.t, mom)
+        peers = getattr(backend, "peers", None)
+        if peers is not None and f.t is peers.fx:      # never hand out the receive buffer itself
+            f = Sharded(f.t.clone(), "x")
         if store is not None:
             i = store["i"]
             sl = slice(topo.x0, topo.x0 + topo.nxl)
@@ -291,8 +386,11 @@ def bench_sharded(cfg, params, rules, K, W, dev, barrier):
            "d2h_bytes_per_step": d2h * topo.world, "ms_per_step": sec * 1e3 / K,
            "note": "every rank uploads its x-slab, runs %d steps, downloads slab + stored rows" % K}
     P = topo.world
+    how = ("layout changes fused into the last advection pass (stores over NVLink into peer shards), "
+           "1 all-reduce + 1 barrier per step") if backend.can_scatter else "2 NCCL all-to-all + 1 all-reduce per step"
+    backend.close()
     return dict(ms=ms, launches=launches, clocks=clocks, prof=prof, e2e=e2e, mean_n=mean_n, scaling="strong",
-                parallelism="x-sharded rows / v-sharded columns over %d GPUs, 2 NCCL all-to-all + 1 all-reduce per step" % P)
+                parallelism="x-sharded rows / v-sharded columns over %d GPUs, %s" % (P, how))
 
 
 def ops_to_x(f, topo):

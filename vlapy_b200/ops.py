@@ -97,6 +97,82 @@ def vdfdx_exp(f, kx, v, dt, out=None, flags=PHASE_EXACT, density_out=None, dv=No
     return out
 
 
+class PeerBuffer:
+    """A device buffer that peer GPUs (other processes on the same NVLink domain) can address:
+    cudaMalloc + CUDA IPC handle (vpfp_ipc_alloc).  ``tensor(shape)`` views it as a torch tensor
+    (torch does not own the memory; keep this object alive while the view is used)."""
+
+    def __init__(self, nbytes):
+        self.nbytes = int(nbytes)
+        ptr = ctypes.c_void_p()
+        hbuf = ctypes.create_string_buffer(64)
+        _lib.check(_lib.lib().vpfp_ipc_alloc(self.nbytes, ctypes.byref(ptr), hbuf))
+        self.ptr, self.handle = ptr.value, hbuf.raw
+        self.opened = []
+
+    def tensor(self, shape, device):
+        class _View:
+            pass
+        v = _View()
+        v.__cuda_array_interface__ = {"shape": tuple(int(s) for s in shape), "typestr": "<f8",
+                                      "data": (self.ptr, False), "version": 3, "strides": None}
+        t = torch.as_tensor(v, device=device)
+        t._vpfp_owner = self
+        return t
+
+    def open_peer(self, handle):
+        """map a peer's buffer (its 64-byte handle) into this process; returns the device pointer"""
+        ptr = ctypes.c_void_p()
+        _lib.check(_lib.lib().vpfp_ipc_open(handle, ctypes.byref(ptr)))
+        self.opened.append(ptr.value)
+        return ptr.value
+
+    def close(self):
+        for p in self.opened:
+            _lib.lib().vpfp_ipc_close(ctypes.c_void_p(p))
+        self.opened = []
+        if self.ptr:
+            _lib.lib().vpfp_ipc_free(ctypes.c_void_p(self.ptr))
+            self.ptr = None
+
+
+def _ptr_array(ptrs):
+    return (ctypes.c_void_p * len(ptrs))(*[ctypes.c_void_p(p) for p in ptrs])
+
+
+def edfdv_exp_scatter(f, e, kv, dt, scratch, peer_ptrs, my_rank, flags=PHASE_EXACT):
+    """e df/dv of an x-shard (rows, nv) whose result lands v-sharded on the peers: column block q is
+    stored over NVLink into peer_ptrs[q] (rank q's (rows*P, nv/P) shard) at rows
+    [my_rank*rows, (my_rank+1)*rows).  scratch: (rows, nv) for the intermediate passes."""
+    rows, ld = _chk_f(f)
+    nv = f.shape[-1]
+    _, lds = _chk_f(scratch, "scratch")
+    _vec(e, rows, "e"); _vec(kv, nv, "kv")
+    _lib.check(_lib.lib().vpfp_edfdv_exp_scatter(f.data_ptr(), ld, scratch.data_ptr(), lds, e.data_ptr(),
+                                                 kv.data_ptr(), float(dt), rows, nv, flags, _ptr_array(peer_ptrs),
+                                                 len(peer_ptrs), int(my_rank), _stream()))
+    _count(3)
+
+
+def vdfdx_exp_scatter(f, kx, v, dt, scratch, peer_ptrs, my_rank, flags=PHASE_EXACT, density_out=None, dv=0.0,
+                      edge_flags=3):
+    """v df/dx of a v-shard (nx, ncols) whose result lands x-sharded on the peers: row block q is
+    stored into peer_ptrs[q] (rank q's (nx/P, ncols*P) shard) at columns
+    [my_rank*ncols, (my_rank+1)*ncols); density_out (nx) receives the partial trapz_v of the result."""
+    _, ld = _chk_f(f)
+    nx, ncols = f.shape[-2], f.shape[-1]
+    _, lds = _chk_f(scratch, "scratch")
+    _vec(kx, nx, "kx"); _vec(v, ncols, "v")
+    if density_out is not None:
+        _vec(density_out, nx, "density_out")
+    _lib.check(_lib.lib().vpfp_vdfdx_exp_scatter(f.data_ptr(), ld, scratch.data_ptr(), lds, kx.data_ptr(),
+                                                 v.data_ptr(), float(dt), nx, ncols, flags,
+                                                 density_out.data_ptr() if density_out is not None else None,
+                                                 float(dv), edge_flags, _ptr_array(peer_ptrs), len(peer_ptrs),
+                                                 int(my_rank), _stream()))
+    _count(3 + (1 if density_out is not None else 0))
+
+
 def edfdv_cd2(f, e, dt, dv, out=None):
     """vlapy/core/vlasov.py:153-163 on device."""
     rows, ld = _chk_f(f)
