@@ -33,6 +33,7 @@ extern "C" {
                               * honoured by the register-resident kernels (256 <= N <= 16384),
                               * the generic kernels always use the exact phases */
 #define VPFP_FORCE_GENERIC 2 /* testing: skip the register-resident kernels */
+#define VPFP_FORCE_THREE_PASS 4 /* testing / A-B timing: skip the single-pass row kernel */
 
 /* collision operator ids (vlapy/core/collisions.py:292-317) */
 #define VPFP_FP_LB 0

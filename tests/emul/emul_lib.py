@@ -12,7 +12,7 @@ CSRC = os.path.join(os.path.dirname(os.path.dirname(HERE)), "vlapy_b200", "csrc"
 
 
 def build(force=False):
-    deps = [SRC] + [os.path.join(CSRC, n) for n in ("advect.h", "rowops.h", "vpfp_common.h", "butterflies.h")]
+    deps = [SRC] + [os.path.join(CSRC, n) for n in ("advect.h", "rowops.h", "vpfp_common.h", "butterflies.h", "rowfft.cuh")]
     if force or not os.path.exists(SO) or any(os.path.getmtime(d) > os.path.getmtime(SO) for d in deps):
         subprocess.check_call(["g++", "-O2", "-ffp-contract=off", "-std=c++17", "-shared", "-fPIC",
                                "-o", SO, SRC])
@@ -41,6 +41,16 @@ def edfdv_exp(f, e, kv, dt, max_single=8192):
     rows, nv = f.shape
     lib().emul_edfdv_exp(_p(f), c_long(nv), _p(out), c_long(nv), _p(np.ascontiguousarray(e)),
                          _p(np.ascontiguousarray(kv)), c_double(dt), c_int(rows), c_int(nv), c_int(max_single))
+    return out
+
+
+def edfdv_rowfft(f, e, kv, dt):
+    """single-pass row kernel (rowfft.cuh), nv in {4096, 8192, 16384}"""
+    f = np.ascontiguousarray(f); out = np.empty_like(f)
+    rows, nv = f.shape
+    rc = lib().emul_edfdv_rowfft(_p(f), c_long(nv), _p(out), c_long(nv), _p(np.ascontiguousarray(e)),
+                                 _p(np.ascontiguousarray(kv)), c_double(dt), c_int(rows), c_int(nv))
+    assert rc == 0
     return out
 
 

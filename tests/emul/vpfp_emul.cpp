@@ -184,3 +184,33 @@ extern "C" int emul_butterfly(double* xy, int radix, int dir) {
   for (int i = 0; i < radix; ++i) { xy[2 * i] = x[i].x; xy[2 * i + 1] = x[i].y; }
   return 0;
 }
+
+// ---- single-pass row kernel (vlapy_b200/csrc/rowfft.cuh): per-thread registers persist across phases
+#include "../../vlapy_b200/csrc/rowfft.cuh"
+template <class P>
+static void run_rowfft(const P& prog) {
+  std::vector<typename P::Regs> regs((size_t)P::T);
+  std::vector<unsigned char> smem((size_t)P::SMEM_BYTES + 64);
+  unsigned char* base = smem.data();
+  base += (16 - ((uintptr_t)base & 15)) & 15;
+  for (int tid = 0; tid < P::T; ++tid) prog.init(tid, regs[tid], base);
+  for (int tid = 0; tid < P::T; ++tid) prog.load_row(0, tid, regs[tid]);
+  for (long row = 0; row < prog.a.nrows; ++row)
+    for (int ph = 0; ph < P::NPH; ++ph)
+      for (int tid = 0; tid < P::T; ++tid)
+        prog.phase(ph, row, row + 1 < prog.a.nrows ? row + 1 : -1, tid, regs[tid], base);
+}
+
+extern "C" int emul_edfdv_rowfft(const double* f_in, long ld_in, double* f_out, long ld_out, const double* e,
+                                 const double* kv, double dt, int rows, int nv) {
+  std::vector<cplx> tw = make_tw(nv);
+  rowfft::Args a;
+  memset(&a, 0, sizeof(a));
+  a.fin = f_in; a.ld_in = ld_in; a.fout = f_out; a.ld_out = ld_out; a.kvec = kv; a.cvec = e; a.dt = dt;
+  a.nrows = rows; a.twN = tw.data();
+  if (nv == 16384) { rowfft::Prog<32, 16> p; p.a = a; run_rowfft(p); }
+  else if (nv == 8192) { rowfft::Prog<16, 16> p; p.a = a; run_rowfft(p); }
+  else if (nv == 4096) { rowfft::Prog<8, 16> p; p.a = a; run_rowfft(p); }
+  else return 1;
+  return 0;
+}

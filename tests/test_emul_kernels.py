@@ -166,3 +166,17 @@ def test_register_butterflies(radix):
     x = rng.standard_normal(radix) + 1j * rng.standard_normal(radix)
     np.testing.assert_allclose(E.butterfly(x, radix, -1), np.fft.fft(x), rtol=0, atol=1e-14)
     np.testing.assert_allclose(E.butterfly(x, radix, +1), np.fft.ifft(x) * radix, rtol=0, atol=1e-14)
+
+
+@pytest.mark.parametrize("nv", [4096, 8192, 16384])
+def test_rowfft_program(nv):
+    """single-pass row kernel (rowfft.cuh: real row as one complex sequence of nv/2 points, pairs
+    (k, M-k) un-mixed in registers) against the oracle: white noise (every bin, Nyquist included)
+    and a smooth Maxwellian-like row, positive and negative sub-steps, odd row count."""
+    rng = np.random.default_rng(nv)
+    dv, v, kv = O.velocity_grid(6.4, nv)
+    f = rng.standard_normal((3, nv))
+    f[1] = np.exp(-v ** 2 / 2) * (1 + 1e-3 * rng.standard_normal(nv))
+    e = np.array([0.05, -0.7, 1.3])
+    for dt in (0.37, -0.066):
+        assert rel_err(E.edfdv_rowfft(f, e, kv, dt), O.edfdv_exponential(f, e, dt, kv)) < TOL

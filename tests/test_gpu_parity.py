@@ -466,3 +466,26 @@ def test_ensemble_matches_independent_oracle_runs(dev, integ, nu_log):
 def test_smoke_entry(dev):
     import __graft_entry__ as ge
     assert ge.smoke()
+
+
+@pytest.mark.parametrize("nv,rows", [(4096, 1024), (8192, 513), (16384, 257), (16384, 1024)])
+def test_single_pass_row_kernel(dev, nv, rows):
+    """e df/dv as one kernel per row (csrc/rowfft.cuh) against the oracle and against the three-pass
+    kernels; smooth + noise rows, both signs of dt, a row pitch larger than the row."""
+    from vlapy_b200 import ops
+    rng = np.random.default_rng(nv + rows)
+    dv, v, kv = O.velocity_grid(6.4, nv)
+    f = np.exp(-v ** 2 / 2)[None, :] * (1 + 0.1 * rng.standard_normal((rows, nv)))
+    f[::7] = rng.standard_normal((len(f[::7]), nv))
+    e = 0.3 * rng.standard_normal(rows)
+    big = torch.zeros((rows, nv + 16), dtype=torch.float64, device=dev)
+    big[:, :nv] = torch.from_numpy(f).to(dev)
+    fd, ed, kd = big[:, :nv], torch.from_numpy(e).to(dev), torch.from_numpy(kv).to(dev)
+    for dt in (0.125, -0.033):
+        ref = O.edfdv_exponential(f, e, dt, kv)
+        one = ops.edfdv_exp(fd, ed, kd, dt, flags=ops.PHASE_TABLE)
+        three = ops.edfdv_exp(fd, ed, kd, dt, flags=ops.PHASE_TABLE | ops.FORCE_THREE_PASS)
+        assert ops.rowfft_serves(rows, nv, ops.PHASE_TABLE)
+        assert rel_err(one.cpu().numpy(), ref) < TOL
+        assert rel_err(three.cpu().numpy(), ref) < TOL
+        assert rel_err(one.cpu().numpy(), three.cpu().numpy()) < TOL

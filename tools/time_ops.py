@@ -39,6 +39,7 @@ def main():
     cases = {
         "copy(torch)": (lambda: out.copy_(f), gb),
         "edfdv_exp(table)": (lambda: ops.edfdv_exp(f, e, kv, 0.125, out=out, flags=1), gb),
+        "edfdv_exp(table,3pass)": (lambda: ops.edfdv_exp(f, e, kv, 0.125, out=out, flags=5), gb),
         "vdfdx_exp(table)": (lambda: ops.vdfdx_exp(f, kx, v, 0.25, out=out, flags=1), gb),
         "edfdv_exp(exact)": (lambda: ops.edfdv_exp(f, e, kv, 0.125, out=out, flags=0), gb),
         "vdfdx_exp(exact)": (lambda: ops.vdfdx_exp(f, kx, v, 0.25, out=out, flags=0), gb),

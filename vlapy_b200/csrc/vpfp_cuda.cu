@@ -17,6 +17,7 @@
 #include "advect.h"
 #include "advect_fast.cuh"
 #include "fp_fast.cuh"
+#include "rowfft.cuh"
 #include "rowops.h"
 
 // ------------------------------------------------------------------------------------------
@@ -486,6 +487,72 @@ static int launch_fp_fast(const fpfast::Args& a, cudaStream_t st) {
 // ------------------------------------------------------------------------------------------
 // C ABI
 // ------------------------------------------------------------------------------------------
+// ---- single-pass row kernel (rowfft.cuh): e df/dv with one HBM read and one write of f
+static int g_rowfft_on = -1;   // VPFP_NO_ROWFFT=1 keeps the three-pass kernels (A/B measurements)
+
+static bool rowfft_eligible(const double* f_in, long ld_in, const double* f_out, long ld_out, int rows, int nv,
+                            int flags) {
+  if (g_rowfft_on < 0) {
+    const char* e = getenv("VPFP_NO_ROWFFT");
+    g_rowfft_on = (e && atoi(e)) ? 0 : 1;
+  }
+  if (!g_rowfft_on || !(flags & VPFP_PHASE_TABLE) || (flags & (VPFP_FORCE_GENERIC | VPFP_FORCE_THREE_PASS))) return false;
+  if (nv != 4096 && nv != 8192 && nv != 16384) return false;
+  if ((long)rows * nv < (1L << 22)) return false;
+  if ((ld_in & 1) || (ld_out & 1) || ((uintptr_t)f_in & 15) || ((uintptr_t)f_out & 15)) return false;
+  return true;
+}
+
+template <class P>
+static int launch_rowfft(const rowfft::Args& ra, cudaStream_t st) {
+  P prog;
+  prog.a = ra;
+  int dev = 0;
+  CUDA_TRY(cudaGetDevice(&dev));
+  static std::map<int, int> grid_for;   // per device: SMs x resident CTAs
+  {
+    static std::mutex mu;
+    std::lock_guard<std::mutex> lk(mu);
+    if (!grid_for.count(dev)) {
+      CUDA_TRY(cudaFuncSetAttribute(rowfft::rowfft_kernel<P>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    (int)P::SMEM_BYTES));
+      int nsm = 0, occ = 0;
+      CUDA_TRY(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev));
+      CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, rowfft::rowfft_kernel<P>, P::T, P::SMEM_BYTES));
+      if (occ < 1) return fail(VPFP_ERR_CUDA, "rowfft kernel does not fit an SM");
+      grid_for[dev] = nsm * occ;
+    }
+  }
+  int grid = grid_for[dev];
+  if (grid > ra.nrows) grid = ra.nrows;
+  {
+    ProfScope ps("edfdv.row", st);
+    rowfft::rowfft_kernel<P><<<grid, P::T, P::SMEM_BYTES, st>>>(prog);
+  }
+  CUDA_TRY(cudaGetLastError());
+  return VPFP_OK;
+}
+
+static int run_rowfft(const double* f_in, long ld_in, double* f_out, long ld_out, const double* e, const double* kv,
+                      double dt, int rows, int nv, const ScatterReq* scat, cudaStream_t st) {
+  rowfft::Args ra;
+  memset(&ra, 0, sizeof(ra));
+  ra.fin = f_in; ra.ld_in = ld_in; ra.fout = f_out; ra.ld_out = ld_out; ra.kvec = kv; ra.cvec = e; ra.dt = dt;
+  ra.nrows = rows;
+  int rc = get_twiddles(nv, &ra.twN);
+  if (rc) return rc;
+  if (scat && scat->mode) {
+    ra.peer_mode = scat->mode; ra.nparts = scat->nparts; ra.my_rank = scat->my_rank;
+    ra.lpart = ilog2(nv / scat->nparts);
+    for (int i = 0; i < scat->nparts; ++i) ra.peer[i] = scat->peer[i];
+  }
+  switch (nv) {
+    case 16384: return launch_rowfft<rowfft::Prog<32, 16>>(ra, st);
+    case 8192: return launch_rowfft<rowfft::Prog<16, 16>>(ra, st);
+    default: return launch_rowfft<rowfft::Prog<8, 16>>(ra, st);
+  }
+}
+
 extern "C" {
 
 int vpfp_moments(const double* f, long ld, const double* v, double dv, double* out, long out_ld,
@@ -542,6 +609,8 @@ int vpfp_edfdv_exp(const double* f_in, long ld_in, double* f_out, long ld_out, c
     return fail(VPFP_ERR_ARG, "vpfp_edfdv_exp: bad argument");
   if (!is_pow2(nv) || nv < 4 || nv > (1 << 24))
     return fail(VPFP_ERR_UNSUPPORTED, "e df/dv: <exponential> needs nv = 2^k >= 4 on the b200 backend");
+  if (rowfft_eligible(f_in, ld_in, f_out, ld_out, rows, nv, flags))
+    return run_rowfft(f_in, ld_in, f_out, ld_out, e, kv, dt, rows, nv, nullptr, (cudaStream_t)stream);
   AdvectProg a;
   memset(&a, 0, sizeof(a));
   a.mode = ADV_ROWS; a.op = OP_PHASE; a.N = nv;
@@ -634,6 +703,11 @@ int vpfp_edfdv_exp_scatter(const double* f_in, long ld_in, double* scratch, long
     return fail(VPFP_ERR_ARG, "vpfp_edfdv_exp_scatter: bad argument");
   if (!is_pow2(nv) || !is_pow2(nparts))
     return fail(VPFP_ERR_UNSUPPORTED, "e df/dv scatter: nv and the number of ranks must be powers of two");
+  if (rowfft_eligible(f_in, ld_in, scratch, ld_scratch, rows, nv, flags)) {
+    ScatterReq sr1; sr1.mode = 1; sr1.nparts = nparts; sr1.my_rank = my_rank;
+    for (int i = 0; i < nparts; ++i) sr1.peer[i] = (double*)peer_fv[i];
+    return run_rowfft(f_in, ld_in, scratch, ld_scratch, e, kv, dt, rows, nv, &sr1, (cudaStream_t)stream);
+  }
   AdvectProg a;
   memset(&a, 0, sizeof(a));
   a.mode = ADV_ROWS; a.op = OP_PHASE; a.N = nv;

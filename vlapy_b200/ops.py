@@ -11,7 +11,7 @@ import torch
 from . import _lib
 
 FP_OPS = {"lb": 0, "dg": 1}
-PHASE_EXACT, PHASE_TABLE, FORCE_GENERIC = 0, 1, 2
+PHASE_EXACT, PHASE_TABLE, FORCE_GENERIC, FORCE_THREE_PASS = 0, 1, 2, 4
 
 # number of kernels of this library launched since the last reset (bench.py's gpu_launches claim)
 launch_count = 0
@@ -70,8 +70,14 @@ def edfdv_exp(f, e, kv, dt, out=None, flags=PHASE_EXACT):
     _vec(e, rows, "e"); _vec(kv, nv, "kv")
     _lib.check(_lib.lib().vpfp_edfdv_exp(f.data_ptr(), ld, out.data_ptr(), ldo, e.data_ptr(), kv.data_ptr(),
                                          float(dt), rows, nv, flags, _stream()))
-    _count(adv_launches("rows", nv, rows * nv))
+    _count(1 if rowfft_serves(rows, nv, flags) else adv_launches("rows", nv, rows * nv))
     return out
+
+
+def rowfft_serves(rows, nv, flags):
+    """whether e df/dv runs as the single-pass row kernel (csrc/rowfft.cuh; mirrors rowfft_eligible)"""
+    return bool(flags & PHASE_TABLE) and not (flags & (FORCE_GENERIC | FORCE_THREE_PASS)) \
+        and nv in (4096, 8192, 16384) and rows * nv >= (1 << 22)
 
 
 def vdfdx_exp(f, kx, v, dt, out=None, flags=PHASE_EXACT, density_out=None, dv=None, edge_flags=3):
