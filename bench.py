@@ -69,7 +69,16 @@ def make_config(workload, nx=None, nv=None):
                               "w0": w_epw, "a0": a0, "k0": k0}}
     nu = 0.0 if landau else abs(nu_ld) * 1e-4
     return dict(nx=nx, nv=nv, k0=k0, x=x, kx=kx, one_over_kx=ook, v=v, dv=dv, kv=kv, dt=dt, nu=nu,
-                pulses=pulses, desc=desc, vmax=vmax)
+                pulses=pulses, desc=desc, vmax=vmax, nt=nt)
+
+
+def steps_in_loop(cfg, max_gb=1.0, nmodes=2):
+    """length of one inner loop as vlapy/manager.py:61-83 sets it (the storage cadence: f, fields and
+    series go back to the host once per inner loop); 105 at 16384 x 16384"""
+    steps = int(1e9 * max_gb / (6 * (2 * nmodes * cfg["nv"] + cfg["nx"] * 8) * 8))
+    if steps > cfg["nt"]:
+        steps = int(cfg["nt"] / 1.25)
+    return max(1, steps)
 
 
 def epw_root(k0):
@@ -429,6 +438,7 @@ def gpu_arm(args):
         # ---- end to end through the public inner-loop API with host buffers
         e2e = None
         if not args.no_e2e:
+            Kb, K = K, (args.e2e_steps or steps_in_loop(cfg))      # one inner loop as the manager issues it
             sim, inner = outer_loop.get_sim_config_and_inner_loop_step(params, stuff, K, rules)
             t_arr = cfg["dt"] * np.arange(K)
             d_arr = torch.empty((K, nx), dtype=torch.float64, pin_memory=True)
@@ -446,8 +456,11 @@ def gpu_arm(args):
             d2h = (8 * K * nx * 8 + 7 * K * 8 + K * 2 * nv * 16 + nx * nv * 8 + nx * 8) / K
             e2e = {"value": nx * nv * K / sec, "unit": "cell-updates/s", "h2d_bytes_per_step": h2d,
                    "d2h_bytes_per_step": d2h, "ms_per_step": sec * 1e3 / K,
-                   "note": "one inner-loop call of %d steps: uploads f,e,driver rows; downloads fields, series, "
-                           "stored modes, f, e (storage cadence of vlapy/manager.py:138-150)" % K}
+                   "steps": K,
+                   "note": "one inner-loop call of %d steps (steps_in_loop of vlapy/manager.py:61-83 for this grid): "
+                           "uploads f,e,driver rows; downloads fields, series, stored modes, f, e (storage cadence "
+                           "of vlapy/manager.py:138-150)" % K}
+            K = Kb
         result = dict(ms=ms, launches=launches, clocks=clocks, prof=prof, e2e=e2e, mean_n=mean_n, scaling="strong",
                       parallelism="1 GPU", graph=use_graph)
 
@@ -516,6 +529,7 @@ def main():
     ap.add_argument("--nx", type=int, default=None)
     ap.add_argument("--nv", type=int, default=None)
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--e2e-steps", type=int, default=0, help="steps of the end-to-end inner loop (default: manager's)")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
     # stdout carries exactly ONE JSON line: anything libraries print there (NCCL's version banner)
