@@ -19,6 +19,41 @@ def build(force=False):
     return SO
 
 
+SIMT_SO = os.path.join(HERE, "libvpfp_simt.so")
+SIMT_SRC = os.path.join(HERE, "fp_simt.cpp")
+
+
+def build_simt(force=False):
+    """fp_fast.cuh / fp_reg.cuh compiled for the host with one OS thread per CUDA thread (simt.h)."""
+    deps = [SIMT_SRC, os.path.join(HERE, "simt.h")] + [os.path.join(CSRC, n) for n in
+                                                        ("fp_fast.cuh", "fp_reg.cuh", "vpfp_common.h")]
+    if force or not os.path.exists(SIMT_SO) or any(os.path.getmtime(d) > os.path.getmtime(SIMT_SO) for d in deps):
+        subprocess.check_call(["g++", "-O2", "-ffp-contract=off", "-std=c++17", "-pthread", "-shared", "-fPIC",
+                               "-o", SIMT_SO, SIMT_SRC])
+    return SIMT_SO
+
+
+_simt = None
+
+
+def fp_simt(which, f, v, nu, dt, dv, op, grid=2):
+    """Fokker-Planck kernels run thread by thread on the host: which = 0 fp_fast.cuh, 1 fp_reg.cuh.
+    Returns (f_new, moments[8, rows])."""
+    global _simt
+    if _simt is None:
+        _simt = ctypes.CDLL(build_simt())
+    f = np.ascontiguousarray(f)
+    rows, nv = f.shape
+    out = np.empty_like(f)
+    mom = np.zeros((8, rows))
+    step = (v[-1] - v[0]) / (nv - 1)          # vlapy_b200.ops.linspace_params
+    rc = _simt.emul_fp_simt(c_int(which), _p(f), c_long(nv), _p(out), c_long(nv), c_double(v[0]), c_double(step),
+                            c_double(v[-1]), c_double(nu), c_double(dt), c_double(dv),
+                            c_int(0 if op == "lb" else 1), _p(mom), c_long(rows), c_int(rows), c_int(nv), c_int(grid))
+    assert rc == 0
+    return out, mom
+
+
 _lib = None
 
 

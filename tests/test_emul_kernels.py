@@ -180,3 +180,53 @@ def test_rowfft_program(nv):
     e = np.array([0.05, -0.7, 1.3])
     for dt in (0.37, -0.066):
         assert rel_err(E.edfdv_rowfft(f, e, kv, dt), O.edfdv_exponential(f, e, dt, kv)) < TOL
+
+
+# ---- Fokker-Planck __global__ kernels run thread by thread on the host (tests/emul/simt.h)
+@pytest.mark.parametrize("which", [0, 1], ids=["fp_fast", "fp_reg"])
+@pytest.mark.parametrize("op", ["lb", "dg"])
+@pytest.mark.parametrize("nv", [4096, 16384])
+def test_fp_global_kernels_on_host(which, op, nv):
+    """fp_fast.cuh (row in shared memory) and fp_reg.cuh (row in registers, determinant recurrences,
+    next row prefetched) against the reference's Thomas sweep and row moments: weak (the C5 value) and
+    strong collisions, three rows over two CTAs so that the row loop and the prefetch are exercised."""
+    dv, v, kv = O.velocity_grid(6.4, nv)
+    rng = np.random.default_rng(nv)
+    f = O.shifted_maxwellian(3, v, 1.0, 0.7) * np.array([1.0, 0.7, 1.3])[:, None]
+    f = f * (1 + 1e-3 * rng.standard_normal(f.shape))
+    for nu in (3e-6, 1e-2):
+        ref = O.collision_step(f, v, nu, 0.25, dv, op)
+        out, mom = E.fp_simt(which, f, v, nu, 0.25, dv, op)
+        err = rel_err(out, ref)
+        if err >= TOL:      # stiff: the reference itself is only good to ~1e-10 (see the test above)
+            truth = fp_longdouble(f, v, nu, 0.25, dv, op)
+            assert rel_err(out, truth) < 4 * rel_err(ref, truth) + TOL
+        mref = np.asarray(O.field_moments(out, v, dv))
+        for p in range(6):
+            assert rel_err(mom[p], mref[p]) < 1e-13
+        assert rel_err(mom[6], O.trapz_last(out ** 2, dv)) < 1e-13
+        assert rel_err(mom[7], O.trapz_last(out * np.log(out), dv)) < 1e-13
+
+
+def test_fp_reg_stiffness_and_nan_semantics():
+    """fp_reg.cuh: very stiff systems (unit-diagonal scaling keeps the determinants in [2^-31, 1]) and
+    numpy's NaN for f ln f of a non-positive cell (vlapy/core/step.py:222-224)."""
+    nv = 4096
+    dv, v, kv = O.velocity_grid(6.0, nv)
+    f = O.shifted_maxwellian(2, v, 1.0, 0.3)
+    for nu in (1.0, 30.0, 1e4):
+        for op in ("lb", "dg"):
+            ref = O.collision_step(f, v, nu, 0.1, dv, op)
+            out, mom = E.fp_simt(1, f, v, nu, 0.1, dv, op)
+            assert np.isfinite(out).all()
+            if rel_err(out, ref) >= TOL:
+                # the diagonal b = 1 + 2 nu dt T / dv^2 carries the "1" of (I - dt C) with an absolute
+                # rounding error eps * b: every fp64 evaluation of this system is uncertain at that level
+                bd = 1 + 2 * nu * 0.1 / dv ** 2
+                truth = fp_longdouble(f, v, nu, 0.1, dv, op)
+                assert rel_err(out, truth) < 4 * rel_err(ref, truth) + TOL + 0.25 * np.finfo(float).eps * bd
+    g = f.copy()
+    g[1, 100] = -1e-3
+    out, mom = E.fp_simt(1, g, v, 0.0, 0.1, dv, "lb")
+    assert rel_err(out, g) < 1e-15            # nu = 0: identity matrix
+    assert np.isfinite(mom[7, 0]) and np.isnan(mom[7, 1])

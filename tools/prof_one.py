@@ -15,11 +15,14 @@ kx, kv, v = (torch.from_numpy(cfg[k]).to(dev) for k in ("kx", "kv", "v"))
 out = torch.empty_like(f)
 mom = torch.zeros((8, nx), dtype=torch.float64, device=dev)
 vg = ops.linspace_params(cfg["v"])
-for _ in range(2):
+reps = int(sys.argv[4]) if len(sys.argv) > 4 else 2
+for _ in range(reps):
     if which in ("all", "edfdv"):
         ops.edfdv_exp(f, e, kv, 0.5 * cfg["dt"], out=out, flags=1)
     if which in ("all", "vdfdx"):
         ops.vdfdx_exp(f, kx, v, cfg["dt"], out=out, flags=1)
     if which in ("all", "fp"):
         ops.fp_step(f, v, cfg["nu"], cfg["dt"], cfg["dv"], "lb", out=out, moments_out=mom, vgrid=vg)
+    if which in ("all", "xmodes"):
+        ops.xmodes(f, 2)
 torch.cuda.synchronize()

@@ -53,12 +53,16 @@ def main():
         "poisson": (lambda: ops.poisson(n, ook), 16.0 * nx / 1e9),
         "cd2": (lambda: ops.edfdv_cd2(f, e, 0.125, cfg["dv"], out=out), gb),
     }
+    only = sys.argv[3].split(",") if len(sys.argv) > 3 else None
     for name, (fn, gbytes) in cases.items():
+        if only and not any(name.startswith(o) for o in only):
+            continue
         best, med = timeit(fn)
         res[name] = dict(ms_best=best, ms_med=med, gbs=gbytes / (best * 1e-3))
         print("%-18s best %9.3f ms  med %9.3f ms  %8.1f GB/s (algorithmic)" % (name, best, med, gbytes / (best * 1e-3)), flush=True)
     os.makedirs("gpurun_out", exist_ok=True)
-    json.dump(res, open("gpurun_out/time_ops_%dx%d.json" % (nx, nv), "w"), indent=1)
+    if not only:
+        json.dump(res, open("gpurun_out/time_ops_%dx%d.json" % (nx, nv), "w"), indent=1)
 
 
 if __name__ == "__main__":

@@ -11,7 +11,7 @@ ROOT = os.path.dirname(PKG)
 SO = os.path.join(PKG, "lib", "libvpfp_b200.so")
 SRC = os.path.join(PKG, "csrc", "vpfp_cuda.cu")
 HEADERS = [os.path.join(PKG, "csrc", n) for n in ("vpfp_common.h", "advect.h", "rowops.h", "butterflies.h", "rowfft.cuh",
-                                                    "advect_fast.cuh", "fp_fast.cuh")] + [
+                                                    "advect_fast.cuh", "fp_fast.cuh", "fp_reg.cuh")] + [
     os.path.join(ROOT, "include", "vpfp_b200.h")]
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",

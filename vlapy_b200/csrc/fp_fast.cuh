@@ -27,6 +27,7 @@ struct Args {
   double* mom_out; long mom_ld;
   int rows, nv;
   const double2* logtab;     // 128 x (1/c_i, ln c_i), c_i = 1 + (i + 1/2)/128
+  const double2* logtab256;  // 256 x (1/c_i, ln c_i), c_i = 1 + (i + 1/2)/256 (fp_reg.cuh)
 };
 
 __device__ __forceinline__ double warp_sum(double x) {
@@ -61,10 +62,15 @@ __device__ __forceinline__ double rcp_near(double p, double r) {
 // into c_i (1 + r); ln x = e ln2 + ln c_i + log1p(r), |r| < 2^-8, degree-6 series.  Absolute error
 // ~1e-16 (what a sum of f ln f needs); non-positive, subnormal or non-finite arguments take the
 // library path so that NaN / -inf semantics match numpy (vlapy/core/step.py:222-224).
+#if defined(__CUDACC__)
+__device__ __noinline__ double log_rare(double x) { return log(x); }
+#else
+inline double log_rare(double x) { return log(x); }
+#endif
 __device__ __forceinline__ double log_sum(double x, const double2* __restrict__ tab) {
   const long long bits = __double_as_longlong(x);
   const int ex = (int)((bits >> 52) & 0x7ff);
-  if (bits <= 0 || ex == 0 || ex == 0x7ff) return log(x);
+  if (bits <= 0 || ex == 0 || ex == 0x7ff) return log_rare(x);   // out of line: 32 inlined copies bloat the kernel
   const double m = __longlong_as_double((bits & 0x000fffffffffffffLL) | 0x3ff0000000000000LL);
   const int idx = (int)((bits >> 45) & 127);
   const double2 t = tab[idx];                          // (1/c_i, ln c_i)
@@ -84,7 +90,7 @@ __global__ void __launch_bounds__(T, 1) fp_kernel(const Args a) {
   constexpr int NW = T / 32;
   constexpr int MI = M - 1;          // interior cells of a chunk
   constexpr int H = MI / 2;          // pivots of cells [H, MI) are kept, [0, H) are recomputed
-  extern __shared__ __align__(16) unsigned char smem_raw[];
+  VPFP_DYN_SMEM(smem_raw);
   double* row = reinterpret_cast<double*>(smem_raw);  // NV + T (one pad per chunk)
   double* red = row + NV + T;                          // 64
   double* X = red + 64;                                // 8 * T scratch (separator system / moments)

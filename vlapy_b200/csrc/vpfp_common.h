@@ -21,6 +21,13 @@
 #define VPFP_ALIGN16 __attribute__((aligned(16)))
 #endif
 
+// dynamic shared memory of a __global__ kernel (tests/emul/simt.h provides the host stand-in)
+#if defined(__CUDACC__)
+#define VPFP_DYN_SMEM(name) extern __shared__ __align__(16) unsigned char name[]
+#else
+#define VPFP_DYN_SMEM(name) unsigned char* name = simt_dyn_smem()
+#endif
+
 struct VPFP_ALIGN16 cplx {
   double x, y;
 };

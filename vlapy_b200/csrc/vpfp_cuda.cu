@@ -17,6 +17,7 @@
 #include "advect.h"
 #include "advect_fast.cuh"
 #include "fp_fast.cuh"
+#include "fp_reg.cuh"
 #include "rowfft.cuh"
 #include "rowops.h"
 
@@ -440,24 +441,25 @@ struct PoissonDftProg {
   }
 };
 
-// table of the f ln f logarithm (fp_fast.cuh log_sum): 128 x (1/c_i, ln c_i), cached per device
-static std::map<int, double2*> g_logtab;
-static int get_logtab(const double2** out) {
+// tables of the f ln f logarithm: n x (1/c_i, ln c_i), c_i = 1 + (i + 1/2)/n, cached per device
+// (n = 128: fp_fast.cuh log_sum, n = 256: fp_reg.cuh log_split)
+static std::map<std::pair<int, int>, double2*> g_logtab;
+static int get_logtab(int n, const double2** out) {
   int dev = 0;
   CUDA_TRY(cudaGetDevice(&dev));
   std::lock_guard<std::mutex> lk(g_cache_mu);
-  auto it = g_logtab.find(dev);
+  auto it = g_logtab.find({dev, n});
   if (it != g_logtab.end()) { *out = it->second; return VPFP_OK; }
-  std::vector<double2> h(128);
-  for (int i = 0; i < 128; ++i) {
-    const long double c = 1.0L + ((long double)i + 0.5L) / 128.0L;
+  std::vector<double2> h(n);
+  for (int i = 0; i < n; ++i) {
+    const long double c = 1.0L + ((long double)i + 0.5L) / (long double)n;
     h[i].x = (double)(1.0L / c);
     h[i].y = (double)(-logl((long double)h[i].x));     // consistent with the rounded reciprocal
   }
   double2* d = nullptr;
-  CUDA_TRY(cudaMalloc(&d, sizeof(double2) * 128));
-  CUDA_TRY(cudaMemcpy(d, h.data(), sizeof(double2) * 128, cudaMemcpyHostToDevice));
-  g_logtab[dev] = d;
+  CUDA_TRY(cudaMalloc(&d, sizeof(double2) * n));
+  CUDA_TRY(cudaMemcpy(d, h.data(), sizeof(double2) * n, cudaMemcpyHostToDevice));
+  g_logtab[{dev, n}] = d;
   *out = d;
   return VPFP_OK;
 }
@@ -479,6 +481,41 @@ static int launch_fp_fast(const fpfast::Args& a, cudaStream_t st) {
   {
     ProfScope ps("fp_step", st);
     fpfast::fp_kernel<M, T><<<(unsigned)grid, T, smem, st>>>(a);
+  }
+  CUDA_TRY(cudaGetLastError());
+  return VPFP_OK;
+}
+
+// register-resident Fokker-Planck kernel (fp_reg.cuh): nv = 32 T, next row prefetched with cp.async.
+// VPFP_NO_FP_REG=1 keeps the shared-memory kernel of fp_fast.cuh (A/B measurements).
+static int g_fp_reg_on = -1;
+static bool fp_reg_eligible(const fpfast::Args& a) {
+  if (g_fp_reg_on < 0) {
+    const char* e = getenv("VPFP_NO_FP_REG");
+    g_fp_reg_on = (e && atoi(e)) ? 0 : 1;
+  }
+  if (!g_fp_reg_on) return false;
+  if (a.nv != 4096 && a.nv != 8192 && a.nv != 16384) return false;
+  if ((a.ld_in & 1) || (a.ld_out & 1)) return false;                      // 16-byte row alignment
+  return (((uintptr_t)a.fin | (uintptr_t)a.fout) & 15) == 0;
+}
+
+template <int M, int T>
+static int launch_fp_reg(const fpfast::Args& a, cudaStream_t st) {
+  const size_t smem = fpreg::Geo<M, T>::SMEM;
+  static bool configured = false;
+  if (!configured) {
+    CUDA_TRY(cudaFuncSetAttribute(fpreg::fp_reg_kernel<M, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = true;
+  }
+  int per_sm = (int)((227 * 1024) / (smem + 1024));
+  if (per_sm > (M >= 64 ? 256 : 512) / T) per_sm = (M >= 64 ? 256 : 512) / T;
+  if (per_sm < 1) per_sm = 1;
+  long grid = 148L * per_sm;                      // persistent: every CTA walks rows blockIdx.x, + grid, ...
+  if (grid > a.rows) grid = a.rows;
+  {
+    ProfScope ps("fp_step", st);
+    fpreg::fp_reg_kernel<M, T><<<(unsigned)grid, T, smem, st>>>(a);
   }
   CUDA_TRY(cudaGetLastError());
   return VPFP_OK;
@@ -566,7 +603,8 @@ int vpfp_shutdown(void) {
   for (auto& kv : g_cache) {
     cudaSetDevice(kv.first);
     for (auto& t : kv.second.tw) cudaFree(t.second);
-    if (g_logtab.count(kv.first)) { cudaFree(g_logtab[kv.first]); g_logtab.erase(kv.first); }
+    for (int n : {128, 256})
+      if (g_logtab.count({kv.first, n})) { cudaFree(g_logtab[{kv.first, n}]); g_logtab.erase({kv.first, n}); }
     for (int i = 0; i < 4; ++i)
       if (kv.second.scratch[i]) cudaFree(kv.second.scratch[i]);
   }
@@ -816,9 +854,18 @@ int vpfp_fp_step_linspace(const double* f_in, long ld_in, double* f_out, long ld
   a.fin = f_in; a.ld_in = ld_in; a.fout = f_out; a.ld_out = ld_out;
   a.v0 = v0; a.vstep = vstep; a.vlast = vlast; a.nu = nu; a.dt = dt; a.dv = dv; a.op = op;
   a.mom_out = moments_out; a.mom_ld = mom_ld; a.rows = rows; a.nv = nv;
-  int rc = get_logtab(&a.logtab);
+  int rc = get_logtab(128, &a.logtab);
+  if (rc) return rc;
+  rc = get_logtab(256, &a.logtab256);
   if (rc) return rc;
   cudaStream_t st = (cudaStream_t)stream;
+  if (fp_reg_eligible(a)) {
+    static int m64 = -1;                 // VPFP_FP_REG_M=64: 64 cells per thread, 255 registers (A/B measurements)
+    if (m64 < 0) { const char* e = getenv("VPFP_FP_REG_M"); m64 = (e && atoi(e) == 64) ? 1 : 0; }
+    if (nv == 16384) return m64 ? launch_fp_reg<64, 256>(a, st) : launch_fp_reg<32, 512>(a, st);
+    if (nv == 8192) return m64 ? launch_fp_reg<64, 128>(a, st) : launch_fp_reg<32, 256>(a, st);
+    return launch_fp_reg<32, 128>(a, st);
+  }
   switch (nv) {
     case 16384: return launch_fp_fast<32, 512>(a, st);
     case 8192: return launch_fp_fast<16, 512>(a, st);
