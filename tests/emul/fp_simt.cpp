@@ -32,7 +32,7 @@ extern "C" int emul_fp_simt(int which, const double* f_in, long ld_in, double* f
   fpfast::Args a;
   a.fin = f_in; a.ld_in = ld_in; a.fout = f_out; a.ld_out = ld_out;
   a.v0 = v0; a.vstep = vstep; a.vlast = vlast; a.nu = nu; a.dt = dt; a.dv = dv; a.op = op;
-  a.mom_out = moments_out; a.mom_ld = mom_ld; a.rows = rows; a.nv = nv; a.logtab = lt.data(); a.logtab256 = lt256.data();
+  a.mom_out = moments_out; a.mom_ld = mom_ld; a.rows = rows; a.nv = nv; a.logtab = lt.data(); a.logtab256 = lt256.data(); a.pf_burst = 0;
   if (which == 1) {
     if (nv == 16384) run_reg<32, 512>(a, grid);
     else if (nv == 8192) run_reg<32, 256>(a, grid);

@@ -53,6 +53,7 @@ alignas(16) inline unsigned char smem[232448];
 
 inline void syncthreads() { cta_bar.wait(0); }
 inline int syncthreads_or(int p) { return cta_bar.wait(p); }
+inline void syncwarp() { (*warps)[threadIdx_.x >> 5].bar.wait(); }
 inline double shfl_xor(double x, int o) {
   Warp& w = (*warps)[threadIdx_.x >> 5];
   const int lane = threadIdx_.x & 31;
@@ -101,6 +102,7 @@ inline unsigned char* simt_dyn_smem() { return simt::smem; }
 #define gridDim simt::gridDim_
 #define __syncthreads() simt::syncthreads()
 #define __syncthreads_or(p) simt::syncthreads_or(p)
+#define __syncwarp() simt::syncwarp()
 #define __shfl_xor_sync(mask, x, o) simt::shfl_xor((x), (o))
 struct double2 { double x, y; };
 inline long long __double_as_longlong(double x) { long long r; memcpy(&r, &x, 8); return r; }

@@ -1,7 +1,7 @@
 """Aggregate an `ncu --page source --csv` export per barrier-separated phase of a kernel."""
 import csv, sys
 rows = list(csv.reader(open(sys.argv[1])))
-hdr = rows[1]; data = rows[2:]
+hdr = rows[1]; data = [r for r in rows[2:] if len(r) == len(hdr)]
 ix = {h: i for i, h in enumerate(hdr)}
 stalls = [h for h in hdr if h.startswith('stall_') and 'Not Issued' not in h]
 def num(s):

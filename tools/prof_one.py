@@ -21,8 +21,8 @@ for _ in range(reps):
         ops.edfdv_exp(f, e, kv, 0.5 * cfg["dt"], out=out, flags=1)
     if which in ("all", "vdfdx"):
         ops.vdfdx_exp(f, kx, v, cfg["dt"], out=out, flags=1)
-    if which in ("all", "fp"):
+    if which in ("all", "fp", "fpx"):
         ops.fp_step(f, v, cfg["nu"], cfg["dt"], cfg["dv"], "lb", out=out, moments_out=mom, vgrid=vg)
-    if which in ("all", "xmodes"):
+    if which in ("all", "xmodes", "fpx"):
         ops.xmodes(f, 2)
 torch.cuda.synchronize()

@@ -207,23 +207,33 @@ __global__ void __launch_bounds__(CB* Geo<L>::TPC) pass13_kernel(const FastArgs 
 #pragma unroll
       for (int j = 0; j < R1; ++j)
         if (valid) gstore<MODE>(a, sim, seq, (long)(r + 8 * j) * N2 + n2, x[q * R1 + j], true);
-      if (MODE == ADV_COLS && a.dens_partial != nullptr) {
-        // charge density of the new f (vlapy/core/field.py:27-36): weighted sum over this tile's
-        // 2*CB real columns, reduced across the CB lanes that share x; one partial row per column tile
-        const int ncols = 2 * a.nseq;
-        const double wa = (valid ? ((2 * seq == 0 && (a.edge_flags & 1)) ? 0.5 * a.dv : a.dv) : 0.0);
-        const double wb = (valid ? ((2 * seq + 1 == ncols - 1 && (a.edge_flags & 2)) ? 0.5 * a.dv : a.dv) : 0.0);
-        constexpr int NSUB = (CB > 32) ? CB / 32 : 1;               // warps per column tile
+    }
+    if (MODE == ADV_COLS && a.dens_partial != nullptr) {
+      // charge density of the new f (vlapy/core/field.py:27-36): weighted sum over this tile's
+      // 2*CB real columns.  Every thread parks its 16 weighted pairs in the (now free) exchange
+      // buffer, D[l][b] with an odd pitch; thread l then adds the CB entries of row l in a fixed
+      // order: one partial row per column tile.
+      double* D = reinterpret_cast<double*>(smem_raw);
+      constexpr int DP = CB + 1;
+      const int ncols = 2 * a.nseq;
+      const double wa = (valid ? ((2 * seq == 0 && (a.edge_flags & 1)) ? 0.5 * a.dv : a.dv) : 0.0);
+      const double wb = (valid ? ((2 * seq + 1 == ncols - 1 && (a.edge_flags & 2)) ? 0.5 * a.dv : a.dv) : 0.0);
+      __syncthreads();                                   // every thread has read its part of S
+#pragma unroll
+      for (int q = 0; q < NA; ++q) {
+        const int r = t + TPC * q;
+#pragma unroll
+        for (int j = 0; j < R1; ++j) D[(r + 8 * j) * DP + b] = wa * x[q * R1 + j].x + wb * x[q * R1 + j].y;
+      }
+      __syncthreads();
+      const int l = threadIdx.x;
+      if (l < L) {
+        double d = 0.0;
+#pragma unroll 8
+        for (int bb = 0; bb < CB; ++bb) d += D[l * DP + bb];
         const int tiles_b = (a.seq_cnt + CB - 1) / CB;
-        const int bt = (a.seq_off / CB + blockIdx.x % tiles_b) * NSUB + (CB > 32 ? b / 32 : 0);
-#pragma unroll
-        for (int j = 0; j < R1; ++j) {
-          double d = wa * x[q * R1 + j].x + wb * x[q * R1 + j].y;
-#pragma unroll
-          for (int o = (CB < 32 ? CB : 32) / 2; o > 0; o >>= 1) d += __shfl_xor_sync(0xffffffffu, d, o);
-          if ((b & 31) == 0 || (CB < 32 && b == 0))
-            a.dens_partial[((long)bt * a.nsim + sim) * a.N + (long)(r + 8 * j) * N2 + n2] = d;
-        }
+        const int bt = a.seq_off / CB + blockIdx.x % tiles_b;
+        a.dens_partial[((long)bt * a.nsim + sim) * a.N + (long)l * N2 + n2] = d;
       }
     }
   }

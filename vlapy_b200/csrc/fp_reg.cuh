@@ -177,6 +177,8 @@ __global__ void __launch_bounds__(T, (M >= 64 ? 256 : 512) / T) fp_reg_kernel(co
   constexpr int NW = T / 32;
   constexpr int MI = G::MI, PITCH = G::PITCH, G1 = G::G1, G2 = G::G2, PCAP = G::PCAP;
   constexpr int U = M / 2;                               // 16-byte units per chunk
+  constexpr int WP = 18;                                 // doubles per lane-row of a warp's transposition slice
+  static_assert(NW * 32 * WP <= (8 + PCAP) * T, "transposition slices fit the scratch area");
   VPFP_DYN_SMEM(smem_raw);
   double* stage = reinterpret_cast<double*>(smem_raw);   // T * PITCH: the row being loaded
   double* red = stage + T * PITCH;                       // 64
@@ -388,8 +390,7 @@ __global__ void __launch_bounds__(T, (M >= 64 ? 256 : 512) / T) fp_reg_kernel(co
       X[t] = rd;
       __syncthreads();
     }
-    // ---------------- interior with known neighbours, in registers.  Parked determinants of a
-    // group [lo, hi): entry j holds N_{lo-1+j}, j = 0 .. hi-lo.
+    // ---------------- interior with known neighbours, in registers
     // chunk -> registers; the staging buffer then receives the CTA's next row
     double c[M];
 #pragma unroll
@@ -400,17 +401,28 @@ __global__ void __launch_bounds__(T, (M >= 64 ? 256 : 512) / T) fp_reg_kernel(co
     const double xe = X[t];
     const double xl = (t > 0) ? X[t - 1] : 0.0;
     __syncthreads();
+    // The back-substitution  x_i = (Z_i - c'_i N_{i-1} x_{i+1}) / N_i  is split into a PREPARE step per
+    // cell, off the critical path (R_i = 1/N_i, c[i] <- Z_i R_i, E_i = c'_i N_{i-1} R_i parked in shared
+    // memory), and a one-FMA recurrence  x_i = c[i] - E_i x_{i+1}.  Three groups of cells
+    // [0,G1) [G1,G2) [G2,MI): the top group is prepared during the forward sweep, the determinants of the
+    // two lower groups are regenerated from a two-value checkpoint.  The cp.async of the next row are
+    // issued one per cell of the forward sweep (a burst of 16 stalls the load/store queue).
     {
       const long rn = r + gridDim.x;
-      if (rn < a.rows) prefetch(rn);
-    }
-    {
+      const bool has_next = rn < a.rows;
+      const double* nsrc = a.fin + (has_next ? rn : r) * a.ld_in + 2 * t;
+      const bool spread = has_next && !a.pf_burst;
+      if (has_next && a.pf_burst) {
+#pragma unroll
+        for (int k = 0; k < U; ++k) cp_async16(stage_t + k * (T / U) * PITCH, nsrc + k * 2 * T);
+      }
       double z = sc * fma(-As, xl, c[0]);                 // right-hand side scaled like the matrix
       c[0] = z;
-      double n2 = 1.0, n1 = bt, k2 = 1.0, k1 = 1.0;       // N_{i-2}, N_{i-1}; checkpoint N_{G1-2}, N_{G1-1}
+      double n2 = 1.0, n1 = bt, k2 = 1.0, k1 = bt;        // N_{i-2}, N_{i-1}; checkpoint N_{G1-2}, N_{G1-1}
       double ab = 0.0, cb = 0.0;
 #pragma unroll
       for (int i = 1; i <= L; ++i) {
+        if (i <= U && spread) cp_async16(stage_t + (i - 1) * (T / U) * PITCH, nsrc + (i - 1) * 2 * T);
         const int o = (i - 1) % TB;
         if (o == 0) { ab = TIE(CAN(i), n1); cb = TIE(CCN(i - 1), n1); }
         const double ai = (o == 0) ? ab : fma(dAn, (double)o, ab);            // a'_i
@@ -421,41 +433,56 @@ __global__ void __launch_bounds__(T, (M >= 64 ? 256 : 512) / T) fp_reg_kernel(co
         z = fma(di, sc * n1, -(ai * z));
         c[i] = z;
         if (i == G2) PV[t] = n1;                          // N_{G2-1}
-        if (i >= G2) PV[(i - G2 + 1) * T + t] = ni;
+        if (i >= G2) PV[(i - G2 + 1) * T + t] = ni;       // slot j of the top group: N_{G2-1+j}
         if (i == G1 - 1) { k2 = n1; k1 = ni; }
         n2 = n1; n1 = ni;
       }
-      double x = z * rcp_fast(n1);
-      c[L] = x;
+      static_assert(U <= L, "one cp.async per forward step");
+      cp_async_commit();
+#pragma unroll
+      for (int i = G2; i <= L; ++i) {                     // prepare the top group from its parked determinants
+        const double R = rcp_fast(PV[(i - G2 + 1) * T + t]);
+        const double e = (CCN(i) * PV[(i - G2) * T + t]) * R;
+        c[i] *= R;
+        if (i < L) PV[(i - G2) * T + t] = e;
+      }
+      double x = c[L];
 #pragma unroll
       for (int i = L - 1; i >= G2; --i) {
-        x = fma(-(CCN(i) * PV[(i - G2) * T + t]), x, c[i]) * rcp_fast(PV[(i - G2 + 1) * T + t]);
+        x = fma(-PV[(i - G2) * T + t], x, c[i]);
         c[i] = x;
       }
       n2 = k2; n1 = k1;                                   // regenerate N_{G1} .. N_{G2-1}
-      PV[t] = n1;
 #pragma unroll
       for (int i = G1; i < G2; ++i) {
         const double ni = fma(bt, n1, -((TIE(CAN(i), n1) * CCN(i - 1)) * n2));
-        PV[(i - G1 + 1) * T + t] = ni;
+        const double R = rcp_fast(ni);
+        c[i] *= R;
+        PV[(i - G1) * T + t] = (CCN(i) * n1) * R;
         n2 = n1; n1 = ni;
       }
 #pragma unroll
       for (int i = G2 - 1; i >= G1; --i) {
-        x = fma(-(CCN(i) * PV[(i - G1) * T + t]), x, c[i]) * rcp_fast(PV[(i - G1 + 1) * T + t]);
+        x = fma(-PV[(i - G1) * T + t], x, c[i]);
         c[i] = x;
       }
-      n2 = 1.0; n1 = bt;                                  // regenerate N_0 .. N_{G1-1}
-      PV[t] = 1.0; PV[T + t] = bt;
+      {                                                   // cell 0: N_{-1} = 1, N_0 = b'
+        const double R = rcp_fast(bt);
+        c[0] *= R;
+        PV[t] = CCN(0) * R;
+      }
+      n2 = 1.0; n1 = bt;                                  // regenerate N_1 .. N_{G1-1}
 #pragma unroll
       for (int i = 1; i < G1; ++i) {
         const double ni = fma(bt, n1, -((TIE(CAN(i), n1) * CCN(i - 1)) * n2));
-        PV[(i + 1) * T + t] = ni;
+        const double R = rcp_fast(ni);
+        c[i] *= R;
+        PV[i * T + t] = (CCN(i) * n1) * R;
         n2 = n1; n1 = ni;
       }
 #pragma unroll
       for (int i = G1 - 1; i >= 0; --i) {
-        x = fma(-(CCN(i) * PV[i * T + t]), x, c[i]) * rcp_fast(PV[(i + 1) * T + t]);
+        x = fma(-PV[i * T + t], x, c[i]);
         c[i] = x;
       }
       c[M - 1] = xe;
@@ -465,11 +492,27 @@ __global__ void __launch_bounds__(T, (M >= 64 ? 256 : 512) / T) fp_reg_kernel(co
 #undef CAN
 #undef TIE
 #undef CCN
-    // ---------------- store (from registers) + moments of the new row
+    // ---------------- store.  A warp owns 32 consecutive chunks = one contiguous piece of the row, but a
+    // thread's chunk is 256 bytes away from its neighbour's: stored straight from registers, every
+    // 16-byte store instruction would touch 32 different 128-byte lines.  The warp transposes 16 cells
+    // per lane at a time through its own slice of the (now idle) scratch area and writes whole lines.
+    __syncthreads();                                      // every warp is done with X and its parked values
     {
-      double* dst = a.fout + r * a.ld_out + s;
+      double* wbuf = X + warp * (32 * WP);
+      double* drow = a.fout + r * a.ld_out + (long)warp * 32 * M;
 #pragma unroll
-      for (int j = 0; j < U; ++j) store2(dst + 2 * j, c[2 * j], c[2 * j + 1]);
+      for (int hh = 0; hh < M / 16; ++hh) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) store2(wbuf + lane * WP + 2 * j, c[16 * hh + 2 * j], c[16 * hh + 2 * j + 1]);
+        __syncwarp();
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const int pc = k * 4 + (lane >> 3), o = (lane & 7) * 2;     // lane-row (chunk of the warp), offset
+          const double2 v2 = ld2(wbuf + pc * WP + o);
+          store2(drow + pc * M + 16 * hh + o, v2.x, v2.y);
+        }
+        __syncwarp();
+      }
     }
     if (a.mom_out) {
       // v^p moments from local monomial sums: v_i = vc + (i - I0) vstep, so

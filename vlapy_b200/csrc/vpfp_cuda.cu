@@ -361,7 +361,7 @@ static int run_advect(AdvectProg a, cudaStream_t st, int flags = VPFP_PHASE_EXAC
     int dens_tiles = 0;
     if (dens && dens->out && a.mode == ADV_COLS) {
       const int CB = (pl.N1 == 128) ? 16 : (pl.N1 == 64 ? 32 : 64);
-      dens_tiles = ((a.nseq + CB - 1) / CB) * (CB > 32 ? CB / 32 : 1);
+      dens_tiles = (a.nseq + CB - 1) / CB;
       void* scr = nullptr;
       rc = get_scratch(SCR_DENSITY, sizeof(double) * (size_t)dens_tiles * a.nsim * a.N, &scr);
       if (rc) return rc;
@@ -576,6 +576,11 @@ static int run_rowfft(const double* f_in, long ld_in, double* f_out, long ld_out
   memset(&ra, 0, sizeof(ra));
   ra.fin = f_in; ra.ld_in = ld_in; ra.fout = f_out; ra.ld_out = ld_out; ra.kvec = kv; ra.cvec = e; ra.dt = dt;
   ra.nrows = rows;
+  {
+    static int pf = -1;                  // VPFP_ROWFFT_L2PF=n: rows of L2 prefetch ahead (default 2, 0 = off)
+    if (pf < 0) { const char* e = getenv("VPFP_ROWFFT_L2PF"); pf = e ? atoi(e) : 2; }
+    ra.l2_prefetch = pf;
+  }
   int rc = get_twiddles(nv, &ra.twN);
   if (rc) return rc;
   if (scat && scat->mode) {
@@ -858,6 +863,11 @@ int vpfp_fp_step_linspace(const double* f_in, long ld_in, double* f_out, long ld
   if (rc) return rc;
   rc = get_logtab(256, &a.logtab256);
   if (rc) return rc;
+  {
+    static int burst = -1;               // VPFP_FP_BURST=1: A/B of the prefetch issue pattern (fp_reg.cuh)
+    if (burst < 0) { const char* e = getenv("VPFP_FP_BURST"); burst = (e && atoi(e)) ? 1 : 0; }
+    a.pf_burst = burst;
+  }
   cudaStream_t st = (cudaStream_t)stream;
   if (fp_reg_eligible(a)) {
     static int m64 = -1;                 // VPFP_FP_REG_M=64: 64 cells per thread, 255 registers (A/B measurements)
