@@ -118,19 +118,23 @@ struct Geo {
 // ln x = e ln2 + ln c_i + log1p(r) with a 256-entry table (c_i = 1 + (i + 1/2)/256, |r| < 2^-9) and a
 // degree-4 series: absolute error < 6e-15, which a weighted sum with sum(w f) ~ 1 does not see at
 // the 1e-12 level.  Returns ln c_i + log1p(r) and the exponent e separately (the caller sums
-// f * e and multiplies by ln2 once).  Non-positive, subnormal or non-finite arguments: library path
-// with numpy's NaN / -inf semantics (vlapy/core/step.py:222-224).
-__device__ __forceinline__ double log_split(double x, const double2* __restrict__ tab256, double* e_out) {
+// f * e and multiplies by ln2 once).  BRANCH FREE, so that the 32 logarithms of a chunk interleave:
+// non-positive, subnormal or non-finite arguments only raise `bad`, and the caller then redoes the
+// two logarithm sums of the chunk on the library path (numpy's NaN / -inf semantics,
+// vlapy/core/step.py:222-224).
+__device__ __forceinline__ double log_split(double x, const double2* __restrict__ tab256, double* e_out, int* bad) {
   const long long bits = __double_as_longlong(x);
-  const int ex = (int)((bits >> 52) & 0x7ff);
-  if (bits <= 0 || ex == 0 || ex == 0x7ff) { *e_out = 0.0; return fpfast::log_rare(x); }
+  const int hi = (int)(bits >> 32);
+  *bad |= ((unsigned)(hi - 0x00100000) >= (unsigned)(0x7ff00000 - 0x00100000)) ? 1 : 0;
   const double m = __longlong_as_double((bits & 0x000fffffffffffffLL) | 0x3ff0000000000000LL);
-  const double2 tb = tab256[(int)((bits >> 44) & 255)];   // (1/c_i, ln c_i)
+  const double2 tb = tab256[(hi >> 12) & 255];            // (1/c_i, ln c_i)
   const double r = fma(m, tb.x, -1.0);
   double p = fma(r, -0.25, 1.0 / 3.0);
   p = fma(r, p, -0.5);
   p = fma(r * r, p, r);
-  *e_out = (double)(ex - 1023);
+  // biased exponent -> double without a conversion instruction: 2^52 + ex as a bit pattern
+  const double eb = __longlong_as_double(0x4330000000000000LL | (long long)((hi >> 20) & 0x7ff));
+  *e_out = eb - 4503599627371519.0;                       // 2^52 + 1023
   return tb.y + p;
 }
 
@@ -141,13 +145,14 @@ __host__ __device__ constexpr double kpow(double d, int q) { return q == 0 ? 1.0
 // se = sum x e.  W = 1: whole cell; W = -1/2: np.trapz correction of an end cell.
 struct ChunkSums {
   double mu[6], s2, sl, se;
+  int bad;
 };
 template <int M, int I, int HALF>
 __device__ __forceinline__ void chunk_terms(ChunkSums& S, double x, const double2* LT) {
   constexpr double d = (double)I - 0.5 * (double)(M - 1);
   const double xs = HALF ? -0.5 * x : x;
   double e;
-  const double lx = log_split(x, LT, &e);
+  const double lx = log_split(x, LT, &e, &S.bad);
   S.mu[0] += xs;
   S.mu[1] = fma(xs, kpow(d, 1), S.mu[1]);
   S.mu[2] = fma(xs, kpow(d, 2), S.mu[2]);
@@ -164,10 +169,16 @@ struct ChunkLoop {
     chunk_terms<M, I, 0>(S, c[I], LT);
     ChunkLoop<M, I + 1>::run(S, c, LT);
   }
+  // library path of the two logarithm sums (a chunk holds a cell that log_split cannot take)
+  __device__ __forceinline__ static void rare(double& sl, const double (&c)[M]) {
+    sl = fma(c[I], fpfast::log_rare(c[I]), sl);
+    ChunkLoop<M, I + 1>::rare(sl, c);
+  }
 };
 template <int M>
 struct ChunkLoop<M, M> {
   __device__ __forceinline__ static void run(ChunkSums&, const double (&)[M], const double2*) {}
+  __device__ __forceinline__ static void rare(double&, const double (&)[M]) {}
 };
 
 template <int M, int T>
@@ -390,45 +401,34 @@ __global__ void __launch_bounds__(T, (M >= 64 ? 256 : 512) / T) fp_reg_kernel(co
       X[t] = rd;
       __syncthreads();
     }
-    // ---------------- interior with known neighbours, in registers
-    // chunk -> registers; the staging buffer then receives the CTA's next row
-    double c[M];
-#pragma unroll
-    for (int j = 0; j < U; ++j) {
-      const double2 f2 = ld2_fresh(sp + 2 * j);
-      c[2 * j] = f2.x; c[2 * j + 1] = f2.y;
-    }
-    const double xe = X[t];
-    const double xl = (t > 0) ? X[t - 1] : 0.0;
-    __syncthreads();
+    // ---------------- interior with known neighbours.  The forward sweep reads the staged chunk (pairs,
+    // one ahead, like the spike sweeps) and leaves the eliminated right-hand sides Z_i in REGISTERS:
+    // from here on the chunk lives in c[], and once every thread is through, the staging buffer
+    // receives the CTA's next row.
     // The back-substitution  x_i = (Z_i - c'_i N_{i-1} x_{i+1}) / N_i  is split into a PREPARE step per
     // cell, off the critical path (R_i = 1/N_i, c[i] <- Z_i R_i, E_i = c'_i N_{i-1} R_i parked in shared
     // memory), and a one-FMA recurrence  x_i = c[i] - E_i x_{i+1}.  Three groups of cells
-    // [0,G1) [G1,G2) [G2,MI): the top group is prepared during the forward sweep, the determinants of the
-    // two lower groups are regenerated from a two-value checkpoint.  The cp.async of the next row are
-    // issued one per cell of the forward sweep (a burst of 16 stalls the load/store queue).
+    // [0,G1) [G1,G2) [G2,MI): the determinants of the top group are parked by the forward sweep, those of
+    // the two lower groups are regenerated from a two-value checkpoint.  The cp.async of the next row
+    // are issued one per prepared cell (a burst of 16 stalls the load/store queue).
+    double c[M];
+    const double xe = X[t];
     {
-      const long rn = r + gridDim.x;
-      const bool has_next = rn < a.rows;
-      const double* nsrc = a.fin + (has_next ? rn : r) * a.ld_in + 2 * t;
-      const bool spread = has_next && !a.pf_burst;
-      if (has_next && a.pf_burst) {
-#pragma unroll
-        for (int k = 0; k < U; ++k) cp_async16(stage_t + k * (T / U) * PITCH, nsrc + k * 2 * T);
-      }
-      double z = sc * fma(-As, xl, c[0]);                 // right-hand side scaled like the matrix
+      const double xl = (t > 0) ? X[t - 1] : 0.0;
+      double2 lp = ld2_fresh(sp), lq = ld2_fresh(sp + 2);
+      double z = sc * fma(-As, xl, lp.x);                 // right-hand side scaled like the matrix
       c[0] = z;
       double n2 = 1.0, n1 = bt, k2 = 1.0, k1 = bt;        // N_{i-2}, N_{i-1}; checkpoint N_{G1-2}, N_{G1-1}
       double ab = 0.0, cb = 0.0;
 #pragma unroll
       for (int i = 1; i <= L; ++i) {
-        if (i <= U && spread) cp_async16(stage_t + (i - 1) * (T / U) * PITCH, nsrc + (i - 1) * 2 * T);
+        if ((i & 1) == 0) { lp = lq; if (i + 2 <= L) lq = ld2_fresh(sp + i + 2); }
         const int o = (i - 1) % TB;
         if (o == 0) { ab = TIE(CAN(i), n1); cb = TIE(CCN(i - 1), n1); }
         const double ai = (o == 0) ? ab : fma(dAn, (double)o, ab);            // a'_i
         const double ck = (o == 0) ? cb : fma(-dAn, (double)o, cb);           // c'_{i-1}
         const double ni = fma(bt, n1, -((ai * ck) * n2));
-        double di = c[i];
+        double di = (i & 1) ? lp.y : lp.x;
         if (i == L) di = fma(-Ce1, xe, di);
         z = fma(di, sc * n1, -(ai * z));
         c[i] = z;
@@ -437,10 +437,24 @@ __global__ void __launch_bounds__(T, (M >= 64 ? 256 : 512) / T) fp_reg_kernel(co
         if (i == G1 - 1) { k2 = n1; k1 = ni; }
         n2 = n1; n1 = ni;
       }
-      static_assert(U <= L, "one cp.async per forward step");
-      cp_async_commit();
+      __syncthreads();                                    // every thread is done with the staged row
+      const long rn = r + gridDim.x;
+      const bool has_next = rn < a.rows;
+      const double* nsrc = a.fin + (has_next ? rn : r) * a.ld_in + 2 * t;
+      const bool spread = has_next && !a.pf_burst;
+      if (has_next && a.pf_burst) {
+#pragma unroll
+        for (int k = 0; k < U; ++k) cp_async16(stage_t + k * (T / U) * PITCH, nsrc + k * 2 * T);
+      }
+      int pf = 0;                                         // compile-time after unrolling: cp.async issued so far
+#define PF_ONE()                                                                                   \
+  if (pf < U) {                                                                                    \
+    if (spread) cp_async16(stage_t + pf * (T / U) * PITCH, nsrc + pf * 2 * T);                     \
+    ++pf;                                                                                          \
+  }
 #pragma unroll
       for (int i = G2; i <= L; ++i) {                     // prepare the top group from its parked determinants
+        PF_ONE()
         const double R = rcp_fast(PV[(i - G2 + 1) * T + t]);
         const double e = (CCN(i) * PV[(i - G2) * T + t]) * R;
         c[i] *= R;
@@ -455,6 +469,7 @@ __global__ void __launch_bounds__(T, (M >= 64 ? 256 : 512) / T) fp_reg_kernel(co
       n2 = k2; n1 = k1;                                   // regenerate N_{G1} .. N_{G2-1}
 #pragma unroll
       for (int i = G1; i < G2; ++i) {
+        PF_ONE()
         const double ni = fma(bt, n1, -((TIE(CAN(i), n1) * CCN(i - 1)) * n2));
         const double R = rcp_fast(ni);
         c[i] *= R;
@@ -474,12 +489,16 @@ __global__ void __launch_bounds__(T, (M >= 64 ? 256 : 512) / T) fp_reg_kernel(co
       n2 = 1.0; n1 = bt;                                  // regenerate N_1 .. N_{G1-1}
 #pragma unroll
       for (int i = 1; i < G1; ++i) {
+        PF_ONE()
         const double ni = fma(bt, n1, -((TIE(CAN(i), n1) * CCN(i - 1)) * n2));
         const double R = rcp_fast(ni);
         c[i] *= R;
         PV[i * T + t] = (CCN(i) * n1) * R;
         n2 = n1; n1 = ni;
       }
+      static_assert(MI - 1 >= U, "one cp.async per prepared cell covers the row");
+#undef PF_ONE
+      cp_async_commit();
 #pragma unroll
       for (int i = G1 - 1; i >= 0; --i) {
         x = fma(-PV[i * T + t], x, c[i]);
@@ -520,10 +539,17 @@ __global__ void __launch_bounds__(T, (M >= 64 ? 256 : 512) / T) fp_reg_kernel(co
       ChunkSums S;
 #pragma unroll
       for (int q = 0; q < 6; ++q) S.mu[q] = 0.0;
-      S.s2 = 0.0; S.sl = 0.0; S.se = 0.0;
+      S.s2 = 0.0; S.sl = 0.0; S.se = 0.0; S.bad = 0;
       ChunkLoop<M, 0>::run(S, c, LT);
       if (first_thread) chunk_terms<M, 0, 1>(S, c[0], LT);              // np.trapz: half weight at both ends
       if (last_thread) chunk_terms<M, M - 1, 1>(S, c[M - 1], LT);
+      if (S.bad) {
+        double sl = 0.0;
+        ChunkLoop<M, 0>::rare(sl, c);
+        if (first_thread) sl = fma(-0.5 * c[0], fpfast::log_rare(c[0]), sl);
+        if (last_thread) sl = fma(-0.5 * c[M - 1], fpfast::log_rare(c[M - 1]), sl);
+        S.sl = sl; S.se = 0.0;
+      }
       const double dl = a.vstep, vc = fma(0.5 * (double)(M - 1), dl, vs);
       const double dl2 = dl * dl;
       const double n0 = S.mu[0], n1 = S.mu[1] * dl, n2 = S.mu[2] * dl2, n3 = S.mu[3] * (dl2 * dl),

@@ -577,8 +577,8 @@ static int run_rowfft(const double* f_in, long ld_in, double* f_out, long ld_out
   ra.fin = f_in; ra.ld_in = ld_in; ra.fout = f_out; ra.ld_out = ld_out; ra.kvec = kv; ra.cvec = e; ra.dt = dt;
   ra.nrows = rows;
   {
-    static int pf = -1;                  // VPFP_ROWFFT_L2PF=n: rows of L2 prefetch ahead (default 2, 0 = off)
-    if (pf < 0) { const char* e = getenv("VPFP_ROWFFT_L2PF"); pf = e ? atoi(e) : 2; }
+    static int pf = -1;                  // VPFP_ROWFFT_L2PF=n: rows of L2 prefetch ahead (default 1, 0 = off)
+    if (pf < 0) { const char* e = getenv("VPFP_ROWFFT_L2PF"); pf = e ? atoi(e) : 1; }
     ra.l2_prefetch = pf;
   }
   int rc = get_twiddles(nv, &ra.twN);
