@@ -28,11 +28,11 @@ extern "C" int emul_fp_simt(int which, const double* f_in, long ld_in, double* f
                             double* moments_out, long mom_ld, int rows, int nv, int grid) {
   std::vector<double2> lt, lt256;
   fill_logtab(lt, 128);
-  fill_logtab(lt256, 256);
+  fill_logtab(lt256, 64);
   fpfast::Args a;
   a.fin = f_in; a.ld_in = ld_in; a.fout = f_out; a.ld_out = ld_out;
   a.v0 = v0; a.vstep = vstep; a.vlast = vlast; a.nu = nu; a.dt = dt; a.dv = dv; a.op = op;
-  a.mom_out = moments_out; a.mom_ld = mom_ld; a.rows = rows; a.nv = nv; a.logtab = lt.data(); a.logtab256 = lt256.data(); a.pf_burst = 0;
+  a.mom_out = moments_out; a.mom_ld = mom_ld; a.rows = rows; a.nv = nv; a.logtab = lt.data(); a.logtab64 = lt256.data(); a.pf_burst = 0;
   if (which == 1) {
     if (nv == 16384) run_reg<32, 512>(a, grid);
     else if (nv == 8192) run_reg<32, 256>(a, grid);

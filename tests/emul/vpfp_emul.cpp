@@ -194,7 +194,7 @@ static void run_rowfft(const P& prog) {
   unsigned char* base = smem.data();
   base += (16 - ((uintptr_t)base & 15)) & 15;
   for (int tid = 0; tid < P::T; ++tid) prog.init(tid, regs[tid], base);
-  for (int tid = 0; tid < P::T; ++tid) prog.load_row(0, tid, regs[tid]);
+  for (int tid = 0; tid < P::T; ++tid) prog.prefetch_row(0, tid, base);
   for (long row = 0; row < prog.a.nrows; ++row)
     for (int ph = 0; ph < P::NPH; ++ph)
       for (int tid = 0; tid < P::T; ++tid)

@@ -284,8 +284,14 @@ struct P2Layout {
   static constexpr int T_ELEMS = 2 * L * CB;
 };
 
-template <int L, int MODE, int CB, bool PF>
-__global__ void __launch_bounds__(CB * 2 * Geo<L>::TPC, PF ? 2 : 4) pass2_kernel(const FastArgs a, const int t1_chunk) {
+// PFM: 0 direct loads (4 CTAs/SM hide the latency), 1 next tile staged with cp.async in a second
+// buffer (2 CTAs/SM), 2 next tile prefetched with cp.async INTO THE EXCHANGE BUFFER: a thread reads
+// last (inverse step A') and first (step A of the next tile) the same 16 slots of S, so it prefetches
+// exactly those, needs no barrier for them and the kernel keeps the shared-memory footprint of PFM 0.
+template <int L, int MODE, int CB, int PFM>
+__global__ void __launch_bounds__(CB * 2 * Geo<L>::TPC, PFM == 1 ? 2 : 4) pass2_kernel(const FastArgs a, const int t1_chunk) {
+  constexpr bool PF = (PFM == 1);
+  constexpr bool AL = (PFM == 2);
   using G = Geo<L>;
   using LY = P2Layout<L, MODE, CB>;
   constexpr int R1 = G::R1, TPC = G::TPC, NA = G::NA;
@@ -299,8 +305,8 @@ __global__ void __launch_bounds__(CB * 2 * Geo<L>::TPC, PF ? 2 : 4) pass2_kernel
   cplx* BASE = PT + 2 * CB * NPT;                     // [2 groups][2 chan][CB]
   cplx* TWL = BASE + 4 * CB;                          // [L]     exp(-2 pi i m / L)
   cplx* TWT = TWL + L;                                // [2][L]  four-step twiddles W_N^(n2 k1) of the staged tile
-  cplx* TWC = TWT + 2 * L;                            // [2][L]  the same for the tile being transformed (PF only)
-  double* PHI = reinterpret_cast<double*>(TWC + (PF ? 2 * L : 0));    // [2 chan][CB]
+  cplx* TWC = TWT + 2 * L;                            // [2][L]  PF: twiddles of the tile being transformed; AL: second buffer
+  double* PHI = reinterpret_cast<double*>(TWC + ((PF || AL) ? 2 * L : 0));    // [2 chan][CB]
 
   // thread roles: b = packed sequence, u = 0..R1-1 (step A: group u / TPC, r-slot u % TPC)
   int b, u;
@@ -362,9 +368,40 @@ __global__ void __launch_bounds__(CB * 2 * Geo<L>::TPC, PF ? 2 : 4) pass2_kernel
     cp_async_commit();
   };
 
+  // PFM 2: this thread's 16 elements of the tile of group pair t1 -> its own slots of S, and its share
+  // of the tile's four-step twiddles -> twbuf
+  auto prefetch_own = [&](int t1, cplx* twbuf) {
+    const int k1g0 = (t1 == 0) ? 0 : t1, k1g1 = (t1 == 0) ? (int)(N1 / 2) : (int)(N1 - t1);
+    const int gq = u / TPC, taq = u % TPC;
+    const long k1 = gq ? k1g1 : k1g0;
+#pragma unroll
+    for (int q = 0; q < NA; ++q)
+#pragma unroll
+      for (int j = 0; j < R1; ++j) {
+        const int r = taq + TPC * q;
+        cplx* dst = S + LY::sidx(gq, j, r, b);
+        const long n = k1 * L + r + 8 * j;
+        if (!valid) { *dst = cmake(0.0, 0.0); continue; }
+        if (MODE == ADV_COLS) {
+          cp_async16(dst, a.fout + ((long)sim * N + n) * a.ld_out + 2 * (long)seq);
+        } else {
+          const long ra = 2 * (long)seq, rb = ra + 1;
+          cp_async8(&dst->x, a.fout + ra * a.ld_out + n);
+          if (rb < a.nrows) cp_async8(&dst->y, a.fout + rb * a.ld_out + n);
+          else dst->y = a.phantom ? a.phantom[n] : 0.0;
+        }
+      }
+    for (int w = threadIdx.x; w < 2 * L; w += NT) {
+      const int n2 = w % L, gg = w / L;
+      cp_async16(twbuf + w, a.twN + (long)n2 * (gg ? k1g1 : k1g0));
+    }
+    cp_async_commit();
+  };
+
   for (int w = threadIdx.x; w < L; w += NT) TWL[w] = ldg_c(a.twL2 + w);
   const int t1_begin = chunk * t1_chunk, t1_end = min(T1, (chunk + 1) * t1_chunk);
   if (PF) prefetch(t1_begin);
+  if (AL) prefetch_own(t1_begin, TWT);
 
   if (!a.exact) {
     // phi = (K[1] dt) c ; G = exp(-i N1 phi); PT[j] = G^j = H[j>>3] * Lo[j&7]
@@ -420,6 +457,19 @@ __global__ void __launch_bounds__(CB * 2 * Geo<L>::TPC, PF ? 2 : 4) pass2_kernel
       TWI = TWC;
       __syncthreads();                                 // STG consumed, S free (previous tile's readers done)
       if (t1 + 1 < t1_end) prefetch(t1 + 1);
+    } else if (AL) {
+      // own slots of S and this tile's twiddle buffer were filled by prefetch_own one tile earlier
+      cplx* TWcur = ((t1 - t1_begin) & 1) ? TWC : TWT;
+      TWI = TWcur;
+      cp_async_wait_all();
+      __syncthreads();                                 // twiddles (and BASE) visible; previous tile done with BASE
+#pragma unroll
+      for (int q = 0; q < NA; ++q)
+#pragma unroll
+        for (int j = 0; j < R1; ++j) {
+          const int r = ta + TPC * q;
+          x[q * R1 + j] = cmul(S[LY::sidx(g, j, r, b)], TWcur[g * L + r + 8 * j]);
+        }
     } else {
       // direct loads (4 CTAs per SM hide the latency); twiddles of this tile into shared memory
 #pragma unroll
@@ -546,6 +596,11 @@ __global__ void __launch_bounds__(CB * 2 * Geo<L>::TPC, PF ? 2 : 4) pass2_kernel
       const int r = ta + TPC * q;
 #pragma unroll
       for (int m = 0; m < R1; ++m) x[q * R1 + m] = S[LY::sidx(g, m, r, b)];
+    }
+    if (AL && t1 + 1 < t1_end) prefetch_own(t1 + 1, ((t1 + 1 - t1_begin) & 1) ? TWC : TWT);
+#pragma unroll
+    for (int q = 0; q < NA; ++q) {
+      const int r = ta + TPC * q;
       fftR<R1, 1>(x + q * R1);
 #pragma unroll
       for (int j = 0; j < R1; ++j) {
@@ -559,9 +614,9 @@ __global__ void __launch_bounds__(CB * 2 * Geo<L>::TPC, PF ? 2 : 4) pass2_kernel
 }
 
 template <int L, int CB>
-constexpr size_t pass2_smem(int mode, bool pf) {
-  return sizeof(cplx) * (size_t)(((mode == ADV_ROWS) ? CB * 2 * (L / 8) * 9 : 2 * L * CB) + (pf ? 2 * L * CB : 0) +
-                                 2 * CB * (8 + L / 16 + 1) + 4 * CB + 3 * L + (pf ? 2 * L : 0)) +
+constexpr size_t pass2_smem(int mode, int pfm) {
+  return sizeof(cplx) * (size_t)(((mode == ADV_ROWS) ? CB * 2 * (L / 8) * 9 : 2 * L * CB) + (pfm == 1 ? 2 * L * CB : 0) +
+                                 2 * CB * (8 + L / 16 + 1) + 4 * CB + 3 * L + (pfm ? 2 * L : 0)) +
          sizeof(double) * 2 * CB;
 }
 

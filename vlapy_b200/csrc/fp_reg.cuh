@@ -112,24 +112,28 @@ struct Geo {
   static constexpr int PITCH = M + 2;                    // doubles per chunk in the staging buffer
   static constexpr int G1 = MI / 3, G2 = (2 * MI) / 3;   // back-substitution groups [0,G1) [G1,G2) [G2,MI)
   static constexpr int PCAP = imax(imax(G1, G2 - G1), MI - G2) + 1;   // N_{lo-1} .. N_{hi-1} of a group
-  static constexpr size_t SMEM = sizeof(double) * (size_t)(T * PITCH + 64 + 8 * T + PCAP * T + 512);
+  static constexpr size_t SMEM = sizeof(double) * (size_t)(T * PITCH + 64 + 8 * T + PCAP * T + 1024);
 };
 
-// ln x = e ln2 + ln c_i + log1p(r) with a 256-entry table (c_i = 1 + (i + 1/2)/256, |r| < 2^-9) and a
-// degree-4 series: absolute error < 6e-15, which a weighted sum with sum(w f) ~ 1 does not see at
-// the 1e-12 level.  Returns ln c_i + log1p(r) and the exponent e separately (the caller sums
-// f * e and multiplies by ln2 once).  BRANCH FREE, so that the 32 logarithms of a chunk interleave:
-// non-positive, subnormal or non-finite arguments only raise `bad`, and the caller then redoes the
-// two logarithm sums of the chunk on the library path (numpy's NaN / -inf semantics,
-// vlapy/core/step.py:222-224).
-__device__ __forceinline__ double log_split(double x, const double2* __restrict__ tab256, double* e_out, int* bad) {
+// ln x = e ln2 + ln c_i + log1p(r) with a 64-entry table (c_i = 1 + (i + 1/2)/64, |r| < 2^-7) and a
+// degree-6 series: absolute error < 3e-16.  The table is REPLICATED 8 times in shared memory, entry i
+// of replica g at 16-byte slot 8 i + g, and a lane reads replica (lane & 7): the eight lanes that
+// share a 128-bit shared-memory transaction hit eight different bank groups whatever their
+// arguments are (one shared copy costs ~3x the transactions in bank conflicts).
+// Returns ln c_i + log1p(r) and the exponent e separately (the caller sums f * e and multiplies by
+// ln2 once).  BRANCH FREE, so that the 32 logarithms of a chunk interleave: non-positive, subnormal
+// or non-finite arguments only raise `bad`, and the caller then redoes the two logarithm sums of the
+// chunk on the library path (numpy's NaN / -inf semantics, vlapy/core/step.py:222-224).
+__device__ __forceinline__ double log_split(double x, const double2* __restrict__ tab_lane, double* e_out, int* bad) {
   const long long bits = __double_as_longlong(x);
   const int hi = (int)(bits >> 32);
   *bad |= ((unsigned)(hi - 0x00100000) >= (unsigned)(0x7ff00000 - 0x00100000)) ? 1 : 0;
   const double m = __longlong_as_double((bits & 0x000fffffffffffffLL) | 0x3ff0000000000000LL);
-  const double2 tb = tab256[(hi >> 12) & 255];            // (1/c_i, ln c_i)
+  const double2 tb = tab_lane[((hi >> 14) & 63) * 8];     // (1/c_i, ln c_i), this lane's replica
   const double r = fma(m, tb.x, -1.0);
-  double p = fma(r, -0.25, 1.0 / 3.0);
+  double p = fma(r, -1.0 / 6.0, 0.2);
+  p = fma(r, p, -0.25);
+  p = fma(r, p, 1.0 / 3.0);
   p = fma(r, p, -0.5);
   p = fma(r * r, p, r);
   // biased exponent -> double without a conversion instruction: 2^52 + ex as a bit pattern
@@ -195,10 +199,11 @@ __global__ void __launch_bounds__(T, (M >= 64 ? 256 : 512) / T) fp_reg_kernel(co
   double* red = stage + T * PITCH;                       // 64
   double* X = red + 64;                                  // 8 * T scratch (separator system / moments)
   volatile double* PV = X + 8 * T;                       // PCAP * T parked pivots (private to a thread)
-  double2* LT = reinterpret_cast<double2*>(X + 8 * T + PCAP * T);   // 256 entries of the log table
+  double2* LT = reinterpret_cast<double2*>(X + 8 * T + PCAP * T);   // 64 x 8 entries of the log table
   const int t = threadIdx.x;
   const int lane = t & 31, warp = t >> 5;
-  for (int i = t; i < 256; i += T) LT[i] = a.logtab256[i];
+  for (int i = t; i < 512; i += T) LT[i] = a.logtab64[i >> 3];      // 8 replicas, see log_split
+  const double2* const LTl = LT + (t & 7);                          // this lane's replica
   const int s = t * M;
   const double vs0 = fma((double)s, a.vstep, a.v0);      // velocity of the chunk's first cell
   const bool first_thread = (t == 0), last_thread = (t == T - 1);
@@ -540,9 +545,9 @@ __global__ void __launch_bounds__(T, (M >= 64 ? 256 : 512) / T) fp_reg_kernel(co
 #pragma unroll
       for (int q = 0; q < 6; ++q) S.mu[q] = 0.0;
       S.s2 = 0.0; S.sl = 0.0; S.se = 0.0; S.bad = 0;
-      ChunkLoop<M, 0>::run(S, c, LT);
-      if (first_thread) chunk_terms<M, 0, 1>(S, c[0], LT);              // np.trapz: half weight at both ends
-      if (last_thread) chunk_terms<M, M - 1, 1>(S, c[M - 1], LT);
+      ChunkLoop<M, 0>::run(S, c, LTl);
+      if (first_thread) chunk_terms<M, 0, 1>(S, c[0], LTl);             // np.trapz: half weight at both ends
+      if (last_thread) chunk_terms<M, M - 1, 1>(S, c[M - 1], LTl);
       if (S.bad) {
         double sl = 0.0;
         ChunkLoop<M, 0>::rare(sl, c);
@@ -563,15 +568,16 @@ __global__ void __launch_bounds__(T, (M >= 64 ? 256 : 512) / T) fp_reg_kernel(co
       acc[5] = fma(vc, fma(vc, fma(vc, fma(vc, fma(vc, n0, 5.0 * n1), 10.0 * n2), 10.0 * n3), 5.0 * n4), n5);
       acc[6] = S.s2;
       acc[7] = fma(S.se, 6.93147180369123816490e-01, fma(S.se, 1.90821492927058770002e-10, S.sl));
+      // reduction over the CTA: the eight sums of every thread through shared memory (warp w adds
+      // sum w in a fixed order: 8 x 10 shuffles per CTA instead of 80 per thread)
+      __syncthreads();                                    // the transposition slices are idle
 #pragma unroll
-      for (int k = 0; k < 8; ++k) acc[k] = warp_sum(acc[k] * a.dv);
-      __syncthreads();
-      if (lane == 0)
-#pragma unroll
-        for (int k = 0; k < 8; ++k) X[k * NW + warp] = acc[k];
+      for (int k = 0; k < 8; ++k) X[k * T + t] = acc[k] * a.dv;
       __syncthreads();
       for (int k = warp; k < 8; k += NW) {
-        double y = (lane < NW) ? X[k * NW + lane] : 0.0;
+        double y = 0.0;
+#pragma unroll
+        for (int j = 0; j < T / 32; ++j) y += X[k * T + lane + 32 * j];
         y = warp_sum(y);
         if (lane == 0) a.mom_out[(long)k * a.mom_ld + r] = y;
       }

@@ -52,6 +52,24 @@ struct Args {
   int l2_prefetch;      // rows ahead that thread 0 asks L2 to fetch (0: off)
 };
 
+// 16-byte asynchronous copy global -> shared (host emulation: plain copy)
+VPFP_HD void cp_async16(void* smem, const void* gmem) {
+#if defined(__CUDA_ARCH__)
+  const unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(sa), "l"(gmem) : "memory");
+#else
+  memcpy(smem, gmem, 16);
+#endif
+}
+VPFP_HD void cp_async_commit_wait(bool wait) {
+#if defined(__CUDA_ARCH__)
+  if (wait) asm volatile("cp.async.wait_group 0;\n" ::: "memory");
+  else asm volatile("cp.async.commit_group;\n" ::: "memory");
+#else
+  (void)wait;
+#endif
+}
+
 // cos(2 pi j / 32), j = 0..16 (no recursion: folds to an immediate once the caller's loop is unrolled)
 VPFP_HD constexpr double cos32(int j) {
   return j == 0 ? 1.0 : j == 1 ? 0.98078528040323044913 : j == 2 ? 0.92387953251128675613
@@ -164,18 +182,18 @@ struct Prog {
 #endif
   }
 
-  // row (global -> registers) and its phase slope; issued one row ahead (end of the previous row's
-  // last phase), so that the latency is hidden behind the other warps' work
-  VPFP_HD void load_row(long row, int tid, Regs& r) const {
-    r.phi_pi = mul_rn(mul_rn(a.kvec[1], a.dt), a.cvec[row]) * 0.31830988618379067154;
+  // The next row travels global -> shared memory with cp.async while the current row is finished:
+  // thread tid copies the complex points m = tid + T k, k = 0..V-1, to X[m].  These are exactly the
+  // points the thread itself reads last from X in the final phase (inverse stage 1) and first in the
+  // next row's first phase (stage 1: m = m1 L2 + tid + T q), so the copy needs no barrier on either
+  // side, only the thread's own cp.async.wait_group.
+  static_assert(L2 % T == 0, "a thread's stage-1 points are the points it prefetches");
+  VPFP_HD void prefetch_row(long row, int tid, unsigned char* smem) const {
+    cplx* X = xbuf(smem);
     const double* src = a.fin + row * a.ld_in;
 #pragma unroll
-    for (int q = 0; q < NQ1; ++q) {
-      const int rr = tid + T * q;
-#pragma unroll
-      for (int m1 = 0; m1 < R1; ++m1)
-        r.x[q * R1 + m1] = *reinterpret_cast<const cplx*>(src + 2L * (m1 * L2 + rr));
-    }
+    for (int k = 0; k < V; ++k) cp_async16(X + tid + T * k, src + 2L * (tid + T * k));
+    cp_async_commit_wait(false);
   }
 
   // phase tables of the row in registers: G[j] = exp(-i phi S j), Lo[j] = exp(-i phi j),
@@ -242,11 +260,15 @@ struct Prog {
     cplx* x = r.x;
     switch (ph) {
       case 0: {
-        // ---- phase tables; stage 1 on the row loaded one row ahead (load_row)
+        // ---- phase tables; stage 1 on the row that prefetch_row brought into X
+        r.phi_pi = mul_rn(mul_rn(a.kvec[1], a.dt), a.cvec[row]) * 0.31830988618379067154;
         row_tables(tid, r, smem);
+        cp_async_commit_wait(true);
 #pragma unroll
         for (int q = 0; q < NQ1; ++q) {
           const int rr = tid + T * q;
+#pragma unroll
+          for (int m1 = 0; m1 < R1; ++m1) x[q * R1 + m1] = X[m1 * L2 + rr];
           fftR<R1, -1>(x + q * R1);
           twiddle1<false>(x + q * R1, r.w1[q], r.w4[q]);
 #pragma unroll
@@ -376,18 +398,22 @@ struct Prog {
         }
       } break;
       default: {
-        // ---- inverse stage 1, store
+        // ---- inverse stage 1, store; the thread's part of X is free once it is in registers
 #pragma unroll
         for (int q = 0; q < NQ1; ++q) {
           const int rr = tid + T * q;
 #pragma unroll
           for (int k1 = 0; k1 < R1; ++k1) x[q * R1 + k1] = X[k1 * L2 + rr];
+        }
+        if (nextrow >= 0) prefetch_row(nextrow, tid, smem);
+#pragma unroll
+        for (int q = 0; q < NQ1; ++q) {
+          const int rr = tid + T * q;
           twiddle1<true>(x + q * R1, r.w1[q], r.w4[q]);
           fftR<R1, 1>(x + q * R1);
 #pragma unroll
           for (int m1 = 0; m1 < R1; ++m1) store_pair(row, m1 * L2 + rr, x[q * R1 + m1]);
         }
-        if (nextrow >= 0) load_row(nextrow, tid, r);
       } break;
     }
   }
@@ -400,7 +426,7 @@ __global__ void __launch_bounds__(P::T, 1) rowfft_kernel(const P prog) {
   typename P::Regs r;
   const int tid = (int)threadIdx.x;
   prog.init(tid, r, smem_raw);
-  if (blockIdx.x < prog.a.nrows) prog.load_row(blockIdx.x, tid, r);
+  if (blockIdx.x < prog.a.nrows) prog.prefetch_row(blockIdx.x, tid, smem_raw);
   __syncthreads();
   for (long row = blockIdx.x; row < prog.a.nrows; row += gridDim.x) {
     long nxt = row + gridDim.x;

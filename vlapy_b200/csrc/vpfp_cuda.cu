@@ -180,16 +180,16 @@ static int launch_pass13(const fast::FastArgs& fa, cudaStream_t st) {
   return VPFP_OK;
 }
 
-static int g_pass2_prefetch = 0;   // 0: direct loads, 4 CTAs/SM; 1: cp.async staging, 2 CTAs/SM (VPFP_PASS2_PREFETCH)
+static int g_pass2_prefetch = 0;   // pass2_kernel PFM (advect_fast.cuh): 0 direct loads, 1 staged, 2 into the exchange buffer
 
-template <int L, int MODE, bool PF>
+template <int L, int MODE, int PFM>
 static int launch_pass2_pf(const fast::FastArgs& fa, cudaStream_t st) {
   constexpr int CB = (L == 128) ? 8 : (L == 64 ? 16 : 32);
   constexpr int threads = CB * 2 * fast::Geo<L>::TPC;
-  const size_t smem = fast::pass2_smem<L, CB>(MODE, PF);
+  const size_t smem = fast::pass2_smem<L, CB>(MODE, PFM);
   static bool configured = false;
   if (!configured) {
-    int rc = opt_in_smem(fast::pass2_kernel<L, MODE, CB, PF>, smem);
+    int rc = opt_in_smem(fast::pass2_kernel<L, MODE, CB, PFM>, smem);
     if (rc) return rc;
     configured = true;
   }
@@ -200,7 +200,7 @@ static int launch_pass2_pf(const fast::FastArgs& fa, cudaStream_t st) {
   if (grid > 2147483647L) return fail(VPFP_ERR_UNSUPPORTED, "grid too large");
   {
     ProfScope ps(MODE == ADV_COLS ? "vdfdx.pass2" : "edfdv.pass2", st);
-    fast::pass2_kernel<L, MODE, CB, PF><<<(unsigned)grid, threads, smem, st>>>(fa, t1_chunk);
+    fast::pass2_kernel<L, MODE, CB, PFM><<<(unsigned)grid, threads, smem, st>>>(fa, t1_chunk);
   }
   CUDA_TRY(cudaGetLastError());
   return VPFP_OK;
@@ -214,7 +214,8 @@ static int launch_pass2(const fast::FastArgs& fa, cudaStream_t st) {
     if (e) g_pass2_prefetch = atoi(e);
     init = 1;
   }
-  return g_pass2_prefetch ? launch_pass2_pf<L, MODE, true>(fa, st) : launch_pass2_pf<L, MODE, false>(fa, st);
+  if (g_pass2_prefetch == 2) return launch_pass2_pf<L, MODE, 2>(fa, st);
+  return g_pass2_prefetch ? launch_pass2_pf<L, MODE, 1>(fa, st) : launch_pass2_pf<L, MODE, 0>(fa, st);
 }
 
 template <int MODE>
@@ -442,7 +443,7 @@ struct PoissonDftProg {
 };
 
 // tables of the f ln f logarithm: n x (1/c_i, ln c_i), c_i = 1 + (i + 1/2)/n, cached per device
-// (n = 128: fp_fast.cuh log_sum, n = 256: fp_reg.cuh log_split)
+// (n = 128: fp_fast.cuh log_sum, n = 64: fp_reg.cuh log_split)
 static std::map<std::pair<int, int>, double2*> g_logtab;
 static int get_logtab(int n, const double2** out) {
   int dev = 0;
@@ -608,7 +609,7 @@ int vpfp_shutdown(void) {
   for (auto& kv : g_cache) {
     cudaSetDevice(kv.first);
     for (auto& t : kv.second.tw) cudaFree(t.second);
-    for (int n : {128, 256})
+    for (int n : {128, 64})
       if (g_logtab.count({kv.first, n})) { cudaFree(g_logtab[{kv.first, n}]); g_logtab.erase({kv.first, n}); }
     for (int i = 0; i < 4; ++i)
       if (kv.second.scratch[i]) cudaFree(kv.second.scratch[i]);
@@ -861,7 +862,7 @@ int vpfp_fp_step_linspace(const double* f_in, long ld_in, double* f_out, long ld
   a.mom_out = moments_out; a.mom_ld = mom_ld; a.rows = rows; a.nv = nv;
   int rc = get_logtab(128, &a.logtab);
   if (rc) return rc;
-  rc = get_logtab(256, &a.logtab256);
+  rc = get_logtab(64, &a.logtab64);
   if (rc) return rc;
   {
     static int burst = -1;               // VPFP_FP_BURST=1: A/B of the prefetch issue pattern (fp_reg.cuh)
