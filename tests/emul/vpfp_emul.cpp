@@ -195,10 +195,18 @@ static void run_rowfft(const P& prog) {
   base += (16 - ((uintptr_t)base & 15)) & 15;
   for (int tid = 0; tid < P::T; ++tid) prog.init(tid, regs[tid], base);
   for (int tid = 0; tid < P::T; ++tid) prog.prefetch_row(0, tid, base);
+  // threads of a phase may run in any order: VPFP_EMUL_ORDER=1 reverses it, 2 interleaves halves
+  // (a race between threads inside a phase shows up as a result that depends on the order)
+  const char* oe = getenv("VPFP_EMUL_ORDER");
+  const int order = oe ? atoi(oe) : 0;
   for (long row = 0; row < prog.a.nrows; ++row)
     for (int ph = 0; ph < P::NPH; ++ph)
-      for (int tid = 0; tid < P::T; ++tid)
+      for (int i = 0; i < P::T; ++i) {
+        int tid = i;
+        if (order == 1) tid = P::T - 1 - i;
+        else if (order == 2) tid = (i & 1) ? P::T / 2 + i / 2 : i / 2;
         prog.phase(ph, row, row + 1 < prog.a.nrows ? row + 1 : -1, tid, regs[tid], base);
+      }
 }
 
 extern "C" int emul_edfdv_rowfft(const double* f_in, long ld_in, double* f_out, long ld_out, const double* e,

@@ -302,8 +302,8 @@ __global__ void __launch_bounds__(CB * 2 * Geo<L>::TPC, PFM == 1 ? 2 : 4) pass2_
   cplx* S = reinterpret_cast<cplx*>(smem_raw);        // exchange
   cplx* STG = S + LY::S_ELEMS;                        // staging (prefetched tile), PF only
   cplx* PT = STG + (PF ? LY::T_ELEMS : 0);            // [2 chan][CB][NPT]
-  cplx* BASE = PT + 2 * CB * NPT;                     // [2 groups][2 chan][CB]
-  cplx* TWL = BASE + 4 * CB;                          // [L]     exp(-2 pi i m / L)
+  cplx* BASE0 = PT + 2 * CB * NPT;                    // [2 tiles (parity)][2 groups][2 chan][CB]
+  cplx* TWL = BASE0 + 8 * CB;                         // [L]     exp(-2 pi i m / L)
   cplx* TWT = TWL + L;                                // [2][L]  four-step twiddles W_N^(n2 k1) of the staged tile
   cplx* TWC = TWT + 2 * L;                            // [2][L]  PF: twiddles of the tile being transformed; AL: second buffer
   double* PHI = reinterpret_cast<double*>(TWC + ((PF || AL) ? 2 * L : 0));    // [2 chan][CB]
@@ -430,7 +430,9 @@ __global__ void __launch_bounds__(CB * 2 * Geo<L>::TPC, PFM == 1 ? 2 : 4) pass2_
     const bool self = (t1 == 0);
     const int k1g0 = self ? 0 : t1, k1g1 = self ? (int)(N1 / 2) : (int)(N1 - t1);
 #define K1G(g) ((g) ? k1g1 : k1g0)
-    if (!PF) __syncthreads();                          // previous tile's pointwise is done with BASE
+    // BASE alternates between two buffers: the writers of tile t1 cannot overtake the pointwise readers
+    // of tile t1-2 (barriers of tile t1-1 lie between), so no barrier is needed here
+    cplx* BASE = BASE0 + ((t1 - t1_begin) & 1) * 4 * CB;
     if (!a.exact) {
       for (int w = threadIdx.x; w < 4 * CB; w += NT) {     // base(k1) per group/channel, scaled by 1/(2N)
         const int bb = w % CB, gc = w / CB, g = gc >> 1, ch = gc & 1;
@@ -580,7 +582,7 @@ __global__ void __launch_bounds__(CB * 2 * Geo<L>::TPC, PFM == 1 ? 2 : 4) pass2_
     // ---------------- step B': inverse radix-8, conj twiddle, exchange
     fft8<1>(x);
     fft8<1>(x + 8);
-    __syncthreads();
+    // (in place: the slots written here are the slots this thread read for step B, no barrier)
 #pragma unroll
     for (int r = 0; r < 8; ++r) {
       cplx va = x[r], vb = x[8 + r];
@@ -616,7 +618,7 @@ __global__ void __launch_bounds__(CB * 2 * Geo<L>::TPC, PFM == 1 ? 2 : 4) pass2_
 template <int L, int CB>
 constexpr size_t pass2_smem(int mode, int pfm) {
   return sizeof(cplx) * (size_t)(((mode == ADV_ROWS) ? CB * 2 * (L / 8) * 9 : 2 * L * CB) + (pfm == 1 ? 2 * L * CB : 0) +
-                                 2 * CB * (8 + L / 16 + 1) + 4 * CB + 3 * L + (pfm ? 2 * L : 0)) +
+                                 2 * CB * (8 + L / 16 + 1) + 8 * CB + 3 * L + (pfm ? 2 * L : 0)) +
          sizeof(double) * 2 * CB;
 }
 
