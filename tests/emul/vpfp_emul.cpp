@@ -146,7 +146,15 @@ int emul_xmodes(const double* f, long ld, double* out, int nmodes, int batch, in
   p.xchunks = xch;
   std::vector<double> partial((size_t)batch * xch * nmodes * ncols * 2);
   p.partial = partial.data();
-  run_prog(p, (long)batch * xch * p.cblocks, threads, 0, 1);
+  if (nmodes == 2 && (ncols & 1) == 0 && (ld & 1) == 0 && ((uintptr_t)f & 15) == 0) {   // as vpfp_xmodes_partial
+    Xmodes2Prog p2;
+    p2.f = f; p2.ld = ld; p2.partial = p.partial; p2.batch = batch; p2.nx = nx; p2.ncols = ncols;
+    p2.xchunks = xch; p2.cblocks = (ncols / 2 + threads - 1) / threads;
+    p2.x_offset = 0; p2.nx_total = nx;
+    run_prog(p2, (long)batch * xch * p2.cblocks, threads, 0, 1);
+  } else {
+    run_prog(p, (long)batch * xch * p.cblocks, threads, 0, 1);
+  }
   XmodesReduceProg r;
   r.partial = p.partial; r.out = out; r.nmodes = nmodes; r.batch = batch; r.ncols = ncols; r.xchunks = xch;
   long total = (long)batch * nmodes * ncols * 2;

@@ -22,7 +22,7 @@
 //            S - s (S = R1 R2), i.e. BOTH members of every pair (k, M-k): bin k = s + S k3 pairs
 //            with (S - s) + S (15 - k3).
 // Two shared-memory exchanges on the way in and two on the way out; T = M/32 threads per row.
-// The exchange buffer holds the M points ONCE, in one XOR-swizzled layout that every stage reads
+// The exchange buffer holds the M points ONCE, in one padded layout that every stage reads
 // and writes IN PLACE (a thread writes the slots it has just read), so a stage is one barrier-free
 // phase: five barriers per row.
 // Stage-1 twiddles are powers of one per-thread constant (generated in registers), stage-2
@@ -138,7 +138,7 @@ struct Prog {
   static constexpr int NHI = S / 32;
   static constexpr int NPH = 5;
   // shared memory: exchange buffer, stage-2 twiddles, per-row phase tables
-  static constexpr int X_ELEMS = M;
+  static constexpr int X_ELEMS = R1 * (R2 * 16 + 1);
   static constexpr int NTAB = 16 + 32 + NHI;
   static constexpr long SMEM_BYTES = (long)sizeof(cplx) * (X_ELEMS + L2 + NTAB) + 16;
 
@@ -157,11 +157,13 @@ struct Prog {
   VPFP_HD static cplx* tabs(unsigned char* smem) { return tw2(smem) + L2; }   // G[16], Lo[32], Hi[NHI]
   VPFP_HD static double* cosM(unsigned char* smem) { return reinterpret_cast<double*>(tabs(smem) + NTAB); }
 
-  // slot of point (a, b, c), a < R1, b < R2, c < 16, in the exchange buffer: natural position
-  // a L2 + 16 b + c with c swizzled by a ^ b.  Whichever of a, c (or a alone) runs along the lanes, the
-  // eight lanes of a 128-bit shared-memory transaction land in eight different bank groups.
-  VPFP_HD static int slot(int a_, int b_, int c_) { return a_ * L2 + b_ * 16 + (c_ ^ ((a_ ^ b_) & 15)); }
-  VPFP_HD static int slot_r(int a_, int r_) { return slot(a_, r_ >> 4, r_ & 15); }
+  // slot of point (a, b, c), a < R1, b < R2, c < 16, in the exchange buffer: a (L2 + 1) + 16 b + c.
+  // Stages 1 and 2 run their lanes along c (consecutive slots), stage 3 along a: the odd pitch of a
+  // puts the eight lanes of a 128-bit shared-memory transaction into eight different bank groups.
+  // Addresses stay affine in the thread index (one base register, immediate offsets).
+  static constexpr int PA = L2 + 1;
+  VPFP_HD static int slot(int a_, int b_, int c_) { return a_ * PA + b_ * 16 + c_; }
+  VPFP_HD static int slot_r(int a_, int r_) { return a_ * PA + r_; }
 
   // once per CTA: per-thread constants and the stage-2 twiddle table
   VPFP_HD void init(int tid, Regs& r, unsigned char* smem) const {
@@ -395,13 +397,20 @@ struct Prog {
       } break;
       default: {
         // ---- inverse stage 1, store; the thread's part of X is free once it is in registers
+        const double* nsrc = a.fin + (nextrow >= 0 ? nextrow : row) * a.ld_in;
 #pragma unroll
         for (int q = 0; q < NQ1; ++q) {
           const int rr = tid + T * q;
 #pragma unroll
-          for (int k1 = 0; k1 < R1; ++k1) x[q * R1 + k1] = X[slot_r(k1, rr)];
+          for (int k1 = 0; k1 < R1; ++k1) {
+            // read the slot, then hand it to the cp.async that brings in the next row's point
+            // (same thread, same address: the asynchronous write cannot land before the read)
+            cplx* sl = X + slot_r(k1, rr);
+            x[q * R1 + k1] = *sl;
+            if (nextrow >= 0) cp_async16(sl, nsrc + 2L * (k1 * L2 + rr));
+          }
         }
-        if (nextrow >= 0) prefetch_row(nextrow, tid, smem);
+        cp_async_commit_wait(false);
 #pragma unroll
         for (int q = 0; q < NQ1; ++q) {
           const int rr = tid + T * q;

@@ -431,6 +431,74 @@ struct XmodesProg {
   }
 };
 
+// Two modes (k = 0, 1: what vlapy/core/step.py:130-135 stores), two adjacent columns per thread
+// (16-byte loads) and eight rows in flight.  Inside a group of eight rows the phases are constants,
+//     sum_q f[xg+q] W^(xg+q) = W^xg * sum_q f[xg+q] W^q,      W = exp(-2 pi i / nx_total),
+// so a row costs one add and two FMAs per column, and the running phase W^xg is advanced once per group.
+// Same partial-sum layout as XmodesProg (second stage: XmodesReduceProg).
+struct Xmodes2Prog {
+  const double* f;
+  long ld;
+  double* partial;  // [batch][xchunks][2][ncols][2]
+  int batch, nx, ncols, xchunks, cblocks;
+  int x_offset, nx_total;
+
+  VPFP_HD int nphases() const { return 1; }
+  VPFP_HD void phase(int, long blk, int tid, int nthr, unsigned char*) const {
+    const int cb = (int)(blk % cblocks);
+    const long rr = blk / cblocks;
+    const int xc = (int)(rr % xchunks);
+    const int b = (int)(rr / xchunks);
+    const int j = 2 * (cb * nthr + tid);
+    if (j >= ncols) return;
+    const int x0 = (int)((long)nx * xc / xchunks), x1 = (int)((long)nx * (xc + 1) / xchunks);
+    const double* col = f + ((long)b * nx) * ld + j;
+    const double ang = -2.0 * 3.14159265358979323846 / (double)nx_total;
+    double cr[8], ci[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) sincos_hd(ang * (double)q, &ci[q], &cr[q]);
+    double gr, gi, wr, wi;                     // W^8 and the running W^xg
+    sincos_hd(ang * 8.0, &gi, &gr);
+    sincos_hd(ang * (double)(x0 + x_offset), &wi, &wr);
+    double s0a = 0.0, s0b = 0.0, sra = 0.0, sia = 0.0, srb = 0.0, sib = 0.0;
+    int x = x0;
+    for (; x + 8 <= x1; x += 8) {
+      double va[8], vb[8];
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const cplx v2 = *reinterpret_cast<const cplx*>(col + (long)(x + q) * ld);
+        va[q] = v2.x; vb[q] = v2.y;
+      }
+      double ta = 0.0, tb = 0.0, ra = 0.0, ia = 0.0, rb = 0.0, ib = 0.0;
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        ta += va[q]; tb += vb[q];
+        ra += va[q] * cr[q]; ia += va[q] * ci[q];
+        rb += vb[q] * cr[q]; ib += vb[q] * ci[q];
+      }
+      s0a += ta; s0b += tb;
+      sra += ra * wr - ia * wi; sia += ra * wi + ia * wr;
+      srb += rb * wr - ib * wi; sib += rb * wi + ib * wr;
+      const double nw = wr * gr - wi * gi;
+      wi = wr * gi + wi * gr;
+      wr = nw;
+    }
+    for (; x < x1; ++x) {
+      const cplx v2 = *reinterpret_cast<const cplx*>(col + (long)x * ld);
+      s0a += v2.x; s0b += v2.y;
+      sra += v2.x * wr; sia += v2.x * wi;
+      srb += v2.y * wr; sib += v2.y * wi;
+      const double nw = wr * cr[1] - wi * ci[1];
+      wi = wr * ci[1] + wi * cr[1];
+      wr = nw;
+    }
+    long o = ((((long)b * xchunks + xc) * 2 + 0) * ncols + j) * 2;
+    partial[o] = s0a; partial[o + 1] = 0.0; partial[o + 2] = s0b; partial[o + 3] = 0.0;
+    o = ((((long)b * xchunks + xc) * 2 + 1) * ncols + j) * 2;
+    partial[o] = sra; partial[o + 1] = sia; partial[o + 2] = srb; partial[o + 3] = sib;
+  }
+};
+
 struct XmodesReduceProg {
   const double* partial;
   double* out;  // [batch][nmodes][ncols][2]

@@ -916,7 +916,15 @@ int vpfp_xmodes_partial(const double* f, long ld, double* out, int nmodes, int b
   int rc = get_scratch(SCR_XMODES, bytes, &scratch);
   if (rc) return rc;
   p.partial = (double*)scratch;
-  rc = launch_prog(p, (long)batch * xch * p.cblocks, threads, 0, 1, (cudaStream_t)stream, "xmodes");
+  if (nmodes == 2 && (ncols & 1) == 0 && (ld & 1) == 0 && ((uintptr_t)f & 15) == 0) {
+    Xmodes2Prog p2;                       // two columns per thread, eight rows in flight
+    p2.f = f; p2.ld = ld; p2.partial = p.partial; p2.batch = batch; p2.nx = nx; p2.ncols = ncols;
+    p2.xchunks = xch; p2.cblocks = (ncols / 2 + threads - 1) / threads;
+    p2.x_offset = x_offset; p2.nx_total = nx_total;
+    rc = launch_prog(p2, (long)batch * xch * p2.cblocks, threads, 0, 1, (cudaStream_t)stream, "xmodes");
+  } else {
+    rc = launch_prog(p, (long)batch * xch * p.cblocks, threads, 0, 1, (cudaStream_t)stream, "xmodes");
+  }
   if (rc) return rc;
   XmodesReduceProg r;
   r.partial = p.partial; r.out = out; r.nmodes = nmodes; r.batch = batch; r.ncols = ncols; r.xchunks = xch;
