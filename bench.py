@@ -268,6 +268,16 @@ class ClockSampler(threading.Thread):
                 "power_w_max": max(pw) if pw else None, "reasons": reasons, "samples": len(self.rows)}
 
 
+def ncu_traffic():
+    """DRAM bytes per launch of each kernel from the committed ncu --set full capture
+    (profiles/ncu_traffic_r01.json, written by tools/ncu_traffic.py); {} when absent."""
+    path = os.path.join(ROOT, "profiles", "ncu_traffic_r01.json")
+    if not os.path.exists(path):
+        return {}, None
+    d = json.load(open(path))
+    return d.get("kernels", {}), d.get("source")
+
+
 def peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -481,6 +491,11 @@ def gpu_arm(args):
         kernels = {label: {"launches_per_step": n / K, "ms_per_launch": tot / n,
                            "gbs_algorithmic": 16.0 * cells / (tot / n * 1e-3) / 1e9}
                    for label, (n, tot) in prof.items() if tot / n > 0.02}
+        traffic, traffic_src = ncu_traffic()
+        if world == 1 and (nx, nv) == (16384, 16384):        # the capture is of this configuration
+            for label, k in kernels.items():
+                if label in traffic:
+                    k["dram_bytes_ncu"] = traffic[label]["dram_bytes"]
         dom = max(prof.items(), key=lambda kv: kv[1][1])
         dom_label, (dom_n, dom_tot) = dom
         achieved = 16.0 * cells / (dom_tot / dom_n * 1e-3) / 1e9
@@ -498,7 +513,10 @@ def gpu_arm(args):
                        "cuda_graph": bool(result.get("graph", False))},
             "clocks": result["clocks"], "gpu_launches": result["launches"],
             "roofline": {"bound": "hbm", "kernel": dom_label, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                         "frac": achieved / peak,
+                         "traffic": (traffic.get(dom_label, {}).get("dram_bytes")
+                                     if world == 1 and (nx, nv) == (16384, 16384) else None),
+                         "traffic_source": traffic_src, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": 16.0 * cells,
                          "step": {"bytes_per_cell_update": step_bytes / (nx * nv),
                                   "achieved": step_bytes / (ms / K * 1e-3) / 1e9 / world,

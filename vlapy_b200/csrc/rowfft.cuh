@@ -22,9 +22,6 @@
 //            S - s (S = R1 R2), i.e. BOTH members of every pair (k, M-k): bin k = s + S k3 pairs
 //            with (S - s) + S (15 - k3).
 // Two shared-memory exchanges on the way in and two on the way out; T = M/32 threads per row.
-// The exchange buffer holds the M points ONCE, in one padded layout that every stage reads
-// and writes IN PLACE (a thread writes the slots it has just read), so a stage is one barrier-free
-// phase: five barriers per row.
 // Stage-1 twiddles are powers of one per-thread constant (generated in registers), stage-2
 // twiddles a 256-entry table in shared memory, phase factors P_k = exp(-i phi k) come from three
 // small geometric tables per row (phi = (K[1] dt) e[x]):  P(s + S k3) = Lo[s & 31] Hi[s >> 5] G[k3].
@@ -136,9 +133,9 @@ struct Prog {
   static constexpr int L2 = R2 * 16;
   static constexpr int NQ1 = V / R1, NQ2 = V / R2;
   static constexpr int NHI = S / 32;
-  static constexpr int NPH = 5;
-  // shared memory: exchange buffer, stage-2 twiddles, per-row phase tables
-  static constexpr int X_ELEMS = R1 * (R2 * 16 + 1);
+  static constexpr int NPH = 8;
+  // shared memory: exchange buffer (two layouts), stage-2 twiddles, per-row phase tables
+  static constexpr int X_ELEMS = (S * 17 > M) ? S * 17 : M;
   static constexpr int NTAB = 16 + 32 + NHI;
   static constexpr long SMEM_BYTES = (long)sizeof(cplx) * (X_ELEMS + L2 + NTAB) + 16;
 
@@ -156,14 +153,6 @@ struct Prog {
   VPFP_HD static cplx* tw2(unsigned char* smem) { return xbuf(smem) + X_ELEMS; }
   VPFP_HD static cplx* tabs(unsigned char* smem) { return tw2(smem) + L2; }   // G[16], Lo[32], Hi[NHI]
   VPFP_HD static double* cosM(unsigned char* smem) { return reinterpret_cast<double*>(tabs(smem) + NTAB); }
-
-  // slot of point (a, b, c), a < R1, b < R2, c < 16, in the exchange buffer: a (L2 + 1) + 16 b + c.
-  // Stages 1 and 2 run their lanes along c (consecutive slots), stage 3 along a: the odd pitch of a
-  // puts the eight lanes of a 128-bit shared-memory transaction into eight different bank groups.
-  // Addresses stay affine in the thread index (one base register, immediate offsets).
-  static constexpr int PA = L2 + 1;
-  VPFP_HD static int slot(int a_, int b_, int c_) { return a_ * PA + b_ * 16 + c_; }
-  VPFP_HD static int slot_r(int a_, int r_) { return a_ * PA + r_; }
 
   // once per CTA: per-thread constants and the stage-2 twiddle table
   VPFP_HD void init(int tid, Regs& r, unsigned char* smem) const {
@@ -194,19 +183,16 @@ struct Prog {
   }
 
   // The next row travels global -> shared memory with cp.async while the current row is finished:
-  // thread tid copies the complex points m = m1 L2 + tid + T q to their slots.  These are exactly the
-  // slots the thread itself reads last in the final phase (inverse stage 1) and first in the next
-  // row's first phase (stage 1), so the copy needs no barrier on either side, only the thread's own
-  // cp.async.wait_group.
+  // thread tid copies the complex points m = tid + T k, k = 0..V-1, to X[m].  These are exactly the
+  // points the thread itself reads last from X in the final phase (inverse stage 1) and first in the
+  // next row's first phase (stage 1: m = m1 L2 + tid + T q), so the copy needs no barrier on either
+  // side, only the thread's own cp.async.wait_group.
+  static_assert(L2 % T == 0, "a thread's stage-1 points are the points it prefetches");
   VPFP_HD void prefetch_row(long row, int tid, unsigned char* smem) const {
     cplx* X = xbuf(smem);
     const double* src = a.fin + row * a.ld_in;
 #pragma unroll
-    for (int q = 0; q < NQ1; ++q) {
-      const int rr = tid + T * q;
-#pragma unroll
-      for (int m1 = 0; m1 < R1; ++m1) cp_async16(X + slot_r(m1, rr), src + 2L * (m1 * L2 + rr));
-    }
+    for (int k = 0; k < V; ++k) cp_async16(X + tid + T * k, src + 2L * (tid + T * k));
     cp_async_commit_wait(false);
   }
 
@@ -274,7 +260,7 @@ struct Prog {
     cplx* x = r.x;
     switch (ph) {
       case 0: {
-        // ---- phase tables; stage 1 on the row that prefetch_row brought into X (in place)
+        // ---- phase tables; stage 1 on the row that prefetch_row brought into X
         r.phi_pi = mul_rn(mul_rn(a.kvec[1], a.dt), a.cvec[row]) * 0.31830988618379067154;
         row_tables(tid, r, smem);
         cp_async_commit_wait(true);
@@ -282,35 +268,41 @@ struct Prog {
         for (int q = 0; q < NQ1; ++q) {
           const int rr = tid + T * q;
 #pragma unroll
-          for (int m1 = 0; m1 < R1; ++m1) x[q * R1 + m1] = X[slot_r(m1, rr)];
+          for (int m1 = 0; m1 < R1; ++m1) x[q * R1 + m1] = X[m1 * L2 + rr];
           fftR<R1, -1>(x + q * R1);
           twiddle1<false>(x + q * R1, r.w1[q], r.w4[q]);
 #pragma unroll
-          for (int k1 = 0; k1 < R1; ++k1) X[slot_r(k1, rr)] = x[q * R1 + k1];
+          for (int k1 = 0; k1 < R1; ++k1) X[k1 * L2 + rr] = x[q * R1 + k1];
         }
       } break;
       case 1: {
-        // ---- stage 2: (k1, m3) butterflies over m2, in place
+        // ---- stage 2: (k1, m3) butterflies over m2
 #pragma unroll
         for (int q = 0; q < NQ2; ++q) {
           const int c = tid + T * q, k1 = c >> 4, m3 = c & 15;
 #pragma unroll
-          for (int m2 = 0; m2 < R2; ++m2) x[q * R2 + m2] = X[slot(k1, m2, m3)];
+          for (int m2 = 0; m2 < R2; ++m2) x[q * R2 + m2] = X[k1 * L2 + m2 * 16 + m3];
           fftR<R2, -1>(x + q * R2);
 #pragma unroll
           for (int k2 = 1; k2 < R2; ++k2) x[q * R2 + k2] = cmul(x[q * R2 + k2], TW2[m3 * k2]);
-#pragma unroll
-          for (int k2 = 0; k2 < R2; ++k2) X[slot(k1, k2, m3)] = x[q * R2 + k2];
         }
       } break;
       case 2: {
-        // ---- stage 3 for sub-transforms sA, sB (s = k1 + R1 k2); pointwise on pairs; inverse stage 3
+#pragma unroll
+        for (int q = 0; q < NQ2; ++q) {
+          const int c = tid + T * q, k1 = c >> 4, m3 = c & 15;
+#pragma unroll
+          for (int k2 = 0; k2 < R2; ++k2) X[(k1 + R1 * k2) * 17 + m3] = x[q * R2 + k2];
+        }
+      } break;
+      case 3: {
+        // ---- stage 3 for sub-transforms sA, sB; pointwise on pairs; inverse stage 3
         const bool special = (tid == 0);
         const int sA = special ? 0 : tid, sB = special ? T : S - tid;
 #pragma unroll
         for (int m3 = 0; m3 < 16; ++m3) {
-          x[m3] = X[slot(sA % R1, sA / R1, m3)];
-          x[16 + m3] = X[slot(sB % R1, sB / R1, m3)];
+          x[m3] = X[sA * 17 + m3];
+          x[16 + m3] = X[sB * 17 + m3];
         }
         fft16<-1>(x);
         fft16<-1>(x + 16);
@@ -373,44 +365,47 @@ struct Prog {
         }
         fft16<1>(x);
         fft16<1>(x + 16);
+      } break;
+      case 4: {
+        const bool special = (tid == 0);
+        const int sA = special ? 0 : tid, sB = special ? T : S - tid;
 #pragma unroll
         for (int m3 = 0; m3 < 16; ++m3) {
-          X[slot(sA % R1, sA / R1, m3)] = x[m3];
-          X[slot(sB % R1, sB / R1, m3)] = x[16 + m3];
+          X[sA * 17 + m3] = x[m3];
+          X[sB * 17 + m3] = x[16 + m3];
         }
       } break;
-      case 3: {
-        // ---- inverse stage 2, in place
+      case 5: {
+        // ---- inverse stage 2
 #pragma unroll
         for (int q = 0; q < NQ2; ++q) {
           const int c = tid + T * q, k1 = c >> 4, m3 = c & 15;
 #pragma unroll
           for (int k2 = 0; k2 < R2; ++k2) {
-            cplx val = X[slot(k1, k2, m3)];
+            cplx val = X[(k1 + R1 * k2) * 17 + m3];
             if (k2 > 0) val = cmulc(val, TW2[m3 * k2]);
             x[q * R2 + k2] = val;
           }
           fftR<R2, 1>(x + q * R2);
+        }
+      } break;
+      case 6: {
 #pragma unroll
-          for (int m2 = 0; m2 < R2; ++m2) X[slot(k1, m2, m3)] = x[q * R2 + m2];
+        for (int q = 0; q < NQ2; ++q) {
+          const int c = tid + T * q, k1 = c >> 4, m3 = c & 15;
+#pragma unroll
+          for (int m2 = 0; m2 < R2; ++m2) X[k1 * L2 + m2 * 16 + m3] = x[q * R2 + m2];
         }
       } break;
       default: {
         // ---- inverse stage 1, store; the thread's part of X is free once it is in registers
-        const double* nsrc = a.fin + (nextrow >= 0 ? nextrow : row) * a.ld_in;
 #pragma unroll
         for (int q = 0; q < NQ1; ++q) {
           const int rr = tid + T * q;
 #pragma unroll
-          for (int k1 = 0; k1 < R1; ++k1) {
-            // read the slot, then hand it to the cp.async that brings in the next row's point
-            // (same thread, same address: the asynchronous write cannot land before the read)
-            cplx* sl = X + slot_r(k1, rr);
-            x[q * R1 + k1] = *sl;
-            if (nextrow >= 0) cp_async16(sl, nsrc + 2L * (k1 * L2 + rr));
-          }
+          for (int k1 = 0; k1 < R1; ++k1) x[q * R1 + k1] = X[k1 * L2 + rr];
         }
-        cp_async_commit_wait(false);
+        if (nextrow >= 0) prefetch_row(nextrow, tid, smem);
 #pragma unroll
         for (int q = 0; q < NQ1; ++q) {
           const int rr = tid + T * q;

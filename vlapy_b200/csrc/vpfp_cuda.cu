@@ -180,7 +180,7 @@ static int launch_pass13(const fast::FastArgs& fa, cudaStream_t st) {
   return VPFP_OK;
 }
 
-static int g_pass2_prefetch = 0;   // pass2_kernel PFM (advect_fast.cuh): 0 direct loads, 1 staged, 2 into the exchange buffer
+static int g_pass2_prefetch = 2;   // pass2_kernel PFM (advect_fast.cuh): 0 direct loads, 1 staged, 2 into the exchange buffer
 
 template <int L, int MODE, int PFM>
 static int launch_pass2_pf(const fast::FastArgs& fa, cudaStream_t st) {
@@ -578,8 +578,8 @@ static int run_rowfft(const double* f_in, long ld_in, double* f_out, long ld_out
   ra.fin = f_in; ra.ld_in = ld_in; ra.fout = f_out; ra.ld_out = ld_out; ra.kvec = kv; ra.cvec = e; ra.dt = dt;
   ra.nrows = rows;
   {
-    static int pf = -1;                  // VPFP_ROWFFT_L2PF=n: rows of L2 prefetch ahead (default 1, 0 = off)
-    if (pf < 0) { const char* e = getenv("VPFP_ROWFFT_L2PF"); pf = e ? atoi(e) : 1; }
+    static int pf = -1;                  // VPFP_ROWFFT_L2PF=n: rows of L2 prefetch ahead (default 0 = off: the cp.async of rowfft.cuh already runs a phase ahead)
+    if (pf < 0) { const char* e = getenv("VPFP_ROWFFT_L2PF"); pf = e ? atoi(e) : 0; }
     ra.l2_prefetch = pf;
   }
   int rc = get_twiddles(nv, &ra.twN);
