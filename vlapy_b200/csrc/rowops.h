@@ -599,8 +599,28 @@ struct SeriesProg {
     const int nt = tree_phases(nthr);
     const long o = blk * nx;
     if (ph == 0) {
+      // one CTA per simulation: the loop is latency bound, so two cells per thread (1024 threads) are in flight
       double a[7] = {0, 0, 0, 0, 0, 0, 0};
-      for (int i = tid; i < nx; i += nthr) {
+      int i = tid;
+      for (; i + nthr < nx; i += 2 * nthr) {
+        double v[2][7];
+        for (int q = 0; q < 2; ++q) {
+          const long c = o + i + (long)q * nthr;
+          v[q][0] = mom[0 * mom_ld + c];
+          v[q][1] = mom[1 * mom_ld + c];
+          v[q][2] = mom[2 * mom_ld + c];
+          v[q][3] = e[c];
+          v[q][4] = de ? de[c] : 0.0;
+          v[q][5] = mom[6 * mom_ld + c];
+          v[q][6] = mom[7 * mom_ld + c];
+        }
+        for (int q = 0; q < 2; ++q) {
+          a[0] += v[q][0]; a[1] += v[q][1]; a[2] += v[q][2];
+          a[3] += v[q][3] * v[q][3]; a[4] += v[q][4] * v[q][4];
+          a[5] += v[q][5]; a[6] += v[q][6];
+        }
+      }
+      for (; i < nx; i += nthr) {
         a[0] += mom[0 * mom_ld + o + i];
         a[1] += mom[1 * mom_ld + o + i];
         a[2] += mom[2 * mom_ld + o + i];

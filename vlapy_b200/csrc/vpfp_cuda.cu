@@ -960,7 +960,7 @@ int vpfp_series_batch(const double* moments, long mom_ld, const double* e, const
   if (!moments || !e || !out || nx <= 0 || batch <= 0) return fail(VPFP_ERR_ARG, "vpfp_series: bad argument");
   SeriesProg p;
   p.mom = moments; p.mom_ld = mom_ld; p.e = e; p.de = de; p.out = out; p.nx = nx;
-  int threads = 256;
+  int threads = (nx >= 4096) ? 1024 : 256;
   while (threads > 32 && threads > nx) threads >>= 1;
   return launch_prog(p, batch, threads, p.smem_bytes(threads), p.nphases(threads), (cudaStream_t)stream, "series");
 }
