@@ -230,3 +230,23 @@ def test_fp_reg_stiffness_and_nan_semantics():
     out, mom = E.fp_simt(1, g, v, 0.0, 0.1, dv, "lb")
     assert rel_err(out, g) < 1e-15            # nu = 0: identity matrix
     assert np.isfinite(mom[7, 0]) and np.isnan(mom[7, 1])
+
+
+def test_rowfft4_program(monkeypatch):
+    """rowfft4.cuh (512 threads x 16 points, radix 16 x 8 x 8 x 8, one in-place exchange layout) against
+    the oracle, in three thread orders (a race inside a phase would make the result order dependent)."""
+    nv = 16384
+    rng = np.random.default_rng(4)
+    dv, v, kv = O.velocity_grid(6.4, nv)
+    f = rng.standard_normal((5, nv))
+    f[1] = np.exp(-v ** 2 / 2) * (1 + 1e-3 * rng.standard_normal(nv))
+    e = np.array([0.05, -0.7, 1.3, 0.0, 2.5])
+    monkeypatch.setenv("VPFP_EMUL_ROWFFT4", "1")
+    outs = []
+    for order in ("0", "1", "2"):
+        monkeypatch.setenv("VPFP_EMUL_ORDER", order)
+        for dt in (0.37, -0.066):
+            out = E.edfdv_rowfft(f, e, kv, dt)
+            assert rel_err(out, O.edfdv_exponential(f, e, dt, kv)) < TOL
+            outs.append(out)
+    assert np.array_equal(outs[0], outs[2]) and np.array_equal(outs[0], outs[4])

@@ -19,6 +19,7 @@
 #include "fp_fast.cuh"
 #include "fp_reg.cuh"
 #include "rowfft.cuh"
+#include "rowfft4.cuh"
 #include "rowops.h"
 
 // ------------------------------------------------------------------------------------------
@@ -571,6 +572,34 @@ static int launch_rowfft(const rowfft::Args& ra, cudaStream_t st) {
   return VPFP_OK;
 }
 
+// 512-thread radix 16x8x8x8 variant for nv = 16384 (rowfft4.cuh)
+static int launch_rowfft4(const rowfft::Args& ra, cudaStream_t st) {
+  rowfft4::Prog prog;
+  prog.a = ra;
+  int dev = 0;
+  CUDA_TRY(cudaGetDevice(&dev));
+  static std::map<int, int> grid_for;
+  {
+    static std::mutex mu;
+    std::lock_guard<std::mutex> lk(mu);
+    if (!grid_for.count(dev)) {
+      CUDA_TRY(cudaFuncSetAttribute(rowfft4::rowfft4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    (int)rowfft4::Prog::SMEM_BYTES));
+      int nsm = 0;
+      CUDA_TRY(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev));
+      grid_for[dev] = nsm;
+    }
+  }
+  int grid = grid_for[dev];
+  if (grid > ra.nrows) grid = ra.nrows;
+  {
+    ProfScope ps("edfdv.row", st);
+    rowfft4::rowfft4_kernel<<<grid, rowfft4::Prog::T, rowfft4::Prog::SMEM_BYTES, st>>>(prog);
+  }
+  CUDA_TRY(cudaGetLastError());
+  return VPFP_OK;
+}
+
 static int run_rowfft(const double* f_in, long ld_in, double* f_out, long ld_out, const double* e, const double* kv,
                       double dt, int rows, int nv, const ScatterReq* scat, cudaStream_t st) {
   rowfft::Args ra;
@@ -588,6 +617,11 @@ static int run_rowfft(const double* f_in, long ld_in, double* f_out, long ld_out
     ra.peer_mode = scat->mode; ra.nparts = scat->nparts; ra.my_rank = scat->my_rank;
     ra.lpart = ilog2(nv / scat->nparts);
     for (int i = 0; i < scat->nparts; ++i) ra.peer[i] = scat->peer[i];
+  }
+  if (nv == 16384) {
+    static int v4 = -1;                  // VPFP_ROWFFT4=0 keeps the 256-thread radix 32x16x16 kernel (A/B)
+    if (v4 < 0) { const char* e = getenv("VPFP_ROWFFT4"); v4 = e ? atoi(e) : 1; }
+    if (v4) return launch_rowfft4(ra, st);
   }
   switch (nv) {
     case 16384: return launch_rowfft<rowfft::Prog<32, 16>>(ra, st);
