@@ -61,6 +61,10 @@ struct FastArgs {
   double* peer[8];
 };
 
+__device__ __forceinline__ cplx ldg_plain(const double* p) {
+  const double2 v = *reinterpret_cast<const double2*>(p);
+  return cmake(v.x, v.y);
+}
 __device__ __forceinline__ cplx ldg_c(const cplx* p) {
   const double2 v = __ldg(reinterpret_cast<const double2*>(p));
   return cmake(v.x, v.y);
@@ -144,6 +148,17 @@ __global__ void __launch_bounds__(CB* Geo<L>::TPC) pass13_kernel(const FastArgs 
     valid = seq < a.seq_off + a.seq_cnt;
   }
   const long N2 = a.N2;
+  // twiddles exp(-2 pi i m / L) of this length-L transform: one copy per CTA in shared memory (read
+  // through the cache by every thread they were 15 dependent L2 round trips in the middle of the tile)
+  cplx* TWS = S + L * CB;
+  for (int w = threadIdx.x; w < L; w += CB * TPC) TWS[w] = ldg_c(a.twL1 + w);
+  // COLS: element (l, seq) sits at base + l * rs; one base per thread and compile-time multiples of rs,
+  // so neither loads nor stores wait for address registers of their predecessors
+  const long rs_in = N2 * a.ld_in, rs_out = N2 * a.ld_out;
+  const double* in0 = a.fin + ((long)sim * a.N + n2) * a.ld_in + 2L * seq;
+  double* out0 = a.fout + ((long)sim * a.N + n2) * a.ld_out + 2L * seq;
+  auto ldc = [](const double* p) { const double2 v = *reinterpret_cast<const double2*>(p); return cmake(v.x, v.y); };
+  auto stc = [](double* p, cplx v) { *reinterpret_cast<double2*>(p) = make_double2(v.x, v.y); };
   cplx x[16];
   if (!INV) {
     // ---- step A: radix-R1 over l = r + 8 j
@@ -151,17 +166,23 @@ __global__ void __launch_bounds__(CB* Geo<L>::TPC) pass13_kernel(const FastArgs 
 #pragma unroll
     for (int q = 0; q < NA; ++q) {
       const int r = t + TPC * q;
+      const double* pr = in0 + (long)r * rs_in;
 #pragma unroll
-      for (int j = 0; j < R1; ++j)
-        x[q * R1 + j] = valid ? gload<MODE>(a, src, a.ld_in, sim, seq, (long)(r + 8 * j) * N2 + n2, true)
-                              : cmake(0.0, 0.0);
+      for (int j = 0; j < R1; ++j) {
+        if (MODE == ADV_COLS)
+          x[q * R1 + j] = valid ? ldc(pr + (long)(8 * j) * rs_in) : cmake(0.0, 0.0);
+        else
+          x[q * R1 + j] = valid ? gload<MODE>(a, src, a.ld_in, sim, seq, (long)(r + 8 * j) * N2 + n2, true)
+                                : cmake(0.0, 0.0);
+      }
     }
+    __syncthreads();                                     // TWS
 #pragma unroll
     for (int q = 0; q < NA; ++q) {
       const int r = t + TPC * q;
       fftR<R1, -1>(x + q * R1);
 #pragma unroll
-      for (int m = 1; m < R1; ++m) x[q * R1 + m] = cmul(x[q * R1 + m], ldg_c(a.twL1 + r * m));
+      for (int m = 1; m < R1; ++m) x[q * R1 + m] = cmul(x[q * R1 + m], TWS[r * m]);
 #pragma unroll
       for (int m = 0; m < R1; ++m) S[(m * 8 + r) * CB + b] = x[q * R1 + m];
     }
@@ -174,9 +195,13 @@ __global__ void __launch_bounds__(CB* Geo<L>::TPC) pass13_kernel(const FastArgs 
       for (int r = 0; r < 8; ++r) x[s * 8 + r] = S[(m * 8 + r) * CB + b];
       fft8<-1>(x + s * 8);
 #pragma unroll
+      double* pm = out0 + (long)m * rs_out;
+#pragma unroll
       for (int kp = 0; kp < 8; ++kp) {
         const int k1 = m + R1 * kp;
-        if (valid) gstore<MODE>(a, sim, seq, (long)k1 * N2 + n2, x[s * 8 + kp], false);
+        if (!valid) continue;
+        if (MODE == ADV_COLS) stc(pm + (long)(R1 * kp) * rs_out, x[s * 8 + kp]);
+        else gstore<MODE>(a, sim, seq, (long)k1 * N2 + n2, x[s * 8 + kp], false);
       }
     }
   } else {
@@ -184,15 +209,25 @@ __global__ void __launch_bounds__(CB* Geo<L>::TPC) pass13_kernel(const FastArgs 
 #pragma unroll
     for (int s = 0; s < 2; ++s) {
       const int m = t + TPC * s;
+      const double* pm = out0 + (long)m * rs_out;
 #pragma unroll
-      for (int kp = 0; kp < 8; ++kp)
-        x[s * 8 + kp] = valid ? gload<MODE>(a, a.fout, a.ld_out, sim, seq, (long)(m + R1 * kp) * N2 + n2, false)
-                              : cmake(0.0, 0.0);
+      for (int kp = 0; kp < 8; ++kp) {
+        if (MODE == ADV_COLS)
+          x[s * 8 + kp] = valid ? ldc(pm + (long)(R1 * kp) * rs_out) : cmake(0.0, 0.0);
+        else
+          x[s * 8 + kp] = valid ? gload<MODE>(a, a.fout, a.ld_out, sim, seq, (long)(m + R1 * kp) * N2 + n2, false)
+                                : cmake(0.0, 0.0);
+      }
+    }
+    __syncthreads();                                     // TWS
+#pragma unroll
+    for (int s = 0; s < 2; ++s) {
+      const int m = t + TPC * s;
       fft8<1>(x + s * 8);
 #pragma unroll
       for (int r = 0; r < 8; ++r) {
         cplx val = x[s * 8 + r];
-        if (r * m != 0) val = cmulc(val, ldg_c(a.twL1 + r * m));
+        if (r * m != 0) val = cmulc(val, TWS[r * m]);
         S[(m * 8 + r) * CB + b] = val;
       }
     }
@@ -204,9 +239,16 @@ __global__ void __launch_bounds__(CB* Geo<L>::TPC) pass13_kernel(const FastArgs 
 #pragma unroll
       for (int m = 0; m < R1; ++m) x[q * R1 + m] = S[(m * 8 + r) * CB + b];
       fftR<R1, 1>(x + q * R1);
+      if (MODE == ADV_COLS && !a.peer_mode) {
+        double* pr = out0 + (long)r * rs_out;
 #pragma unroll
-      for (int j = 0; j < R1; ++j)
-        if (valid) gstore<MODE>(a, sim, seq, (long)(r + 8 * j) * N2 + n2, x[q * R1 + j], true);
+        for (int j = 0; j < R1; ++j)
+          if (valid) stc(pr + (long)(8 * j) * rs_out, x[q * R1 + j]);
+      } else {
+#pragma unroll
+        for (int j = 0; j < R1; ++j)
+          if (valid) gstore<MODE>(a, sim, seq, (long)(r + 8 * j) * N2 + n2, x[q * R1 + j], true);
+      }
     }
     if (MODE == ADV_COLS && a.dens_partial != nullptr) {
       // charge density of the new f (vlapy/core/field.py:27-36): weighted sum over this tile's
@@ -370,6 +412,8 @@ __global__ void __launch_bounds__(CB * 2 * Geo<L>::TPC, PFM == 1 ? 2 : 4) pass2_
 
   // PFM 2: this thread's 16 elements of the tile of group pair t1 -> its own slots of S, and its share
   // of the tile's four-step twiddles -> twbuf
+  // COLS: column base of this thread's packed sequence (element of row n at col0 + n * ld_out)
+  double* const col0 = a.fout + (long)sim * N * a.ld_out + 2 * (long)seq;
   auto prefetch_own = [&](int t1, cplx* twbuf) {
     const int k1g0 = (t1 == 0) ? 0 : t1, k1g1 = (t1 == 0) ? (int)(N1 / 2) : (int)(N1 - t1);
     const int gq = u / TPC, taq = u % TPC;
@@ -383,7 +427,8 @@ __global__ void __launch_bounds__(CB * 2 * Geo<L>::TPC, PFM == 1 ? 2 : 4) pass2_
         const long n = k1 * L + r + 8 * j;
         if (!valid) { *dst = cmake(0.0, 0.0); continue; }
         if (MODE == ADV_COLS) {
-          cp_async16(dst, a.fout + ((long)sim * N + n) * a.ld_out + 2 * (long)seq);
+          // one base per (tile, thread), compile-time multiples of the row pitch
+          cp_async16(dst, col0 + (k1 * L + taq) * a.ld_out + (long)(TPC * q + 8 * j) * a.ld_out);
         } else {
           const long ra = 2 * (long)seq, rb = ra + 1;
           cp_async8(&dst->x, a.fout + ra * a.ld_out + n);
@@ -478,8 +523,12 @@ __global__ void __launch_bounds__(CB * 2 * Geo<L>::TPC, PFM == 1 ? 2 : 4) pass2_
       for (int q = 0; q < NA; ++q)
 #pragma unroll
         for (int j = 0; j < R1; ++j)
-          x[q * R1 + j] = valid ? gload<MODE>(a, a.fout, a.ld_out, sim, seq, (long)K1G(g) * L + (ta + TPC * q) + 8 * j, false)
-                                : cmake(0.0, 0.0);
+          if (MODE == ADV_COLS)
+            x[q * R1 + j] = valid ? ldg_plain(col0 + ((long)K1G(g) * L + ta) * a.ld_out + (long)(TPC * q + 8 * j) * a.ld_out)
+                                  : cmake(0.0, 0.0);
+          else
+            x[q * R1 + j] = valid ? gload<MODE>(a, a.fout, a.ld_out, sim, seq, (long)K1G(g) * L + (ta + TPC * q) + 8 * j, false)
+                                  : cmake(0.0, 0.0);
       __syncthreads();                                 // previous tile done with S, TWT, BASE
       for (int w = threadIdx.x; w < 2 * L; w += NT) TWT[w] = ldg_c(a.twN + (long)(w % L) * K1G(w / L));
       TWI = TWT;
@@ -605,10 +654,14 @@ __global__ void __launch_bounds__(CB * 2 * Geo<L>::TPC, PFM == 1 ? 2 : 4) pass2_
       const int r = ta + TPC * q;
       fftR<R1, 1>(x + q * R1);
 #pragma unroll
+      double* const pr = col0 + ((long)K1G(g) * L + r) * a.ld_out;
+#pragma unroll
       for (int j = 0; j < R1; ++j) {
         const int n2 = r + 8 * j;
         const cplx val = cmulc(x[q * R1 + j], TWI[g * L + n2]);
-        if (valid) gstore<MODE>(a, sim, seq, (long)K1G(g) * L + n2, val, false);
+        if (!valid) continue;
+        if (MODE == ADV_COLS) *reinterpret_cast<double2*>(pr + (long)(8 * j) * a.ld_out) = make_double2(val.x, val.y);
+        else gstore<MODE>(a, sim, seq, (long)K1G(g) * L + n2, val, false);
       }
     }
 #undef K1G

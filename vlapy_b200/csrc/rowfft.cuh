@@ -411,8 +411,16 @@ struct Prog {
           const int rr = tid + T * q;
           twiddle1<true>(x + q * R1, r.w1[q], r.w4[q]);
           fftR<R1, 1>(x + q * R1);
+          if (!a.peer_mode) {
+            // one base address, compile-time offsets: a store must not wait for the address registers
+            // of the previous one (they are held until the load/store unit has taken the store)
+            cplx* dst = reinterpret_cast<cplx*>(a.fout + row * a.ld_out) + rr;
 #pragma unroll
-          for (int m1 = 0; m1 < R1; ++m1) store_pair(row, m1 * L2 + rr, x[q * R1 + m1]);
+            for (int m1 = 0; m1 < R1; ++m1) dst[m1 * L2] = x[q * R1 + m1];
+          } else {
+#pragma unroll
+            for (int m1 = 0; m1 < R1; ++m1) store_pair(row, m1 * L2 + rr, x[q * R1 + m1]);
+          }
         }
       } break;
     }

@@ -38,21 +38,20 @@ struct Prog {
   static constexpr int NPH = 7;
   static constexpr int X_ELEMS = 16 * PA;
   static constexpr int NTAB = 8 + 32 + NHI;      // G[8], Lo[32], Hi[NHI]
-  static constexpr long SMEM_BYTES = (long)sizeof(cplx) * (X_ELEMS + 512 + 64 + NTAB) + 16;
+  static constexpr long SMEM_BYTES = (long)sizeof(cplx) * (X_ELEMS + NTAB) + 16;
 
   struct Regs {
     cplx x[V];
     cplx w1, w4;      // W_M^t and its fourth power (stage-1 twiddles are powers of w1)
     cplx wA, wB;      // W_N^sA, W_N^sB
+    cplx v2, v3;      // W_512^(t & 63), W_64^(t & 7): bases of the stage-2 / stage-3 twiddles (both butterflies of a thread share them)
     double phi_pi;    // phase slope of the row: (K[1] dt e[row]) / pi
   };
 
   Args a;
 
   VPFP_HD static cplx* xbuf(unsigned char* smem) { return reinterpret_cast<cplx*>(smem); }
-  VPFP_HD static cplx* tw512(unsigned char* smem) { return xbuf(smem) + X_ELEMS; }   // exp(-2 pi i j / 512)
-  VPFP_HD static cplx* tw64(unsigned char* smem) { return tw512(smem) + 512; }       // exp(-2 pi i j / 64)
-  VPFP_HD static cplx* tabs(unsigned char* smem) { return tw64(smem) + 64; }         // G[8], Lo[32], Hi[NHI]
+  VPFP_HD static cplx* tabs(unsigned char* smem) { return xbuf(smem) + X_ELEMS; }    // G[8], Lo[32], Hi[NHI]
   VPFP_HD static double* cosM(unsigned char* smem) { return reinterpret_cast<double*>(tabs(smem) + NTAB); }
   VPFP_HD static int slot(int k1, int u) { return k1 * PA + u; }
 
@@ -64,10 +63,21 @@ struct Prog {
     const int sA = (tid == 0) ? 0 : tid, sB = (tid == 0) ? S / 2 : S - tid;
     r.wA = a.twN[sA];
     r.wB = a.twN[sB];
-    cplx* T5 = tw512(smem);
-    cplx* T6 = tw64(smem);
-    for (int j = tid; j < 512; j += T) T5[j] = a.twN[(long)j * (N / 512)];
-    for (int j = tid; j < 64; j += T) T6[j] = a.twN[(long)j * (N / 64)];
+    r.v2 = a.twN[(long)(tid & 63) * (N / 512)];
+    r.v3 = a.twN[(long)(tid & 7) * (N / 64)];
+    (void)smem;
+  }
+
+  // w^1 .. w^7 (six complex multiplies; cheaper than seven table reads per butterfly, which made the
+  // kernel shared-memory bound)
+  VPFP_HD static void powers7(const cplx w, cplx* p) {
+    p[1] = w;
+    p[2] = cmul(w, w);
+    p[3] = cmul(p[2], w);
+    p[4] = cmul(p[2], p[2]);
+    p[5] = cmul(p[4], w);
+    p[6] = cmul(p[3], p[3]);
+    p[7] = cmul(p[6], w);
   }
 
   VPFP_HD void prefetch_row(long row, int tid, unsigned char* smem) const {
@@ -110,8 +120,6 @@ struct Prog {
 
   VPFP_HD void phase(int ph, long row, long nextrow, int tid, Regs& r, unsigned char* smem) const {
     cplx* X = xbuf(smem);
-    cplx* T5 = tw512(smem);
-    cplx* T6 = tw64(smem);
     cplx* G = tabs(smem);
     cplx* LO = G + 8;
     cplx* HI = LO + 32;
@@ -131,6 +139,8 @@ struct Prog {
       } break;
       case 1: {
         // ---- stage 2: radix 8 over m2 for (k1, r2), in place
+        cplx tw[8];
+        powers7(r.v2, tw);
 #pragma unroll
         for (int q = 0; q < 2; ++q) {
           const int c = tid + T * q, k1 = c >> 6, r2 = c & 63;
@@ -138,13 +148,15 @@ struct Prog {
           for (int m2 = 0; m2 < 8; ++m2) x[q * 8 + m2] = X[slot(k1, m2 * 64 + r2)];
           fft8<-1>(x + q * 8);
 #pragma unroll
-          for (int k2 = 1; k2 < 8; ++k2) x[q * 8 + k2] = cmul(x[q * 8 + k2], T5[r2 * k2]);
+          for (int k2 = 1; k2 < 8; ++k2) x[q * 8 + k2] = cmul(x[q * 8 + k2], tw[k2]);
 #pragma unroll
           for (int k2 = 0; k2 < 8; ++k2) X[slot(k1, k2 * 64 + r2)] = x[q * 8 + k2];
         }
       } break;
       case 2: {
         // ---- stage 3: radix 8 over m3 for (k1, k2, m4), in place
+        cplx tw[8];
+        powers7(r.v3, tw);
 #pragma unroll
         for (int q = 0; q < 2; ++q) {
           const int c = tid + T * q, k1 = c >> 6, k2 = (c >> 3) & 7, m4 = c & 7;
@@ -152,7 +164,7 @@ struct Prog {
           for (int m3 = 0; m3 < 8; ++m3) x[q * 8 + m3] = X[slot(k1, k2 * 64 + m3 * 8 + m4)];
           fft8<-1>(x + q * 8);
 #pragma unroll
-          for (int k3 = 1; k3 < 8; ++k3) x[q * 8 + k3] = cmul(x[q * 8 + k3], T6[m4 * k3]);
+          for (int k3 = 1; k3 < 8; ++k3) x[q * 8 + k3] = cmul(x[q * 8 + k3], tw[k3]);
 #pragma unroll
           for (int k3 = 0; k3 < 8; ++k3) X[slot(k1, k2 * 64 + k3 * 8 + m4)] = x[q * 8 + k3];
         }
@@ -231,13 +243,15 @@ struct Prog {
       } break;
       case 4: {
         // ---- inverse stage 3, in place
+        cplx tw[8];
+        powers7(r.v3, tw);
 #pragma unroll
         for (int q = 0; q < 2; ++q) {
           const int c = tid + T * q, k1 = c >> 6, k2 = (c >> 3) & 7, m4 = c & 7;
 #pragma unroll
           for (int k3 = 0; k3 < 8; ++k3) {
             cplx val = X[slot(k1, k2 * 64 + k3 * 8 + m4)];
-            if (k3 > 0) val = cmulc(val, T6[m4 * k3]);
+            if (k3 > 0) val = cmulc(val, tw[k3]);
             x[q * 8 + k3] = val;
           }
           fft8<1>(x + q * 8);
@@ -247,13 +261,15 @@ struct Prog {
       } break;
       case 5: {
         // ---- inverse stage 2, in place
+        cplx tw[8];
+        powers7(r.v2, tw);
 #pragma unroll
         for (int q = 0; q < 2; ++q) {
           const int c = tid + T * q, k1 = c >> 6, r2 = c & 63;
 #pragma unroll
           for (int k2 = 0; k2 < 8; ++k2) {
             cplx val = X[slot(k1, k2 * 64 + r2)];
-            if (k2 > 0) val = cmulc(val, T5[r2 * k2]);
+            if (k2 > 0) val = cmulc(val, tw[k2]);
             x[q * 8 + k2] = val;
           }
           fft8<1>(x + q * 8);
@@ -274,7 +290,14 @@ struct Prog {
         rowfft::Prog<16, 16>::twiddle1<true>(x, r.w1, r.w4);
         fft16<1>(x);
 #pragma unroll
-        for (int m1 = 0; m1 < 16; ++m1) store_pair(row, m1 * 512 + tid, x[m1]);
+        if (!a.peer_mode) {
+          cplx* dst = reinterpret_cast<cplx*>(a.fout + row * a.ld_out) + tid;
+#pragma unroll
+          for (int m1 = 0; m1 < 16; ++m1) dst[m1 * 512] = x[m1];
+        } else {
+#pragma unroll
+          for (int m1 = 0; m1 < 16; ++m1) store_pair(row, m1 * 512 + tid, x[m1]);
+        }
       } break;
     }
   }

@@ -168,7 +168,7 @@ template <int L, int MODE, int INV>
 static int launch_pass13(const fast::FastArgs& fa, cudaStream_t st) {
   constexpr int CB = (L == 128) ? 16 : (L == 64 ? 32 : 64);
   constexpr int threads = CB * fast::Geo<L>::TPC;
-  const size_t smem = sizeof(cplx) * L * CB;
+  const size_t smem = sizeof(cplx) * (L * CB + L);     // exchange buffer + twiddle table
   long grid;
   if (MODE == ADV_COLS) grid = (long)fa.nsim * fa.N2 * ((fa.seq_cnt + CB - 1) / CB);
   else grid = ((long)fa.seq_cnt * fa.N2 + CB - 1) / CB;
@@ -619,8 +619,8 @@ static int run_rowfft(const double* f_in, long ld_in, double* f_out, long ld_out
     for (int i = 0; i < scat->nparts; ++i) ra.peer[i] = scat->peer[i];
   }
   if (nv == 16384) {
-    static int v4 = -1;                  // VPFP_ROWFFT4=0 keeps the 256-thread radix 32x16x16 kernel (A/B)
-    if (v4 < 0) { const char* e = getenv("VPFP_ROWFFT4"); v4 = e ? atoi(e) : 1; }
+    static int v4 = -1;                  // VPFP_ROWFFT4=1 selects the 512-thread radix 16x8x8x8 kernel (measured slower: shared-memory bound)
+    if (v4 < 0) { const char* e = getenv("VPFP_ROWFFT4"); v4 = e ? atoi(e) : 0; }
     if (v4) return launch_rowfft4(ra, st);
   }
   switch (nv) {
