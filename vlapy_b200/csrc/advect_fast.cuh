@@ -260,6 +260,27 @@ __global__ void __launch_bounds__(CB* Geo<L>::TPC) pass13_kernel(const FastArgs 
       const int ncols = 2 * a.nseq;
       const double wa = (valid ? ((2 * seq == 0 && (a.edge_flags & 1)) ? 0.5 * a.dv : a.dv) : 0.0);
       const double wb = (valid ? ((2 * seq + 1 == ncols - 1 && (a.edge_flags & 2)) ? 0.5 * a.dv : a.dv) : 0.0);
+      const int tiles_b = (a.seq_cnt + CB - 1) / CB;
+      const int bt = a.seq_off / CB + blockIdx.x % tiles_b;
+      if (CB == 16 && NA == 1) {
+        // the 16 lanes of a half warp hold the tile's columns of the same 16 rows l = t + 8 j: recursive
+        // halving (exchange one half of the values with lane ^ 8, 4, 2, 1 and add) leaves lane b with
+        // the complete sum of row j = b -- 15 exchanges per thread, no shared memory, no barrier
+        double d[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) d[j] = wa * x[j].x + wb * x[j].y;
+#pragma unroll
+        for (int n = 16, m = 8; m >= 1; n >>= 1, m >>= 1) {
+          const bool up = (b & m) != 0;
+#pragma unroll
+          for (int i = 0; i < n / 2; ++i) {
+            const double lo = d[i], hi = d[i + n / 2];
+            const double recv = __shfl_xor_sync(0xffffffffu, up ? lo : hi, m);
+            d[i] = (up ? hi : lo) + recv;
+          }
+        }
+        a.dens_partial[((long)bt * a.nsim + sim) * a.N + (long)(t + 8 * b) * N2 + n2] = d[0];
+      } else {
       __syncthreads();                                   // every thread has read its part of S
 #pragma unroll
       for (int q = 0; q < NA; ++q) {
@@ -273,9 +294,8 @@ __global__ void __launch_bounds__(CB* Geo<L>::TPC) pass13_kernel(const FastArgs 
         double d = 0.0;
 #pragma unroll 8
         for (int bb = 0; bb < CB; ++bb) d += D[l * DP + bb];
-        const int tiles_b = (a.seq_cnt + CB - 1) / CB;
-        const int bt = a.seq_off / CB + blockIdx.x % tiles_b;
         a.dens_partial[((long)bt * a.nsim + sim) * a.N + (long)l * N2 + n2] = d;
+      }
       }
     }
   }
