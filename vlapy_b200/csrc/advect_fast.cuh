@@ -254,7 +254,8 @@ __global__ void __launch_bounds__(CB* Geo<L>::TPC) pass13_kernel(const FastArgs 
       // charge density of the new f (vlapy/core/field.py:27-36): weighted sum over this tile's
       // 2*CB real columns.  Every thread parks its 16 weighted pairs in the (now free) exchange
       // buffer, D[l][b] with an odd pitch; thread l then adds the CB entries of row l in a fixed
-      // order: one partial row per column tile.
+      // order: one partial row per column tile.  (A recursive-halving shuffle reduction without shared
+      // memory was measured slower: 0.97 ms against 0.83 ms for pass 3.)
       double* D = reinterpret_cast<double*>(smem_raw);
       constexpr int DP = CB + 1;
       const int ncols = 2 * a.nseq;
@@ -262,25 +263,6 @@ __global__ void __launch_bounds__(CB* Geo<L>::TPC) pass13_kernel(const FastArgs 
       const double wb = (valid ? ((2 * seq + 1 == ncols - 1 && (a.edge_flags & 2)) ? 0.5 * a.dv : a.dv) : 0.0);
       const int tiles_b = (a.seq_cnt + CB - 1) / CB;
       const int bt = a.seq_off / CB + blockIdx.x % tiles_b;
-      if (CB == 16 && NA == 1) {
-        // the 16 lanes of a half warp hold the tile's columns of the same 16 rows l = t + 8 j: recursive
-        // halving (exchange one half of the values with lane ^ 8, 4, 2, 1 and add) leaves lane b with
-        // the complete sum of row j = b -- 15 exchanges per thread, no shared memory, no barrier
-        double d[16];
-#pragma unroll
-        for (int j = 0; j < 16; ++j) d[j] = wa * x[j].x + wb * x[j].y;
-#pragma unroll
-        for (int n = 16, m = 8; m >= 1; n >>= 1, m >>= 1) {
-          const bool up = (b & m) != 0;
-#pragma unroll
-          for (int i = 0; i < n / 2; ++i) {
-            const double lo = d[i], hi = d[i + n / 2];
-            const double recv = __shfl_xor_sync(0xffffffffu, up ? lo : hi, m);
-            d[i] = (up ? hi : lo) + recv;
-          }
-        }
-        a.dens_partial[((long)bt * a.nsim + sim) * a.N + (long)(t + 8 * b) * N2 + n2] = d[0];
-      } else {
       __syncthreads();                                   // every thread has read its part of S
 #pragma unroll
       for (int q = 0; q < NA; ++q) {
@@ -295,7 +277,6 @@ __global__ void __launch_bounds__(CB* Geo<L>::TPC) pass13_kernel(const FastArgs 
 #pragma unroll 8
         for (int bb = 0; bb < CB; ++bb) d += D[l * DP + bb];
         a.dens_partial[((long)bt * a.nsim + sim) * a.N + (long)l * N2 + n2] = d;
-      }
       }
     }
   }
@@ -350,7 +331,9 @@ struct P2Layout {
 // buffer (2 CTAs/SM), 2 next tile prefetched with cp.async INTO THE EXCHANGE BUFFER: a thread reads
 // last (inverse step A') and first (step A of the next tile) the same 16 slots of S, so it prefetches
 // exactly those, needs no barrier for them and the kernel keeps the shared-memory footprint of PFM 0.
-template <int L, int MODE, int CB, int PFM>
+// EX: per-bin sincos of the reference's own rounding (VPFP_PHASE_EXACT) instead of the geometric tables -- a
+// template parameter, so that the table kernel does not carry the registers and code of the sincos path.
+template <int L, int MODE, int CB, int PFM, bool EX>
 __global__ void __launch_bounds__(CB * 2 * Geo<L>::TPC, PFM == 1 ? 2 : 4) pass2_kernel(const FastArgs a, const int t1_chunk) {
   constexpr bool PF = (PFM == 1);
   constexpr bool AL = (PFM == 2);
@@ -468,7 +451,7 @@ __global__ void __launch_bounds__(CB * 2 * Geo<L>::TPC, PFM == 1 ? 2 : 4) pass2_
   if (PF) prefetch(t1_begin);
   if (AL) prefetch_own(t1_begin, TWT);
 
-  if (!a.exact) {
+  if (!EX) {
     // phi = (K[1] dt) c ; G = exp(-i N1 phi); PT[j] = G^j = H[j>>3] * Lo[j&7]
     for (int w = threadIdx.x; w < 2 * CB; w += NT) {
       const int ch = w / CB, bb = w % CB;
@@ -498,7 +481,7 @@ __global__ void __launch_bounds__(CB * 2 * Geo<L>::TPC, PFM == 1 ? 2 : 4) pass2_
     // BASE alternates between two buffers: the writers of tile t1 cannot overtake the pointwise readers
     // of tile t1-2 (barriers of tile t1-1 lie between), so no barrier is needed here
     cplx* BASE = BASE0 + ((t1 - t1_begin) & 1) * 4 * CB;
-    if (!a.exact) {
+    if (!EX) {
       for (int w = threadIdx.x; w < 4 * CB; w += NT) {     // base(k1) per group/channel, scaled by 1/(2N)
         const int bb = w % CB, gc = w / CB, g = gc >> 1, ch = gc & 1;
         double sn, cs;
@@ -596,7 +579,7 @@ __global__ void __launch_bounds__(CB * 2 * Geo<L>::TPC, PFM == 1 ? 2 : 4) pass2_
       // table phases: P = base(k1) * Hi[j >> 3] * Lo[j & 7]; within a thread j & 7 takes one value for
       // the bins below Nyquist and one above (k2 = m + R1 k', R1 a multiple of 8), base one per group
       cplx baseA_a, baseA_b, loP_a, loP_b, loN_a, loN_b;
-      if (!a.exact) {
+      if (!EX) {
         baseA_a = BASE[(gA * 2 + 0) * CB + b]; baseA_b = BASE[(gA * 2 + 1) * CB + b];
         const int mlo = (special ? 0 : mA) & 7;
         loP_a = PT[b * NPT + mlo]; loP_b = PT[(CB + b) * NPT + mlo];
@@ -606,7 +589,7 @@ __global__ void __launch_bounds__(CB * 2 * Geo<L>::TPC, PFM == 1 ? 2 : 4) pass2_
         const bool neg = (2 * kbin > N);
         const bool nyq = (2 * kbin == N);
         cplx Pa, Pb;  // scaled by 1/(2N)
-        if (a.exact) {
+        if (EX) {
           const long kr = neg ? N - kbin : kbin;
           const double kdt = mul_rn(K[kr], a.dt);
           double sn, cs;

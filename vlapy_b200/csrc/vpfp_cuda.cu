@@ -181,16 +181,16 @@ static int launch_pass13(const fast::FastArgs& fa, cudaStream_t st) {
   return VPFP_OK;
 }
 
-static int g_pass2_prefetch = 2;   // pass2_kernel PFM (advect_fast.cuh): 0 direct loads, 1 staged, 2 into the exchange buffer
+static int g_pass2_prefetch = 2;   // pass2_kernel PFM (advect_fast.cuh): 0 direct loads, 2 prefetch into the exchange buffer
 
-template <int L, int MODE, int PFM>
+template <int L, int MODE, int PFM, bool EX>
 static int launch_pass2_pf(const fast::FastArgs& fa, cudaStream_t st) {
   constexpr int CB = (L == 128) ? 8 : (L == 64 ? 16 : 32);
   constexpr int threads = CB * 2 * fast::Geo<L>::TPC;
   const size_t smem = fast::pass2_smem<L, CB>(MODE, PFM);
   static bool configured = false;
   if (!configured) {
-    int rc = opt_in_smem(fast::pass2_kernel<L, MODE, CB, PFM>, smem);
+    int rc = opt_in_smem(fast::pass2_kernel<L, MODE, CB, PFM, EX>, smem);
     if (rc) return rc;
     configured = true;
   }
@@ -201,7 +201,7 @@ static int launch_pass2_pf(const fast::FastArgs& fa, cudaStream_t st) {
   if (grid > 2147483647L) return fail(VPFP_ERR_UNSUPPORTED, "grid too large");
   {
     ProfScope ps(MODE == ADV_COLS ? "vdfdx.pass2" : "edfdv.pass2", st);
-    fast::pass2_kernel<L, MODE, CB, PFM><<<(unsigned)grid, threads, smem, st>>>(fa, t1_chunk);
+    fast::pass2_kernel<L, MODE, CB, PFM, EX><<<(unsigned)grid, threads, smem, st>>>(fa, t1_chunk);
   }
   CUDA_TRY(cudaGetLastError());
   return VPFP_OK;
@@ -211,12 +211,13 @@ template <int L, int MODE>
 static int launch_pass2(const fast::FastArgs& fa, cudaStream_t st) {
   static int init = 0;
   if (!init) {
-    const char* e = getenv("VPFP_PASS2_PREFETCH");
+    const char* e = getenv("VPFP_PASS2_PREFETCH");      // 0: direct loads, 2 (default): own-slot cp.async prefetch
     if (e) g_pass2_prefetch = atoi(e);
     init = 1;
   }
-  if (g_pass2_prefetch == 2) return launch_pass2_pf<L, MODE, 2>(fa, st);
-  return g_pass2_prefetch ? launch_pass2_pf<L, MODE, 1>(fa, st) : launch_pass2_pf<L, MODE, 0>(fa, st);
+  if (g_pass2_prefetch == 0)
+    return fa.exact ? launch_pass2_pf<L, MODE, 0, true>(fa, st) : launch_pass2_pf<L, MODE, 0, false>(fa, st);
+  return fa.exact ? launch_pass2_pf<L, MODE, 2, true>(fa, st) : launch_pass2_pf<L, MODE, 2, false>(fa, st);
 }
 
 template <int MODE>
