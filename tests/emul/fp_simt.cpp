@@ -15,7 +15,8 @@ static void fill_logtab(std::vector<double2>& h, int n) {
 
 template <int M, int T>
 static void run_reg(const fpfast::Args& a, int grid) {
-  simt::launch((unsigned)grid, T, [&] { fpreg::fp_reg_kernel<M, T>(a); });
+  if (a.op == 0) simt::launch((unsigned)grid, T, [&] { fpreg::fp_reg_kernel<M, T, 0>(a); });
+  else simt::launch((unsigned)grid, T, [&] { fpreg::fp_reg_kernel<M, T, 1>(a); });
 }
 template <int M, int T>
 static void run_fast(const fpfast::Args& a, int grid) {
@@ -32,7 +33,7 @@ extern "C" int emul_fp_simt(int which, const double* f_in, long ld_in, double* f
   fpfast::Args a;
   a.fin = f_in; a.ld_in = ld_in; a.fout = f_out; a.ld_out = ld_out;
   a.v0 = v0; a.vstep = vstep; a.vlast = vlast; a.nu = nu; a.dt = dt; a.dv = dv; a.op = op;
-  a.mom_out = moments_out; a.mom_ld = mom_ld; a.rows = rows; a.nv = nv; a.logtab = lt.data(); a.logtab64 = lt256.data(); a.pf_burst = 0;
+  a.mom_out = moments_out; a.mom_ld = mom_ld; a.rows = rows; a.nv = nv; a.logtab = lt.data(); a.logtab64 = lt256.data();
   if (which == 1) {
     if (nv == 16384) run_reg<32, 512>(a, grid);
     else if (nv == 8192) run_reg<32, 256>(a, grid);

@@ -28,7 +28,6 @@ struct Args {
   int rows, nv;
   const double2* logtab;     // 128 x (1/c_i, ln c_i), c_i = 1 + (i + 1/2)/128
   const double2* logtab64;   // 64 x (1/c_i, ln c_i), c_i = 1 + (i + 1/2)/64 (fp_reg.cuh)
-  int pf_burst;              // fp_reg.cuh: 1 = issue the next row's cp.async in one burst (A/B), 0 = one per cell
 };
 
 __device__ __forceinline__ double warp_sum(double x) {

@@ -185,7 +185,9 @@ struct ChunkLoop<M, M> {
   __device__ __forceinline__ static void rare(double&, const double (&)[M]) {}
 };
 
-template <int M, int T>
+// OP: 0 Lenard-Bernstein, 1 Dougherty (a template parameter: the kernel of one operator does not carry the
+// registers and code of the other)
+template <int M, int T, int OP>
 __global__ void __launch_bounds__(T, (M >= 64 ? 256 : 512) / T) fp_reg_kernel(const Args a) {
   using G = Geo<M, T>;
   static_assert(M >= 16 && G::G1 >= 3 && (M % 2) == 0 && T % 32 == 0 && T <= 512, "chunk geometry");
@@ -231,7 +233,7 @@ __global__ void __launch_bounds__(T, (M >= 64 ? 256 : 512) / T) fp_reg_kernel(co
     const double vs = fma(zero, (double)r, vs0);
     const double v_lo = vs, v_hi = fma((double)(M - 1), a.vstep, vs);
     double acc0 = 0.0;
-    if (a.op == 0) {
+    if (OP == 0) {
 #pragma unroll
       for (int j = 0; j < U; ++j) {
         const double2 f2 = ld2(sp + 2 * j);
@@ -252,7 +254,7 @@ __global__ void __launch_bounds__(T, (M >= 64 ? 256 : 512) / T) fp_reg_kernel(co
       if (last_thread) acc0 = fma(-0.5 * sp[M - 1], v_hi, acc0);
     }
     double Tm = fpfast::block_sum<T>(acc0 * a.dv, red), vbar = 0.0;
-    if (a.op == 1) {
+    if (OP == 1) {
       vbar = Tm;
       double acc1 = 0.0;
 #pragma unroll
@@ -446,11 +448,7 @@ __global__ void __launch_bounds__(T, (M >= 64 ? 256 : 512) / T) fp_reg_kernel(co
       const long rn = r + gridDim.x;
       const bool has_next = rn < a.rows;
       const double* nsrc = a.fin + (has_next ? rn : r) * a.ld_in + 2 * t;
-      const bool spread = has_next && !a.pf_burst;
-      if (has_next && a.pf_burst) {
-#pragma unroll
-        for (int k = 0; k < U; ++k) cp_async16(stage_t + k * (T / U) * PITCH, nsrc + k * 2 * T);
-      }
+      const bool spread = has_next;
       int pf = 0;                                         // compile-time after unrolling: cp.async issued so far
 #define PF_ONE()                                                                                   \
   if (pf < U) {                                                                                    \

@@ -503,25 +503,30 @@ static bool fp_reg_eligible(const fpfast::Args& a) {
   return (((uintptr_t)a.fin | (uintptr_t)a.fout) & 15) == 0;
 }
 
-template <int M, int T>
-static int launch_fp_reg(const fpfast::Args& a, cudaStream_t st) {
+template <int M, int T, int OP>
+static int launch_fp_reg_op(const fpfast::Args& a, cudaStream_t st) {
   const size_t smem = fpreg::Geo<M, T>::SMEM;
   static bool configured = false;
   if (!configured) {
-    CUDA_TRY(cudaFuncSetAttribute(fpreg::fp_reg_kernel<M, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CUDA_TRY(cudaFuncSetAttribute(fpreg::fp_reg_kernel<M, T, OP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = true;
   }
   int per_sm = (int)((227 * 1024) / (smem + 1024));
-  if (per_sm > (M >= 64 ? 256 : 512) / T) per_sm = (M >= 64 ? 256 : 512) / T;
+  if (per_sm > 512 / T) per_sm = 512 / T;
   if (per_sm < 1) per_sm = 1;
   long grid = 148L * per_sm;                      // persistent: every CTA walks rows blockIdx.x, + grid, ...
   if (grid > a.rows) grid = a.rows;
   {
     ProfScope ps("fp_step", st);
-    fpreg::fp_reg_kernel<M, T><<<(unsigned)grid, T, smem, st>>>(a);
+    fpreg::fp_reg_kernel<M, T, OP><<<(unsigned)grid, T, smem, st>>>(a);
   }
   CUDA_TRY(cudaGetLastError());
   return VPFP_OK;
+}
+
+template <int M, int T>
+static int launch_fp_reg(const fpfast::Args& a, cudaStream_t st) {
+  return a.op == 0 ? launch_fp_reg_op<M, T, 0>(a, st) : launch_fp_reg_op<M, T, 1>(a, st);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -899,17 +904,10 @@ int vpfp_fp_step_linspace(const double* f_in, long ld_in, double* f_out, long ld
   if (rc) return rc;
   rc = get_logtab(64, &a.logtab64);
   if (rc) return rc;
-  {
-    static int burst = -1;               // VPFP_FP_BURST=1: A/B of the prefetch issue pattern (fp_reg.cuh)
-    if (burst < 0) { const char* e = getenv("VPFP_FP_BURST"); burst = (e && atoi(e)) ? 1 : 0; }
-    a.pf_burst = burst;
-  }
   cudaStream_t st = (cudaStream_t)stream;
   if (fp_reg_eligible(a)) {
-    static int m64 = -1;                 // VPFP_FP_REG_M=64: 64 cells per thread, 255 registers (A/B measurements)
-    if (m64 < 0) { const char* e = getenv("VPFP_FP_REG_M"); m64 = (e && atoi(e) == 64) ? 1 : 0; }
-    if (nv == 16384) return m64 ? launch_fp_reg<64, 256>(a, st) : launch_fp_reg<32, 512>(a, st);
-    if (nv == 8192) return m64 ? launch_fp_reg<64, 128>(a, st) : launch_fp_reg<32, 256>(a, st);
+    if (nv == 16384) return launch_fp_reg<32, 512>(a, st);
+    if (nv == 8192) return launch_fp_reg<32, 256>(a, st);
     return launch_fp_reg<32, 128>(a, st);
   }
   switch (nv) {
