@@ -123,7 +123,9 @@ VPFP_HD void pair_op(cplx& Z, cplx& Zp, const cplx Wk, const cplx Pk, const cplx
   Zp = cconj(csub(Ye, D));
 }
 
-template <int R1_, int R2_>
+// PEER_: the result is scattered to peer GPUs (Args::peer_mode) -- a template parameter, so that the
+// single-GPU kernel does not carry the registers and code of the scatter path.
+template <int R1_, int R2_, bool PEER_ = false>
 struct Prog {
   static constexpr int R1 = R1_, R2 = R2_, V = 32;
   static constexpr int S = R1 * R2;        // stage-3 sub-transforms
@@ -411,7 +413,7 @@ struct Prog {
           const int rr = tid + T * q;
           twiddle1<true>(x + q * R1, r.w1[q], r.w4[q]);
           fftR<R1, 1>(x + q * R1);
-          if (!a.peer_mode) {
+          if (!PEER_) {
             // one base address, compile-time offsets: a store must not wait for the address registers
             // of the previous one (they are held until the load/store unit has taken the store)
             cplx* dst = reinterpret_cast<cplx*>(a.fout + row * a.ld_out) + rr;

@@ -629,6 +629,13 @@ static int run_rowfft(const double* f_in, long ld_in, double* f_out, long ld_out
     if (v4 < 0) { const char* e = getenv("VPFP_ROWFFT4"); v4 = e ? atoi(e) : 0; }
     if (v4) return launch_rowfft4(ra, st);
   }
+  if (ra.peer_mode) {
+    switch (nv) {
+      case 16384: return launch_rowfft<rowfft::Prog<32, 16, true>>(ra, st);
+      case 8192: return launch_rowfft<rowfft::Prog<16, 16, true>>(ra, st);
+      default: return launch_rowfft<rowfft::Prog<8, 16, true>>(ra, st);
+    }
+  }
   switch (nv) {
     case 16384: return launch_rowfft<rowfft::Prog<32, 16>>(ra, st);
     case 8192: return launch_rowfft<rowfft::Prog<16, 16>>(ra, st);
