@@ -456,7 +456,6 @@ def gpu_arm(args):
             sim = inner(time_array=t_arr, driver_array=d_arr.numpy(), temp_storage=sim)   # warm-up (allocations)
             sim.pop("_dev", None)                      # force the next call to upload f and e again
             sim["f"], sim["e"] = f_host.numpy(), e_host.numpy()
-            torch.cuda.empty_cache()
             torch.cuda.synchronize()
             t0 = time.perf_counter()
             sim = inner(time_array=t_arr, driver_array=d_arr.numpy(), temp_storage=sim)
