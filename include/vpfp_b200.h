@@ -34,6 +34,9 @@ extern "C" {
                               * the generic kernels always use the exact phases */
 #define VPFP_FORCE_GENERIC 2 /* testing: skip the register-resident kernels */
 #define VPFP_FORCE_THREE_PASS 4 /* testing / A-B timing: skip the single-pass row kernel */
+#define VPFP_ROW_TWO_CTA 8   /* e df/dv at nv = 16384: the two-CTAs-per-SM row kernel (rowfft2.cuh) */
+#define VPFP_ROW_ONE_CTA 16  /* e df/dv at nv = 16384: the one-CTA-per-SM row kernel (rowfft.cuh);
+                              * neither flag: the library default (environment VPFP_ROWFFT2=0/1) */
 
 /* collision operator ids (vlapy/core/collisions.py:292-317) */
 #define VPFP_FP_LB 0

@@ -20,6 +20,7 @@
 #include "fp_reg.cuh"
 #include "rowfft.cuh"
 #include "rowfft4.cuh"
+#include "rowfft2.cuh"
 #include "rowops.h"
 
 // ------------------------------------------------------------------------------------------
@@ -533,6 +534,9 @@ static int launch_fp_reg(const fpfast::Args& a, cudaStream_t st) {
 // C ABI
 // ------------------------------------------------------------------------------------------
 // ---- single-pass row kernel (rowfft.cuh): e df/dv with one HBM read and one write of f
+#ifndef VPFP_ROWFFT2_DEFAULT
+#define VPFP_ROWFFT2_DEFAULT 0      // rowfft2.cuh is opt-in until it is measured faster on the GPU
+#endif
 static int g_rowfft_on = -1;   // VPFP_NO_ROWFFT=1 keeps the three-pass kernels (A/B measurements)
 
 static bool rowfft_eligible(const double* f_in, long ld_in, const double* f_out, long ld_out, int rows, int nv,
@@ -606,8 +610,41 @@ static int launch_rowfft4(const rowfft::Args& ra, cudaStream_t st) {
   return VPFP_OK;
 }
 
+// 128-thread two-CTAs-per-SM variant for nv = 16384 (rowfft2.cuh)
+static int launch_rowfft2(const rowfft::Args& ra, cudaStream_t st) {
+  rowfft2::Prog prog;
+  prog.a = ra;
+  int dev = 0;
+  CUDA_TRY(cudaGetDevice(&dev));
+  static std::map<int, int> grid_for;   // per device: SMs x resident CTAs
+  {
+    static std::mutex mu;
+    std::lock_guard<std::mutex> lk(mu);
+    if (!grid_for.count(dev)) {
+      CUDA_TRY(cudaFuncSetAttribute(rowfft2::rowfft2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    (int)rowfft2::Prog::SMEM_BYTES));
+      CUDA_TRY(cudaFuncSetAttribute(rowfft2::rowfft2_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                    cudaSharedmemCarveoutMaxShared));
+      int nsm = 0, occ = 0;
+      CUDA_TRY(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev));
+      CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, rowfft2::rowfft2_kernel, rowfft2::Prog::T,
+                                                             rowfft2::Prog::SMEM_BYTES));
+      if (occ < 1) return fail(VPFP_ERR_CUDA, "rowfft2 kernel does not fit an SM");
+      grid_for[dev] = nsm * occ;
+    }
+  }
+  int grid = grid_for[dev];
+  if (grid > ra.nrows) grid = ra.nrows;
+  {
+    ProfScope ps("edfdv.row", st);
+    rowfft2::rowfft2_kernel<<<grid, rowfft2::Prog::T, rowfft2::Prog::SMEM_BYTES, st>>>(prog);
+  }
+  CUDA_TRY(cudaGetLastError());
+  return VPFP_OK;
+}
+
 static int run_rowfft(const double* f_in, long ld_in, double* f_out, long ld_out, const double* e, const double* kv,
-                      double dt, int rows, int nv, const ScatterReq* scat, cudaStream_t st) {
+                      double dt, int rows, int nv, const ScatterReq* scat, cudaStream_t st, int flags = 0) {
   rowfft::Args ra;
   memset(&ra, 0, sizeof(ra));
   ra.fin = f_in; ra.ld_in = ld_in; ra.fout = f_out; ra.ld_out = ld_out; ra.kvec = kv; ra.cvec = e; ra.dt = dt;
@@ -628,6 +665,10 @@ static int run_rowfft(const double* f_in, long ld_in, double* f_out, long ld_out
     static int v4 = -1;                  // VPFP_ROWFFT4=1 selects the 512-thread radix 16x8x8x8 kernel (measured slower: shared-memory bound)
     if (v4 < 0) { const char* e = getenv("VPFP_ROWFFT4"); v4 = e ? atoi(e) : 0; }
     if (v4) return launch_rowfft4(ra, st);
+    static int v2 = -1;                  // library default of the two-CTAs-per-SM kernel (rowfft2.cuh): VPFP_ROWFFT2=0/1
+    if (v2 < 0) { const char* e = getenv("VPFP_ROWFFT2"); v2 = e ? atoi(e) : VPFP_ROWFFT2_DEFAULT; }
+    const bool two = (flags & VPFP_ROW_TWO_CTA) || (v2 && !(flags & VPFP_ROW_ONE_CTA));
+    if (two && !ra.peer_mode) return launch_rowfft2(ra, st);
   }
   if (ra.peer_mode) {
     switch (nv) {
@@ -701,7 +742,7 @@ int vpfp_edfdv_exp(const double* f_in, long ld_in, double* f_out, long ld_out, c
   if (!is_pow2(nv) || nv < 4 || nv > (1 << 24))
     return fail(VPFP_ERR_UNSUPPORTED, "e df/dv: <exponential> needs nv = 2^k >= 4 on the b200 backend");
   if (rowfft_eligible(f_in, ld_in, f_out, ld_out, rows, nv, flags))
-    return run_rowfft(f_in, ld_in, f_out, ld_out, e, kv, dt, rows, nv, nullptr, (cudaStream_t)stream);
+    return run_rowfft(f_in, ld_in, f_out, ld_out, e, kv, dt, rows, nv, nullptr, (cudaStream_t)stream, flags);
   AdvectProg a;
   memset(&a, 0, sizeof(a));
   a.mode = ADV_ROWS; a.op = OP_PHASE; a.N = nv;

@@ -12,6 +12,7 @@ from . import _lib
 
 FP_OPS = {"lb": 0, "dg": 1}
 PHASE_EXACT, PHASE_TABLE, FORCE_GENERIC, FORCE_THREE_PASS = 0, 1, 2, 4
+ROW_TWO_CTA, ROW_ONE_CTA = 8, 16     # e df/dv at nv = 16384: rowfft2.cuh / rowfft.cuh (neither: library default)
 
 # number of kernels of this library launched since the last reset (bench.py's gpu_launches claim)
 launch_count = 0
