@@ -3,7 +3,7 @@ utilisation -> profiles/ncu_traffic_r01.json (bench.py reads `dram_bytes` for ro
 text summary.  usage: python tools/ncu_traffic.py <raw.csv> <out.json> <out.txt> <tag>"""
 import csv, json, re, sys
 
-LABELS = [(r"rowfft_kernel", "edfdv.row"), (r"pass13_kernel<\d+, 0, 0", "vdfdx.pass1"), (r"pass2_kernel<\d+, 0", "vdfdx.pass2"),
+LABELS = [(r"rowfft_kernel", "edfdv.row"), (r"rowfft2_kernel", "edfdv.row2"), (r"pass13_kernel<\d+, 0, 0", "vdfdx.pass1"), (r"pass2_kernel<\d+, 0", "vdfdx.pass2"),
           (r"pass13_kernel<\d+, 0, 1", "vdfdx.pass3"), (r"fp_reg_kernel", "fp_step"), (r"Xmodes2Prog|XmodesProg", "xmodes"),
           (r"fp_kernel", "fp_step(shared-memory kernel)")]
 WANT = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum",

@@ -47,7 +47,11 @@ using rowfft::cos32;
 using rowfft::pair_op;
 using rowfft::sin32;
 
-struct Prog {
+// HINTS (cache hints, A/B): bit 0: the finished row is stored with evict-first (st.global.cs), so that
+// it does not push the rows that wait for their parity-1 re-read out of L2; bit 1: the parity-1 re-read is
+// a last-use load (ld.global.lu).
+template <int HINTS>
+struct ProgT {
   static constexpr int T = 128, V = 32;
   static constexpr int M = 8192, N = 16384, L2 = 256, S = 512;
   static constexpr int NPH = 32;                     // 16 phases per parity
@@ -75,6 +79,26 @@ struct Prog {
 #else
     return *p;
 #endif
+  }
+  // a point of the row: parity 0 reads it with the default policy (it is needed again), parity 1 for the last time
+  template <int H>
+  VPFP_HD static cplx ld_row(const cplx* p) {
+#if defined(__CUDA_ARCH__)
+    if (H == 1 && (HINTS & 2)) {
+      const double2 v = __ldlu(reinterpret_cast<const double2*>(p));
+      return cmake(v.x, v.y);
+    }
+#endif
+    return *p;
+  }
+  VPFP_HD static void st_row(cplx* p, const cplx v) {
+#if defined(__CUDA_ARCH__)
+    if (HINTS & 1) {
+      __stcs(reinterpret_cast<double2*>(p), make_double2(v.x, v.y));
+      return;
+    }
+#endif
+    *p = v;
   }
 
   // once per CTA: the stage-2 twiddle table W_L2^j
@@ -155,7 +179,7 @@ struct Prog {
           cplx y[16];
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
-            const cplx za = src[j * L2 + rr], zb = src[(j + 16) * L2 + rr];
+            const cplx za = ld_row<H>(src + j * L2 + rr), zb = ld_row<H>(src + (j + 16) * L2 + rr);
             if (H == 0) y[j] = cadd(za, zb);
             else {
               const cplx d = csub(za, zb);
@@ -352,8 +376,8 @@ struct Prog {
             for (int j = 0; j < 16; ++j) {
               const cplx o = (j == 0) ? y[0] : (j == 8) ? fast::rot_i<1>(y[8]) : fast::mul_w16<1>(y[j], cos32(j), sin32(j));
               const cplx ev = PK[(16 * q + j) * T + tid];
-              dst[j * L2] = cadd(ev, o);
-              dst[(j + 16) * L2] = csub(ev, o);
+              st_row(dst + j * L2, cadd(ev, o));
+              st_row(dst + (j + 16) * L2, csub(ev, o));
             }
           }
         }
@@ -367,30 +391,33 @@ struct Prog {
   }
 };
 
+using Prog = ProgT<0>;
+
 #if defined(__CUDACC__)
 // the 32 phases as straight-line code (compile-time phase index: the registers of Regs never become an array in
 // local memory)
-template <int PH>
-__device__ __forceinline__ void run_phases(const Prog& prog, long row, long nxt, int tid, Prog::Regs& r,
+template <int PH, class P>
+__device__ __forceinline__ void run_phases(const P& prog, long row, long nxt, int tid, typename P::Regs& r,
                                            unsigned char* smem) {
-  if constexpr (PH < Prog::NPH) {
-    if constexpr (PH < 16) prog.phase_h<0>(PH, row, nxt, tid, r, smem);
-    else prog.phase_h<1>(PH - 16, row, nxt, tid, r, smem);
+  if constexpr (PH < P::NPH) {
+    if constexpr (PH < 16) prog.template phase_h<0>(PH, row, nxt, tid, r, smem);
+    else prog.template phase_h<1>(PH - 16, row, nxt, tid, r, smem);
     __syncthreads();
-    run_phases<PH + 1>(prog, row, nxt, tid, r, smem);
+    run_phases<PH + 1, P>(prog, row, nxt, tid, r, smem);
   }
 }
 
-__global__ void __launch_bounds__(Prog::T, 2) rowfft2_kernel(const Prog prog) {
+template <class P>
+__global__ void __launch_bounds__(P::T, 2) rowfft2_kernel(const P prog) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  Prog::Regs r;
+  typename P::Regs r;
   const int tid = (int)threadIdx.x;
   prog.init(tid, r, smem_raw);
   __syncthreads();
   for (long row = blockIdx.x; row < prog.a.nrows; row += gridDim.x) {
     long nxt = row + gridDim.x;
     if (nxt >= prog.a.nrows) nxt = -1;
-    run_phases<0>(prog, row, nxt, tid, r, smem_raw);
+    run_phases<0, P>(prog, row, nxt, tid, r, smem_raw);
   }
 }
 #endif

@@ -537,6 +537,9 @@ static int launch_fp_reg(const fpfast::Args& a, cudaStream_t st) {
 #ifndef VPFP_ROWFFT2_DEFAULT
 #define VPFP_ROWFFT2_DEFAULT 0      // rowfft2.cuh is opt-in until it is measured faster on the GPU
 #endif
+#ifndef VPFP_ROWFFT2_HINTS_DEFAULT
+#define VPFP_ROWFFT2_HINTS_DEFAULT 0
+#endif
 static int g_rowfft_on = -1;   // VPFP_NO_ROWFFT=1 keeps the three-pass kernels (A/B measurements)
 
 static bool rowfft_eligible(const double* f_in, long ld_in, const double* f_out, long ld_out, int rows, int nv,
@@ -611,8 +614,9 @@ static int launch_rowfft4(const rowfft::Args& ra, cudaStream_t st) {
 }
 
 // 128-thread two-CTAs-per-SM variant for nv = 16384 (rowfft2.cuh)
-static int launch_rowfft2(const rowfft::Args& ra, cudaStream_t st) {
-  rowfft2::Prog prog;
+template <class P>
+static int launch_rowfft2_t(const rowfft::Args& ra, cudaStream_t st) {
+  P prog;
   prog.a = ra;
   int dev = 0;
   CUDA_TRY(cudaGetDevice(&dev));
@@ -621,14 +625,13 @@ static int launch_rowfft2(const rowfft::Args& ra, cudaStream_t st) {
     static std::mutex mu;
     std::lock_guard<std::mutex> lk(mu);
     if (!grid_for.count(dev)) {
-      CUDA_TRY(cudaFuncSetAttribute(rowfft2::rowfft2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                    (int)rowfft2::Prog::SMEM_BYTES));
-      CUDA_TRY(cudaFuncSetAttribute(rowfft2::rowfft2_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
+      CUDA_TRY(cudaFuncSetAttribute(rowfft2::rowfft2_kernel<P>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    (int)P::SMEM_BYTES));
+      CUDA_TRY(cudaFuncSetAttribute(rowfft2::rowfft2_kernel<P>, cudaFuncAttributePreferredSharedMemoryCarveout,
                                     cudaSharedmemCarveoutMaxShared));
       int nsm = 0, occ = 0;
       CUDA_TRY(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev));
-      CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, rowfft2::rowfft2_kernel, rowfft2::Prog::T,
-                                                             rowfft2::Prog::SMEM_BYTES));
+      CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, rowfft2::rowfft2_kernel<P>, P::T, P::SMEM_BYTES));
       if (occ < 1) return fail(VPFP_ERR_CUDA, "rowfft2 kernel does not fit an SM");
       grid_for[dev] = nsm * occ;
     }
@@ -637,10 +640,21 @@ static int launch_rowfft2(const rowfft::Args& ra, cudaStream_t st) {
   if (grid > ra.nrows) grid = ra.nrows;
   {
     ProfScope ps("edfdv.row", st);
-    rowfft2::rowfft2_kernel<<<grid, rowfft2::Prog::T, rowfft2::Prog::SMEM_BYTES, st>>>(prog);
+    rowfft2::rowfft2_kernel<P><<<grid, P::T, P::SMEM_BYTES, st>>>(prog);
   }
   CUDA_TRY(cudaGetLastError());
   return VPFP_OK;
+}
+
+static int launch_rowfft2(const rowfft::Args& ra, cudaStream_t st) {
+  static int hints = -1;                 // VPFP_ROWFFT2_HINTS=0..3: cache hints of rowfft2.cuh (A/B)
+  if (hints < 0) { const char* e = getenv("VPFP_ROWFFT2_HINTS"); hints = e ? (atoi(e) & 3) : VPFP_ROWFFT2_HINTS_DEFAULT; }
+  switch (hints) {
+    case 1: return launch_rowfft2_t<rowfft2::ProgT<1>>(ra, st);
+    case 2: return launch_rowfft2_t<rowfft2::ProgT<2>>(ra, st);
+    case 3: return launch_rowfft2_t<rowfft2::ProgT<3>>(ra, st);
+    default: return launch_rowfft2_t<rowfft2::ProgT<0>>(ra, st);
+  }
 }
 
 static int run_rowfft(const double* f_in, long ld_in, double* f_out, long ld_out, const double* e, const double* kv,
