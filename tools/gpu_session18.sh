@@ -4,7 +4,7 @@
 mkdir -p gpurun_out
 cd "$(dirname "$0")/.."
 ( timeout 200 python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "two_cta or (single_pass and 16384-257)" 2>&1 | tail -6 ) > gpurun_out/s18_pytest.txt
-( timeout 100 python tools/time_row2.py 2>&1 | tail -8 ) > gpurun_out/s18_time.txt
+( timeout 100 python tools/time_row2.py 2>&1 | tail -9 ) > gpurun_out/s18_time.txt
 ( VPFP_ROWFFT2_HINTS=1 timeout 60 python tools/time_row2.py short 2>&1 | tail -3 ) >> gpurun_out/s18_time.txt
 ( VPFP_ROWFFT2_HINTS=3 timeout 60 python tools/time_row2.py short 2>&1 | tail -3 ) >> gpurun_out/s18_time.txt
 ( VPFP_ROWFFT_L2PF=1 timeout 60 python tools/time_row2.py short 2>&1 | tail -3 ) >> gpurun_out/s18_time.txt

@@ -12,7 +12,7 @@ from tools.time_ops import timeit
 
 dev = torch.device("cuda:0")
 tag = "L2PF=%s HINTS=%s" % (os.environ.get("VPFP_ROWFFT_L2PF", "0"), os.environ.get("VPFP_ROWFFT2_HINTS", "0"))
-sizes = ((16384, 16384),) if len(sys.argv) > 1 and sys.argv[1] == "short" else ((16384, 16384), (32768, 8192))
+sizes = ((16384, 16384),) if len(sys.argv) > 1 and sys.argv[1] == "short" else ((16384, 16384), (32768, 8192), (65536, 4096))
 for rows, nv in sizes:
     dv, v, kv = O.velocity_grid(6.4, nv)
     kv = torch.from_numpy(kv).to(dev)
