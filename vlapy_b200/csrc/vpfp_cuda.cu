@@ -639,7 +639,7 @@ static int launch_rowfft2_t(const rowfft::Args& ra, cudaStream_t st) {
   int grid = grid_for[dev];
   if (grid > ra.nrows) grid = ra.nrows;
   {
-    ProfScope ps("edfdv.row", st);
+    ProfScope ps("edfdv.row2", st);
     rowfft2::rowfft2_kernel<P><<<grid, P::T, P::SMEM_BYTES, st>>>(prog);
   }
   CUDA_TRY(cudaGetLastError());
