@@ -167,6 +167,24 @@ __device__ __forceinline__ void chunk_terms(ChunkSums& S, double x, const double
   S.sl = fma(xs, lx, S.sl);
   S.se = fma(xs, e, S.se);
 }
+// the same with the cell index as an argument (constant after unrolling): for the loop that interleaves the moment
+// sums with the transposed stores
+template <int M>
+__device__ __forceinline__ void chunk_terms_at(ChunkSums& S, double x, const double2* LT, const int i) {
+  const double d = (double)i - 0.5 * (double)(M - 1);
+  const double d2 = d * d;
+  double e;
+  const double lx = log_split(x, LT, &e, &S.bad);
+  S.mu[0] += x;
+  S.mu[1] = fma(x, d, S.mu[1]);
+  S.mu[2] = fma(x, d2, S.mu[2]);
+  S.mu[3] = fma(x, d2 * d, S.mu[3]);
+  S.mu[4] = fma(x, d2 * d2, S.mu[4]);
+  S.mu[5] = fma(x, d2 * d2 * d, S.mu[5]);
+  S.s2 = fma(x, x, S.s2);
+  S.sl = fma(x, lx, S.sl);
+  S.se = fma(x, e, S.se);
+}
 template <int M, int I>
 struct ChunkLoop {
   __device__ __forceinline__ static void run(ChunkSums& S, const double (&c)[M], const double2* LT) {
@@ -519,6 +537,17 @@ __global__ void __launch_bounds__(T, (M >= 64 ? 256 : 512) / T) fp_reg_kernel(co
     // 16-byte store instruction would touch 32 different 128-byte lines.  The warp transposes 16 cells
     // per lane at a time through its own slice of the (now idle) scratch area and writes whole lines.
     __syncthreads();                                      // every warp is done with X and its parked values
+    // The moment sums of the stored cells are interleaved with the stores (FPREG_INTERLEAVE): transposition and
+    // stores are load/store-queue bound (mio / lg throttle: 13 % of the kernel in the ncu source view), the
+    // sums are fp64 bound, and between the two __syncwarp the scheduler is free to mix them.
+    ChunkSums S;
+#pragma unroll
+    for (int q = 0; q < 6; ++q) S.mu[q] = 0.0;
+    S.s2 = 0.0; S.sl = 0.0; S.se = 0.0; S.bad = 0;
+#ifndef FPREG_INTERLEAVE
+#define FPREG_INTERLEAVE 1
+#endif
+    const bool mom_inline = FPREG_INTERLEAVE && (a.mom_out != nullptr);
     {
       double* wbuf = X + warp * (32 * WP);
       double* drow = a.fout + r * a.ld_out + (long)warp * 32 * M;
@@ -532,6 +561,10 @@ __global__ void __launch_bounds__(T, (M >= 64 ? 256 : 512) / T) fp_reg_kernel(co
           const int pc = k * 4 + (lane >> 3), o = (lane & 7) * 2;     // lane-row (chunk of the warp), offset
           const double2 v2 = ld2(wbuf + pc * WP + o);
           store2(drow + pc * M + 16 * hh + o, v2.x, v2.y);
+          if (mom_inline) {
+            chunk_terms_at<M>(S, c[16 * hh + 2 * k], LTl, 16 * hh + 2 * k);
+            chunk_terms_at<M>(S, c[16 * hh + 2 * k + 1], LTl, 16 * hh + 2 * k + 1);
+          }
         }
         __syncwarp();
       }
@@ -539,11 +572,7 @@ __global__ void __launch_bounds__(T, (M >= 64 ? 256 : 512) / T) fp_reg_kernel(co
     if (a.mom_out) {
       // v^p moments from local monomial sums: v_i = vc + (i - I0) vstep, so
       //   sum_i x_i v_i^p = sum_q C(p,q) vc^(p-q) vstep^q mu_q        (6 FMAs per cell instead of 11 flops)
-      ChunkSums S;
-#pragma unroll
-      for (int q = 0; q < 6; ++q) S.mu[q] = 0.0;
-      S.s2 = 0.0; S.sl = 0.0; S.se = 0.0; S.bad = 0;
-      ChunkLoop<M, 0>::run(S, c, LTl);
+      if (!FPREG_INTERLEAVE) ChunkLoop<M, 0>::run(S, c, LTl);
       if (first_thread) chunk_terms<M, 0, 1>(S, c[0], LTl);             // np.trapz: half weight at both ends
       if (last_thread) chunk_terms<M, M - 1, 1>(S, c[M - 1], LTl);
       if (S.bad) {

@@ -146,7 +146,6 @@ struct Prog {
     cplx w1[NQ1];     // W_M^r for the stage-1 butterflies of this thread
     cplx w4[NQ1];     // (W_M^r)^4
     cplx wA, wB;      // W_N^sA, W_N^sB
-    double phi_pi;    // phase slope of the row whose values sit in x: (K[1] dt e[row]) / pi
   };
 
   Args a;
@@ -190,18 +189,31 @@ struct Prog {
   // next row's first phase (stage 1: m = m1 L2 + tid + T q), so the copy needs no barrier on either
   // side, only the thread's own cp.async.wait_group.
   static_assert(L2 % T == 0, "a thread's stage-1 points are the points it prefetches");
-  VPFP_HD void prefetch_row(long row, int tid, unsigned char* smem) const {
+  VPFP_HD void prefetch_copy(long row, int tid, unsigned char* smem) const {
     cplx* X = xbuf(smem);
     const double* src = a.fin + row * a.ld_in;
 #pragma unroll
     for (int k = 0; k < V; ++k) cp_async16(X + tid + T * k, src + 2L * (tid + T * k));
     cp_async_commit_wait(false);
   }
+  // phase slope of a row over pi: (K[1] dt e[row]) / pi, the reference's two roundings of (k dt) e
+  VPFP_HD double phi_over_pi(long row) const {
+    return mul_rn(mul_rn(a.kvec[1], a.dt), a.cvec[row]) * 0.31830988618379067154;
+  }
+  // first row of a CTA: copy and phase tables.  For the following rows the last phase of the previous row
+  // issues the copy and prepares the tables itself (they are read only by the pointwise phase, which every
+  // thread has left by then), with the loads of K[1] and e[row] issued at the top of that phase: they used to
+  // stall the first phase of every row (4 % of the kernel in the ncu source view).
+  VPFP_HD void prefetch_row(long row, int tid, unsigned char* smem) const {
+    prefetch_copy(row, tid, smem);
+    row_tables(tid, phi_over_pi(row), smem);
+  }
 
   // phase tables of the row in registers: G[j] = exp(-i phi S j), Lo[j] = exp(-i phi j),
-  // Hi[j] = exp(-i phi 32 j)/(4M), cos(phi M).  Entry w is computed by lane w / NWARP of warp
-  // w % NWARP (every warp pays for one sincos).  Written in the first phase, read in the fourth.
-  VPFP_HD void row_tables(int tid, const Regs& r, unsigned char* smem) const {
+  // Hi[j] = exp(-i phi 32 j)/(4M), cos(phi M); phi_pi = (K[1] dt e[row]) / pi.  Entry w is computed by lane
+  // w / NWARP of warp w % NWARP (every warp pays for one sincos).  Written one phase before the row starts
+  // (prefetch_row), read in its fourth phase.
+  VPFP_HD void row_tables(int tid, const double phi_pi, unsigned char* smem) const {
     constexpr int NWARP = (T >= 32) ? T / 32 : 1;
     cplx* G = tabs(smem);
     const int w = (tid & 31) * NWARP + (tid >> 5);
@@ -212,7 +224,7 @@ struct Prog {
       else if (w < NTAB) { k = (double)(32 * (w - 48)); sc = 0.25 / (double)M; }
       else k = (double)M;
       double sn, cs;
-      sincospi_hd(r.phi_pi * k, &sn, &cs);
+      sincospi_hd(phi_pi * k, &sn, &cs);
       if (w < NTAB) G[w] = cmake(cs * sc, -sn * sc);
       else *cosM(smem) = cs;
     }
@@ -262,9 +274,7 @@ struct Prog {
     cplx* x = r.x;
     switch (ph) {
       case 0: {
-        // ---- phase tables; stage 1 on the row that prefetch_row brought into X
-        r.phi_pi = mul_rn(mul_rn(a.kvec[1], a.dt), a.cvec[row]) * 0.31830988618379067154;
-        row_tables(tid, r, smem);
+        // ---- stage 1 on the row that prefetch_row brought into X (its phase tables are in place as well)
         cp_async_commit_wait(true);
 #pragma unroll
         for (int q = 0; q < NQ1; ++q) {
@@ -401,13 +411,14 @@ struct Prog {
       } break;
       default: {
         // ---- inverse stage 1, store; the thread's part of X is free once it is in registers
+        const double phi_next = (nextrow >= 0) ? phi_over_pi(nextrow) : 0.0;   // loads issued here, used at the end
 #pragma unroll
         for (int q = 0; q < NQ1; ++q) {
           const int rr = tid + T * q;
 #pragma unroll
           for (int k1 = 0; k1 < R1; ++k1) x[q * R1 + k1] = X[k1 * L2 + rr];
         }
-        if (nextrow >= 0) prefetch_row(nextrow, tid, smem);
+        if (nextrow >= 0) prefetch_copy(nextrow, tid, smem);
 #pragma unroll
         for (int q = 0; q < NQ1; ++q) {
           const int rr = tid + T * q;
@@ -424,6 +435,7 @@ struct Prog {
             for (int m1 = 0; m1 < R1; ++m1) store_pair(row, m1 * L2 + rr, x[q * R1 + m1]);
           }
         }
+        if (nextrow >= 0) row_tables(tid, phi_next, smem);
       } break;
     }
   }

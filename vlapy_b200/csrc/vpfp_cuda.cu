@@ -196,7 +196,9 @@ static int launch_pass2_pf(const fast::FastArgs& fa, cudaStream_t st) {
     configured = true;
   }
   const int T1 = fa.N1 / 2;
-  const int t1_chunk = 8;
+  static int chunk_env = -1;               // VPFP_PASS2_CHUNK: group-pair tiles per CTA (A/B; default 8)
+  if (chunk_env < 0) { const char* e = getenv("VPFP_PASS2_CHUNK"); chunk_env = (e && atoi(e) > 0) ? atoi(e) : 8; }
+  const int t1_chunk = chunk_env;
   const int nchunks = (T1 + t1_chunk - 1) / t1_chunk;
   const long grid = (long)(MODE == ADV_COLS ? fa.nsim : 1) * ((fa.seq_cnt + CB - 1) / CB) * nchunks;
   if (grid > 2147483647L) return fail(VPFP_ERR_UNSUPPORTED, "grid too large");
