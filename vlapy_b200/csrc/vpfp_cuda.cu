@@ -383,7 +383,7 @@ static int run_advect(AdvectProg a, cudaStream_t st, int flags = VPFP_PHASE_EXAC
       const long n = (long)a.nsim * a.N;
       {
         ProfScope ps("vdfdx.density_reduce", st);
-        fast::dens_reduce_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(fa.dens_partial, dens_tiles, n, dens->out);
+        fast::dens_reduce_kernel<<<(unsigned)((n + 63) / 64), 64, 0, st>>>(fa.dens_partial, dens_tiles, n, dens->out);
       }
       CUDA_TRY(cudaGetLastError());
       if (dens_done) *dens_done = true;
