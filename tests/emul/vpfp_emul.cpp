@@ -9,6 +9,7 @@
 #include <cstring>
 #include <cmath>
 #include <vector>
+#include <utility>
 
 #include "../../vlapy_b200/csrc/advect.h"
 #include "../../vlapy_b200/csrc/rowops.h"
@@ -209,14 +210,24 @@ static void run_rowfft(const P& prog) {
   // (a race between threads inside a phase shows up as a result that depends on the order)
   const char* oe = getenv("VPFP_EMUL_ORDER");
   const int order = oe ? atoi(oe) : 0;
+  // the (row, phase) steps between two barriers form one interval: every thread runs the whole interval before the
+  // next thread starts (P::sync_after(ph) == false: no barrier after that phase, e.g. the last phase of a row and
+  // the first phase of the next one in rowfft.cuh)
+  std::vector<std::pair<long, int>> interval;
   for (long row = 0; row < prog.a.nrows; ++row)
-    for (int ph = 0; ph < P::NPH; ++ph)
+    for (int ph = 0; ph < P::NPH; ++ph) {
+      interval.push_back({row, ph});
+      const bool last = (row + 1 == prog.a.nrows) && (ph + 1 == P::NPH);
+      if (!P::sync_after(ph) && !last) continue;
       for (int i = 0; i < P::T; ++i) {
         int tid = i;
         if (order == 1) tid = P::T - 1 - i;
         else if (order == 2) tid = (i & 1) ? P::T / 2 + i / 2 : i / 2;
-        prog.phase(ph, row, row + 1 < prog.a.nrows ? row + 1 : -1, tid, regs[tid], base);
+        for (auto& st : interval)
+          prog.phase(st.second, st.first, st.first + 1 < prog.a.nrows ? st.first + 1 : -1, tid, regs[tid], base);
       }
+      interval.clear();
+    }
 }
 
 extern "C" int emul_edfdv_rowfft(const double* f_in, long ld_in, double* f_out, long ld_out, const double* e,

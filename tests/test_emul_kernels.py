@@ -169,17 +169,25 @@ def test_register_butterflies(radix):
 
 
 @pytest.mark.parametrize("nv", [4096, 8192, 16384])
-def test_rowfft_program(nv):
+def test_rowfft_program(nv, monkeypatch):
     """single-pass row kernel (rowfft.cuh: real row as one complex sequence of nv/2 points, pairs
     (k, M-k) un-mixed in registers) against the oracle: white noise (every bin, Nyquist included)
-    and a smooth Maxwellian-like row, positive and negative sub-steps, odd row count."""
+    and a smooth Maxwellian-like row, positive and negative sub-steps, odd row count.  Three thread
+    orders: the kernel has no barrier after its pointwise phase and after the last phase of a row (the
+    emulation runs such phases back to back per thread), a race there would make the result order dependent."""
     rng = np.random.default_rng(nv)
     dv, v, kv = O.velocity_grid(6.4, nv)
     f = rng.standard_normal((3, nv))
     f[1] = np.exp(-v ** 2 / 2) * (1 + 1e-3 * rng.standard_normal(nv))
     e = np.array([0.05, -0.7, 1.3])
-    for dt in (0.37, -0.066):
-        assert rel_err(E.edfdv_rowfft(f, e, kv, dt), O.edfdv_exponential(f, e, dt, kv)) < TOL
+    outs = []
+    for order in ("0", "1", "2"):
+        monkeypatch.setenv("VPFP_EMUL_ORDER", order)
+        for dt in (0.37, -0.066):
+            out = E.edfdv_rowfft(f, e, kv, dt)
+            assert rel_err(out, O.edfdv_exponential(f, e, dt, kv)) < TOL
+            outs.append(out)
+    assert np.array_equal(outs[0], outs[2]) and np.array_equal(outs[0], outs[4])
 
 
 # ---- Fokker-Planck __global__ kernels run thread by thread on the host (tests/emul/simt.h)

@@ -609,7 +609,7 @@ __global__ void __launch_bounds__(T, (M >= 64 ? 256 : 512) / T) fp_reg_kernel(co
         if (lane == 0) a.mom_out[(long)k * a.mom_ld + r] = y;
       }
     }
-    __syncthreads();
+    // (no barrier here: the next row starts with cp.async.wait + __syncthreads before anything is written)
   }
 }
 

@@ -55,6 +55,7 @@ struct ProgT {
   static constexpr int T = 128, V = 32;
   static constexpr int M = 8192, N = 16384, L2 = 256, S = 512;
   static constexpr int NPH = 32;                     // 16 phases per parity
+  VPFP_HD static constexpr bool sync_after(int) { return true; }
   static constexpr int X_ELEMS = 128 * 17;           // half a parity, rows of 16 padded to 17 (>= 8 * L2)
   static constexpr int NHI = 16, NTAB = 16 + 32 + NHI;
   static constexpr int PARK = 4096;

@@ -36,6 +36,7 @@ struct Prog {
   static constexpr int PA = 513;                 // pitch of k1 in the exchange buffer
   static constexpr int NHI = S / 32;
   static constexpr int NPH = 7;
+  VPFP_HD static constexpr bool sync_after(int) { return true; }
   static constexpr int X_ELEMS = 16 * PA;
   static constexpr int NTAB = 8 + 32 + NHI;      // G[8], Lo[32], Hi[NHI]
   static constexpr long SMEM_BYTES = (long)sizeof(cplx) * (X_ELEMS + NTAB) + 16;
