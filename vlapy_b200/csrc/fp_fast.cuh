@@ -37,12 +37,13 @@ __device__ __forceinline__ double warp_sum(double x) {
 }
 
 // sum over the CTA; every thread gets the result. red: >= 32 doubles of shared scratch.
-template <int T>
+// PROTECT = false: the caller knows that a barrier already lies between the previous use of red and this call.
+template <int T, bool PROTECT = true>
 __device__ __forceinline__ double block_sum(double x, double* red) {
   constexpr int NW = T / 32;
   x = warp_sum(x);
   const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
-  __syncthreads();  // protect red from the previous use
+  if (PROTECT) __syncthreads();  // protect red from the previous use
   if (l == 0) red[w] = x;
   __syncthreads();
   double y = (l < NW) ? red[l] : 0.0;
