@@ -383,7 +383,14 @@ static int run_advect(AdvectProg a, cudaStream_t st, int flags = VPFP_PHASE_EXAC
       const long n = (long)a.nsim * a.N;
       {
         ProfScope ps("vdfdx.density_reduce", st);
-        fast::dens_reduce_kernel<<<(unsigned)((n + 63) / 64), 64, 0, st>>>(fa.dens_partial, dens_tiles, n, dens->out);
+        const int groups = (dens_tiles >= 64 && dens_tiles % 8 == 0) ? 8 : 1;
+        const unsigned gx = (unsigned)((n + 255) / 256);
+        if (groups > 1) {
+          fast::dens_reduce_kernel<<<dim3(gx, groups), 256, 0, st>>>(fa.dens_partial, dens_tiles / groups, 1, n, nullptr);
+          fast::dens_reduce_kernel<<<gx, 256, 0, st>>>(fa.dens_partial, groups, dens_tiles / groups, n, dens->out);
+        } else {
+          fast::dens_reduce_kernel<<<gx, 256, 0, st>>>(fa.dens_partial, dens_tiles, 1, n, dens->out);
+        }
       }
       CUDA_TRY(cudaGetLastError());
       if (dens_done) *dens_done = true;

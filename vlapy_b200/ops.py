@@ -96,7 +96,10 @@ def vdfdx_exp(f, kx, v, dt, out=None, flags=PHASE_EXACT, density_out=None, dv=No
         _lib.check(_lib.lib().vpfp_vdfdx_exp_density(f.data_ptr(), ld, out.data_ptr(), ldo, kx.data_ptr(),
                                                      v.data_ptr(), float(dt), batch, nx, ncols, flags,
                                                      density_out.data_ptr(), float(dv), edge_flags, _stream()))
-        _count(adv_launches("cols", nx, batch * nx * ncols) + 1)
+        # + the reduction of the per-tile density partials (two stages when there are >= 64 column tiles;
+        # the tile width mirrors launch_pass13 only approximately -- this is a count, not a control path)
+        tiles = -(-(ncols // 2) // (16 if nx >= 8192 else 32 if nx >= 2048 else 64))
+        _count(adv_launches("cols", nx, batch * nx * ncols) + (2 if tiles >= 64 and tiles % 8 == 0 else 1))
         return out
     _lib.check(_lib.lib().vpfp_vdfdx_exp(f.data_ptr(), ld, out.data_ptr(), ldo, kx.data_ptr(), v.data_ptr(),
                                          float(dt), batch, nx, ncols, flags, _stream()))
