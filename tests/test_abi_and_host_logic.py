@@ -84,3 +84,58 @@ def test_non_fftfreq_wavenumbers_are_rejected():
         vlasov._check_wavenumbers(np.arange(8.0), "v df/dx")
     vlasov._check_wavenumbers(np.fft.fftfreq(8) * 3.0, "v df/dx")
     vlasov._check_wavenumbers(np.fft.fftfreq(2), "v df/dx")
+
+
+def test_flag_constants_match_the_header():
+    """the Python mirrors of the C-ABI flag macros (vlapy_b200/ops.py) carry the header's values"""
+    from vlapy_b200 import ops
+    hdr = open(os.path.join(ROOT, "include", "vpfp_b200.h")).read()
+    macros = {m: int(v) for m, v in re.findall(r"#define\s+(VPFP_[A-Z0-9_]+)\s+(\d+)\b", hdr)}
+    for name in ("PHASE_EXACT", "PHASE_TABLE", "FORCE_GENERIC", "FORCE_THREE_PASS", "ROW_TWO_CTA", "ROW_ONE_CTA"):
+        assert macros["VPFP_" + name] == getattr(ops, name), name
+    flags = [macros["VPFP_" + n] for n in ("PHASE_TABLE", "FORCE_GENERIC", "FORCE_THREE_PASS", "ROW_TWO_CTA", "ROW_ONE_CTA")]
+    assert len(set(flags)) == len(flags) and all(f & (f - 1) == 0 for f in flags)      # distinct single bits
+
+
+def test_run_loops_overlaps_storage_with_the_next_batch_and_respects_the_two_buffer_sets():
+    """outer_loop.run_loops with a stand-in inner loop that, like the real one with
+    backend.pinned_sets = 2, returns views into two alternating buffers: every batch is consumed once, in order,
+    with the values of its own batch (a buffer is never rewritten while its consumer is still reading), and the
+    consumer of batch i runs while batch i+1 computes."""
+    import threading
+    import time
+    bufs = [np.zeros(4), np.zeros(4)]
+    state = {"n": 0}
+    log = []
+    busy = threading.Event()
+    overlapped = []
+
+    def inner_loop(time_array, driver_array, temp_storage):
+        overlapped.append(busy.is_set())                 # is a consumer running while this batch "computes"?
+        b = bufs[state["n"] % 2]
+        b[:] = time_array[0]
+        time.sleep(0.02)
+        state["n"] += 1
+        out = dict(temp_storage)
+        out.update(f=b, fields={"n": b}, time_batch=np.asarray(time_array), _dev="private")
+        return out
+
+    def consume(snap):
+        busy.set()
+        first = float(snap["f"][0])
+        time.sleep(0.03)                                 # slower than a batch: the loop has to wait for the buffer
+        assert "_dev" not in snap
+        log.append((float(snap["time_batch"][0]), first, float(snap["f"][0]), float(snap["fields"]["n"][3])))
+        busy.clear()
+
+    batches = [(np.full(3, float(i)), None) for i in range(6)]
+    final = outer_loop.run_loops(inner_loop, {"f": None}, batches, consume)
+    assert [l[0] for l in log] == [float(i) for i in range(6)]
+    assert all(l[0] == l[1] == l[2] == l[3] for l in log)     # never overwritten under the consumer
+    assert any(overlapped[1:])
+    assert final["_dev"] == "private" and state["n"] == 6
+
+    def failing(snap):
+        raise RuntimeError("disk full")
+    with pytest.raises(RuntimeError, match="disk full"):
+        outer_loop.run_loops(inner_loop, {"f": None}, batches[:3], failing)

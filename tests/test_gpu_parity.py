@@ -515,3 +515,50 @@ def test_two_cta_row_kernel(dev, rows):
         assert rel_err(two, one) < 1e-13
         assert not np.array_equal(two, one)        # the two kernels round differently: both really ran
 
+
+
+@pytest.mark.parametrize("graph", [True, False])
+def test_run_loops_with_two_pinned_sets_equals_sequential_calls(dev, graph):
+    """outer_loop.run_loops (storage hand-off overlapped with the next inner loop, backend.pinned_sets = 2): what
+    the consumer sees for every batch, and the final state, equal a plain sequence of inner-loop calls"""
+    from vlapy_b200 import outer_loop
+    cfg = O.nlepw_config(nx=32, nv=256, k0=0.35, log_nu=-2)
+    nloop, nt = 4, 6
+    batches = []
+    for li in range(nloop):
+        t = cfg["dt"] * np.arange(li * nt, (li + 1) * nt)
+        batches.append((t, np.stack([cfg["driver_function"](ti) for ti in t])))
+
+    def grab(sim):
+        return {"f": np.array(sim["f"]), "e": np.array(sim["e"]), "n": np.array(sim["fields"]["n"]),
+                "T": np.array(sim["series"]["mean_T"]), "cum": np.array(sim["series"]["mean_cum_de2"]),
+                "stored_f": np.array(sim["stored_f"]), "t": np.array(sim["time_batch"])}
+
+    params = make_params(cfg, "leapfrog", "lb")
+    params["backend"]["cuda_graph"] = graph
+    sim, inner = outer_loop.get_sim_config_and_inner_loop_step(params, make_stuff(cfg, RULES), nt, RULES)
+    seq = []
+    for t, drv in batches:
+        sim = inner(time_array=t, driver_array=drv, temp_storage=sim)
+        seq.append(grab(sim))
+
+    params = make_params(cfg, "leapfrog", "lb")
+    params["backend"]["cuda_graph"] = graph
+    params["backend"]["pinned_sets"] = 2
+    sim2, inner2 = outer_loop.get_sim_config_and_inner_loop_step(params, make_stuff(cfg, RULES), nt, RULES)
+    seen = []
+
+    def consume(snap):
+        import time
+        first = grab(snap)
+        time.sleep(0.05)                       # the next batch runs (and fills the OTHER pinned set) meanwhile
+        again = grab(snap)
+        assert all(np.array_equal(first[k], again[k]) for k in first)
+        seen.append(first)
+
+    final = outer_loop.run_loops(inner2, sim2, batches, consume)
+    assert len(seen) == nloop
+    for a, b in zip(seq, seen):
+        for k in a:
+            assert np.array_equal(a[k], b[k]), k
+    assert np.array_equal(np.array(final["f"]), seq[-1]["f"])

@@ -60,11 +60,13 @@ def post_inner_loop_update(temp_storage, this_np=np):
     return temp_storage
 
 
-def _device_storage(temp_storage, nt, nx, nv, dev):
+def _device_storage(temp_storage, nt, nx, nv, dev, pinned_sets=1):
     """Device twins of the per-loop buffers of vlapy/outer_loop.py:190-215 (key ``_dev``) and pinned
     host mirrors for the once-per-loop download (key ``_pin``).  The device copies of e and f are
     authoritative between calls; delete ``temp_storage["_dev"]`` to make the next call upload
-    ``temp_storage["e"]`` / ``["f"]`` again."""
+    ``temp_storage["e"]`` / ``["f"]`` again.  ``pinned_sets = 2``: two sets of pinned mirrors used
+    alternately, so that the arrays one call returns stay valid while the next call runs
+    (``run_loops``)."""
     d = temp_storage.get("_dev")
     if d is None or d["nt"] != nt:
         stored = temp_storage["stored_f"]
@@ -80,19 +82,20 @@ def _device_storage(temp_storage, nt, nx, nv, dev):
         }
         temp_storage["_dev"] = d
     p = temp_storage.get("_pin")
-    if p is None or p["nt"] != nt:
+    if p is None or p["nt"] != nt or len(p["sets"]) != pinned_sets:
         sf = d["stored_f"]
-        p = {
-            "nt": nt,
+        p = {"nt": nt, "next": 0, "sets": [{
             "fields": torch.empty(d["fields"].shape, dtype=torch.float64, pin_memory=True),
             "series_rows": torch.empty((nt, 7), dtype=torch.float64, pin_memory=True),
             "stored_f": torch.empty(sf.shape, dtype=torch.complex64 if sf.is_complex() else torch.float64,
                                     pin_memory=True),
             "e": torch.empty(nx, dtype=torch.float64, pin_memory=True),
             "f": torch.empty((nx, nv), dtype=torch.float64, pin_memory=True),
-        }
+        } for _ in range(pinned_sets)]}
         temp_storage["_pin"] = p
-    return d, p
+    pin = p["sets"][p["next"]]
+    p["next"] = (p["next"] + 1) % len(p["sets"])
+    return d, pin
 
 
 class _GraphStep:
@@ -166,6 +169,9 @@ def get_inner_loop_stepper(all_params, stuff_for_time_loop, steps_in_loop):
             "The backend: <" + all_params["backend"]["core"] + "> has not yet been implemented")
     one_step = step.get_timestep(all_params=all_params, stuff_for_time_loop=stuff_for_time_loop)
     graph_opt = all_params["backend"].get("cuda_graph", "auto")
+    pinned_sets = int(all_params["backend"].get("pinned_sets", 1))      # 2: see run_loops
+    if pinned_sets not in (1, 2):
+        raise ValueError("backend.pinned_sets must be 1 or 2")
     graph_state = {}
 
     def want_graph(nx, nv):
@@ -203,7 +209,7 @@ def get_inner_loop_stepper(all_params, stuff_for_time_loop, steps_in_loop):
     def inner_loop(time_array, driver_array, temp_storage):
         dev = device()
         nx, nv = np.asarray(temp_storage["f"]).shape[-2:]
-        d, pin = _device_storage(temp_storage, steps_in_loop, nx, nv, dev)
+        d, pin = _device_storage(temp_storage, steps_in_loop, nx, nv, dev, pinned_sets)
         # host -> device: the driver rows of this loop (asynchronous when the caller pinned them)
         drv = torch.as_tensor(np.ascontiguousarray(driver_array, dtype=np.float64)).to(dev, non_blocking=True)
         if want_graph(nx, nv):
@@ -246,3 +252,30 @@ def get_inner_loop_stepper(all_params, stuff_for_time_loop, steps_in_loop):
         return temp_storage
 
     return inner_loop
+
+
+
+def run_loops(inner_loop, temp_storage, batches, consume):
+    """The loop of vlapy/manager.py:118-150 with the storage hand-off overlapped.
+
+    ``batches`` yields ``(time_array, driver_array)``; for every batch ``consume(snapshot)`` -- the reference's
+    ``storage_manager.batch_update`` -- is called once, in order, on a worker thread WHILE the next batch computes.
+    ``snapshot`` is a shallow copy of the dictionary the inner loop returned (time_batch, series, fields, stored_f,
+    e, f as host arrays).  The inner loop must have been built with ``all_params["backend"]["pinned_sets"] = 2``:
+    the arrays of batch i live in pinned set i % 2, which batch i+2 overwrites, so batch i+1 is not started before
+    ``consume`` of batch i-1 has returned.  Exceptions of ``consume`` are re-raised here.  Returns the final
+    dictionary (device-resident e, f under its private keys, as after a plain sequence of calls)."""
+    import collections
+    from concurrent.futures import ThreadPoolExecutor
+    pending = collections.deque()
+    with ThreadPoolExecutor(max_workers=1) as pool:
+        for time_array, driver_array in batches:
+            while len(pending) >= 2:                  # the pinned set about to be rewritten is still being read
+                pending.popleft().result()
+            temp_storage = inner_loop(time_array=time_array, driver_array=driver_array, temp_storage=temp_storage)
+            snap = {k: (dict(v) if isinstance(v, dict) else v) for k, v in temp_storage.items()
+                    if not k.startswith("_")}
+            pending.append(pool.submit(consume, snap))
+        while pending:
+            pending.popleft().result()
+    return temp_storage
