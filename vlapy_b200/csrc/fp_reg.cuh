@@ -331,6 +331,19 @@ __global__ void __launch_bounds__(T, (M >= 64 ? 256 : 512) / T) fp_reg_kernel(co
 #ifndef FPREG_FUSE
 #define FPREG_FUSE 1
 #endif
+// Z_i = d_i N_{i-1} - a_i Z_{i-1}: with the product d_i N_{i-1} formed first (off the chain: N comes from its own
+// recurrence) the recurrence is ONE dependent FMA per cell; fma(d, N, -(a Z)) puts a multiply and an FMA on the chain
+// (the forward sweep waited on fixed-latency dependencies for 46 % of its samples).  Two roundings either way.
+// Used in the forward sweep only: the spike sweeps are fp64-pipe bound, and there the early products lengthen live
+// ranges until the chunk spills (376 bytes).
+#ifndef FPREG_ZFMA
+#define FPREG_ZFMA 1
+#endif
+#if FPREG_ZFMA
+#define FPREG_ZSTEP(d, n, a_, zprev) fma(-(a_), (zprev), (d) * (n))
+#else
+#define FPREG_ZSTEP(d, n, a_, zprev) fma((d), (n), -((a_) * (zprev)))
+#endif
 #define LU_STEP(k)                                                                        \
   {                                                                                       \
     const int o = ((k) - 1) % TB;                                                         \
@@ -455,13 +468,14 @@ __global__ void __launch_bounds__(T, (M >= 64 ? 256 : 512) / T) fp_reg_kernel(co
       for (int i = 1; i <= L; ++i) {
         if ((i & 1) == 0) { lp = lq; if (i + 2 <= L) lq = ld2_fresh(sp + i + 2); }
         const int o = (i - 1) % TB;
-        if (o == 0) { ab = TIE(CAN(i), n1); cb = TIE(CCN(i - 1), n1); }
+        // (with the one-FMA Z recurrence the coefficients are tied to z: the determinant chain must not run ahead of it)
+        if (o == 0) { ab = TIE(CAN(i), FPREG_ZFMA ? z : n1); cb = TIE(CCN(i - 1), FPREG_ZFMA ? z : n1); }
         const double ai = (o == 0) ? ab : fma(dAn, (double)o, ab);            // a'_i
         const double ck = (o == 0) ? cb : fma(-dAn, (double)o, cb);           // c'_{i-1}
         const double ni = fma(bt, n1, -((ai * ck) * n2));
         double di = (i & 1) ? lp.y : lp.x;
         if (i == L) di = fma(-Ce1, xe, di);
-        z = fma(di, sc * n1, -(ai * z));
+        z = FPREG_ZSTEP(di, sc * n1, ai, z);
         c[i] = z;
         if (i == G2) PV[t] = n1;                          // N_{G2-1}
         if (i >= G2) PV[(i - G2 + 1) * T + t] = ni;       // slot j of the top group: N_{G2-1+j}
