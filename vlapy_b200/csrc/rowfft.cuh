@@ -34,6 +34,10 @@
 
 namespace rowfft {
 
+#ifndef ROWFFT_SPECIAL_BRANCH
+#define ROWFFT_SPECIAL_BRANCH 0   // measured slower (1.607 ms against 1.551 ms, profiles/ab_r01_v15_rowfft_special_branch.txt)
+#endif
+
 using fast::fft16;
 using fast::fft8;
 
@@ -270,52 +274,19 @@ struct Prog {
     *reinterpret_cast<cplx*>(a.fout + row * a.ld_out + n) = val;
   }
 
-  // nextrow: the row this CTA handles after `row` (< 0: none); its tables are prepared in the last phase
-  VPFP_HD void phase(int ph, long row, long nextrow, int tid, Regs& r, unsigned char* smem) const {
+  // stage 3 for the sub-transforms sA, sB of the thread, pointwise step on the pairs, inverse stage 3.
+  // MS = false: the caller knows that this thread is not thread 0 (ROWFFT_SPECIAL_BRANCH: a warp-uniform branch
+  // around the select-based special case of thread 0, so that warps 1.. do not carry its selects).
+  template <bool MS>
+  VPFP_HD void pointwise_phase(int tid, Regs& r, unsigned char* smem) const {
     cplx* X = xbuf(smem);
-    cplx* TW2 = tw2(smem);
     cplx* G = tabs(smem);
     cplx* LO = G + 16;
     cplx* HI = LO + 32;
     cplx* x = r.x;
-    switch (ph) {
-      case 0: {
-        // ---- stage 1 on the row that prefetch_row brought into X (its phase tables are in place as well)
-        cp_async_commit_wait(true);
-#pragma unroll
-        for (int q = 0; q < NQ1; ++q) {
-          const int rr = tid + T * q;
-#pragma unroll
-          for (int m1 = 0; m1 < R1; ++m1) x[q * R1 + m1] = X[m1 * L2 + rr];
-          fftR<R1, -1>(x + q * R1);
-          twiddle1<false>(x + q * R1, r.w1[q], r.w4[q]);
-#pragma unroll
-          for (int k1 = 0; k1 < R1; ++k1) X[k1 * L2 + rr] = x[q * R1 + k1];
-        }
-      } break;
-      case 1: {
-        // ---- stage 2: (k1, m3) butterflies over m2
-#pragma unroll
-        for (int q = 0; q < NQ2; ++q) {
-          const int c = tid + T * q, k1 = c >> 4, m3 = c & 15;
-#pragma unroll
-          for (int m2 = 0; m2 < R2; ++m2) x[q * R2 + m2] = X[k1 * L2 + m2 * 16 + m3];
-          fftR<R2, -1>(x + q * R2);
-#pragma unroll
-          for (int k2 = 1; k2 < R2; ++k2) x[q * R2 + k2] = cmul(x[q * R2 + k2], TW2[m3 * k2]);
-        }
-      } break;
-      case 2: {
-#pragma unroll
-        for (int q = 0; q < NQ2; ++q) {
-          const int c = tid + T * q, k1 = c >> 4, m3 = c & 15;
-#pragma unroll
-          for (int k2 = 0; k2 < R2; ++k2) X[(k1 + R1 * k2) * 17 + m3] = x[q * R2 + k2];
-        }
-      } break;
-      case 3: {
+    {
         // ---- stage 3 for sub-transforms sA, sB; pointwise on pairs; inverse stage 3
-        const bool special = (tid == 0);
+        const bool special = MS && (tid == 0);
         const int sA = special ? 0 : tid, sB = special ? T : S - tid;
 #pragma unroll
         for (int m3 = 0; m3 < 16; ++m3) {
@@ -383,6 +354,59 @@ struct Prog {
         }
         fft16<1>(x);
         fft16<1>(x + 16);
+    }
+  }
+
+  // nextrow: the row this CTA handles after `row` (< 0: none); its tables are prepared in the last phase
+  VPFP_HD void phase(int ph, long row, long nextrow, int tid, Regs& r, unsigned char* smem) const {
+    cplx* X = xbuf(smem);
+    cplx* TW2 = tw2(smem);
+    cplx* G = tabs(smem);
+    cplx* LO = G + 16;
+    cplx* HI = LO + 32;
+    cplx* x = r.x;
+    switch (ph) {
+      case 0: {
+        // ---- stage 1 on the row that prefetch_row brought into X (its phase tables are in place as well)
+        cp_async_commit_wait(true);
+#pragma unroll
+        for (int q = 0; q < NQ1; ++q) {
+          const int rr = tid + T * q;
+#pragma unroll
+          for (int m1 = 0; m1 < R1; ++m1) x[q * R1 + m1] = X[m1 * L2 + rr];
+          fftR<R1, -1>(x + q * R1);
+          twiddle1<false>(x + q * R1, r.w1[q], r.w4[q]);
+#pragma unroll
+          for (int k1 = 0; k1 < R1; ++k1) X[k1 * L2 + rr] = x[q * R1 + k1];
+        }
+      } break;
+      case 1: {
+        // ---- stage 2: (k1, m3) butterflies over m2
+#pragma unroll
+        for (int q = 0; q < NQ2; ++q) {
+          const int c = tid + T * q, k1 = c >> 4, m3 = c & 15;
+#pragma unroll
+          for (int m2 = 0; m2 < R2; ++m2) x[q * R2 + m2] = X[k1 * L2 + m2 * 16 + m3];
+          fftR<R2, -1>(x + q * R2);
+#pragma unroll
+          for (int k2 = 1; k2 < R2; ++k2) x[q * R2 + k2] = cmul(x[q * R2 + k2], TW2[m3 * k2]);
+        }
+      } break;
+      case 2: {
+#pragma unroll
+        for (int q = 0; q < NQ2; ++q) {
+          const int c = tid + T * q, k1 = c >> 4, m3 = c & 15;
+#pragma unroll
+          for (int k2 = 0; k2 < R2; ++k2) X[(k1 + R1 * k2) * 17 + m3] = x[q * R2 + k2];
+        }
+      } break;
+      case 3: {
+#if ROWFFT_SPECIAL_BRANCH
+        if (tid < 32) pointwise_phase<true>(tid, r, smem);
+        else pointwise_phase<false>(tid, r, smem);
+#else
+        pointwise_phase<true>(tid, r, smem);
+#endif
       } break;
       case 4: {
         const bool special = (tid == 0);
