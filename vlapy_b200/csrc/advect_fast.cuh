@@ -194,7 +194,6 @@ __global__ void __launch_bounds__(CB* Geo<L>::TPC) pass13_kernel(const FastArgs 
 #pragma unroll
       for (int r = 0; r < 8; ++r) x[s * 8 + r] = S[(m * 8 + r) * CB + b];
       fft8<-1>(x + s * 8);
-#pragma unroll
       double* pm = out0 + (long)m * rs_out;
 #pragma unroll
       for (int kp = 0; kp < 8; ++kp) {
@@ -669,7 +668,6 @@ __global__ void __launch_bounds__(CB * 2 * Geo<L>::TPC, PFM == 1 ? 2 : 4) pass2_
     for (int q = 0; q < NA; ++q) {
       const int r = ta + TPC * q;
       fftR<R1, 1>(x + q * R1);
-#pragma unroll
       double* const pr = col0 + ((long)K1G(g) * L + r) * a.ld_out;
 #pragma unroll
       for (int j = 0; j < R1; ++j) {

@@ -290,7 +290,6 @@ struct Prog {
         rowfft::cp_async_commit_wait(false);
         rowfft::Prog<16, 16>::twiddle1<true>(x, r.w1, r.w4);
         fft16<1>(x);
-#pragma unroll
         if (!a.peer_mode) {
           cplx* dst = reinterpret_cast<cplx*>(a.fout + row * a.ld_out) + tid;
 #pragma unroll

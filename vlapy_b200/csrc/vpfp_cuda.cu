@@ -47,7 +47,6 @@ static bool is_pow2(long n) { return n > 0 && (n & (n - 1)) == 0; }
 struct ProfRec { const char* label; cudaEvent_t a, b; };
 static bool g_prof_on = false;
 static std::vector<ProfRec> g_prof;
-static const char* g_prof_op = "";
 struct ProfScope {
   cudaStream_t st; bool on; size_t idx;
   ProfScope(const char* label, cudaStream_t s) : st(s), on(g_prof_on), idx(0) {
