@@ -361,9 +361,6 @@ struct Prog {
   VPFP_HD void phase(int ph, long row, long nextrow, int tid, Regs& r, unsigned char* smem) const {
     cplx* X = xbuf(smem);
     cplx* TW2 = tw2(smem);
-    cplx* G = tabs(smem);
-    cplx* LO = G + 16;
-    cplx* HI = LO + 32;
     cplx* x = r.x;
     switch (ph) {
       case 0: {
