@@ -344,15 +344,27 @@ __global__ void __launch_bounds__(T, (M >= 64 ? 256 : 512) / T) fp_reg_kernel(co
 #else
 #define FPREG_ZSTEP(d, n, a_, zprev) fma((d), (n), -((a_) * (zprev)))
 #endif
+// FPREG_ZFMA_SPIKE (candidate for the next A/B, off): the same one-FMA recurrence in the two spike sweeps, coefficients
+// tied to the right-hand-side chains z / tt instead of the determinant chains.
+#ifndef FPREG_ZFMA_SPIKE
+#define FPREG_ZFMA_SPIKE 0
+#endif
+#if FPREG_ZFMA_SPIKE
+#define FPREG_SPIKE_ZSTEP(d, n, a_, zprev) fma(-(a_), (zprev), (d) * (n))
+#define FPREG_SPIKE_TIE(nchain, zchain) (zchain)
+#else
+#define FPREG_SPIKE_ZSTEP(d, n, a_, zprev) fma((d), (n), -((a_) * (zprev)))
+#define FPREG_SPIKE_TIE(nchain, zchain) (nchain)
+#endif
 #define LU_STEP(k)                                                                        \
   {                                                                                       \
     const int o = ((k) - 1) % TB;                                                         \
-    if (o == 0) { ab = TIE(CAN(k), n1); cb = TIE(CCN((k) - 1), n1); }                     \
+    if (o == 0) { ab = TIE(CAN(k), FPREG_SPIKE_TIE(n1, z)); cb = TIE(CCN((k) - 1), FPREG_SPIKE_TIE(n1, z)); } \
     const double ak = (o == 0) ? ab : fma(dAn, (double)o, ab);  /* a'_k */                \
     const double ck = (o == 0) ? cb : fma(-dAn, (double)o, cb); /* c'_{k-1} */            \
     const double nk = fma(bt, n1, -((ak * ck) * n2));                                     \
     if (((k) & 1) == 0) { lp = lq; if ((k) + 2 <= L) lq = ld2_fresh(sp + (k) + 2); }      \
-    z = fma(((k) & 1) ? lp.y : lp.x, n1, -(ak * z));                                      \
+    z = FPREG_SPIKE_ZSTEP(((k) & 1) ? lp.y : lp.x, n1, ak, z);                             \
     g = -ak * g;                                                                          \
     n2 = n1; n1 = nk;                                                                     \
   }
@@ -360,12 +372,12 @@ __global__ void __launch_bounds__(T, (M >= 64 ? 256 : 512) / T) fp_reg_kernel(co
   {                                                                                       \
     const int o = ((k) - 1) % TB;                                                         \
     const int i = L - (k);                                                                \
-    if (o == 0) { ub = TIE(CCN(i), m1); vb = TIE(CAN(i + 1), m1); }                       \
+    if (o == 0) { ub = TIE(CCN(i), FPREG_SPIKE_TIE(m1, tt)); vb = TIE(CAN(i + 1), FPREG_SPIKE_TIE(m1, tt)); } \
     const double ci = (o == 0) ? ub : fma(dAn, (double)o, ub);  /* c'_i */                \
     const double ai = (o == 0) ? vb : fma(-dAn, (double)o, vb); /* a'_{i+1} */            \
     const double mi = fma(bt, m1, -((ai * ci) * m2));                                     \
     if ((i & 1) == 1) { up = uq; if (i - 3 >= 0) uq = ld2_fresh(sp + i - 3); }            \
-    tt = fma((i & 1) ? up.y : up.x, m1, -(ci * tt));                                      \
+    tt = FPREG_SPIKE_ZSTEP((i & 1) ? up.y : up.x, m1, ci, tt);                             \
     h = -ci * h;                                                                          \
     m2 = m1; m1 = mi;                                                                     \
   }
