@@ -1008,11 +1008,20 @@ int vpfp_xmodes_partial(const double* f, long ld, double* out, int nmodes, int b
   XmodesProg p;
   p.f = f; p.ld = ld; p.nmodes = nmodes; p.batch = batch; p.nx = nx; p.ncols = ncols;
   p.x_offset = x_offset; p.nx_total = nx_total;
-  const int threads = 128;
+  // A/B knobs (defaults = the measured configuration): VPFP_XMODES_THREADS (threads per CTA: a CTA reads
+  // threads x 16 contiguous bytes of every row), VPFP_XMODES_XCH (upper limit of the number of row chunks)
+  static int env_threads = -1, env_xch = -1;
+  if (env_threads < 0) {
+    const char* e1 = getenv("VPFP_XMODES_THREADS");
+    const char* e2 = getenv("VPFP_XMODES_XCH");
+    env_threads = (e1 && (atoi(e1) == 64 || atoi(e1) == 256 || atoi(e1) == 512)) ? atoi(e1) : 128;
+    env_xch = (e2 && atoi(e2) >= 1 && atoi(e2) <= 256) ? atoi(e2) : 32;
+  }
+  const int threads = env_threads;
   p.cblocks = (ncols + threads - 1) / threads;
   int xch = nx / 128;
   if (xch < 1) xch = 1;
-  if (xch > 32) xch = 32;
+  if (xch > env_xch) xch = env_xch;
   p.xchunks = xch;
   void* scratch = nullptr;
   size_t bytes = (size_t)batch * xch * nmodes * ncols * 2 * sizeof(double);
