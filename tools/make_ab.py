@@ -1,12 +1,13 @@
 """Prepare an A/B of two builds of the library for one short GPU call.
 
-    python tools/make_ab.py <git-ref> [-D MACRO=VALUE ...]
+    python tools/make_ab.py <git-ref> [-DMACRO=VALUE ...]
 
 builds vlapy_b200/lib/libvpfp_b200_base.so from the sources of <git-ref> (a worktree under /tmp; the working tree is
-not touched) and rebuilds vlapy_b200/lib/libvpfp_b200.so from the working tree (with the given -D flags, if any).  On
-the GPU box:
+not touched) and the working tree into vlapy_b200/lib/libvpfp_b200.so -- or, when -D flags are given (a candidate
+behind a macro), into vlapy_b200/lib/libvpfp_b200_cand.so, so that the product library never carries a candidate's
+flags.  On the GPU box:
 
-    python tools/time_libs.py vlapy_b200/lib/libvpfp_b200_base.so vlapy_b200/lib/libvpfp_b200.so      # e df/dv, one process
+    python tools/time_libs.py vlapy_b200/lib/libvpfp_b200_base.so vlapy_b200/lib/libvpfp_b200[_cand].so   # e df/dv, one process
     VPFP_B200_LIB=$PWD/vlapy_b200/lib/libvpfp_b200_base.so python tools/time_ops.py 16384 16384 "<ops>"   # any operator
     python tools/time_ops.py 16384 16384 "<ops>"
 
@@ -28,11 +29,11 @@ def ptxas_summary(text):
         if m:
             name = m.group(1)
         m = re.search(r"(\d+) bytes stack frame, (\d+) bytes spill stores, (\d+) bytes spill loads", line)
-        if m and name:
-            out.setdefault(name, {})["spill"] = (int(m.group(2)), int(m.group(3)))
+        if m and name and "spill" not in out.setdefault(name, {}):      # (later lines belong to device functions)
+            out[name]["spill"] = (int(m.group(2)), int(m.group(3)))
         m = re.search(r"Used (\d+) registers", line)
-        if m and name:
-            out.setdefault(name, {})["regs"] = int(m.group(1))
+        if m and name and "regs" not in out.setdefault(name, {}):
+            out[name]["regs"] = int(m.group(1))
     return out
 
 
@@ -57,12 +58,14 @@ def main():
         base = build(wt, os.path.join(ROOT, "vlapy_b200", "lib", "libvpfp_b200_base.so"), [])
     finally:
         subprocess.run(["git", "-C", ROOT, "worktree", "remove", "--force", wt], capture_output=True)
-    new = build(ROOT, _lib.SO, defines)
+    target = os.path.join(ROOT, "vlapy_b200", "lib", "libvpfp_b200_cand.so") if defines else _lib.SO
+    new = build(ROOT, target, defines)
     for k in sorted(set(base) | set(new)):
         if base.get(k) != new.get(k):
             short = subprocess.run(["c++filt", k], capture_output=True, text=True).stdout.strip()[:100]
             print("%-100s  base %s  new %s" % (short, base.get(k), new.get(k)))
-    print("base:", ref, "-> vlapy_b200/lib/libvpfp_b200_base.so ; new: working tree", " ".join(defines))
+    print("base:", ref, "-> vlapy_b200/lib/libvpfp_b200_base.so ; new: working tree", " ".join(defines), "->",
+          os.path.relpath(target, ROOT))
 
 
 if __name__ == "__main__":
