@@ -141,7 +141,7 @@ def ensemble_arm(args):
         state = step_fn(state, dt * i)
     barrier()
     sampler = ClockSampler(local_rank); sampler.start()
-    ops.launch_count = 0
+    ops.launch_count(reset=True)
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
     for i in range(W, W + K):
@@ -149,7 +149,7 @@ def ensemble_arm(args):
     ev1.record()
     barrier()
     ms = ev0.elapsed_time(ev1)
-    launches = ops.launch_count
+    launches = ops.launch_count()
     clocks = sampler.summary()
     mean_n = float(state["series"][:, 0].mean())
     # end to end: upload the shard's state, K steps, download state + series
@@ -421,7 +421,7 @@ def gpu_arm(args):
         barrier()
         sampler = ClockSampler(local_rank)
         sampler.start()
-        ops.launch_count = 0
+        ops.launch_count(reset=True)
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         ev0.record()
         for i in range(W, W + K):
@@ -429,17 +429,17 @@ def gpu_arm(args):
         ev1.record()
         barrier()
         ms = ev0.elapsed_time(ev1)
-        launches = ops.launch_count
+        launches = ops.launch_count()
         clocks = sampler.summary()
         # ---- per-kernel durations (second pass over the same steps, events around every launch)
         ops.profile_enable(True)
-        ops.launch_count = 0
+        ops.launch_count(reset=True)
         for i in range(W, W + K):
             work, _ = one_step(work, i)      # eager, so that every launch is bracketed by events
         prof = ops.profile_report()
         ops.profile_enable(False)
         if use_graph:
-            launches = ops.launch_count      # kernels per step are the same in the captured graph
+            launches = ops.launch_count()    # kernels per step are the same in the captured graph
             mean_n = float(rows[W + K - 1, 8 * nx])
         else:
             mean_n = float(work["series"]["_rows"][W + K - 1, 0])

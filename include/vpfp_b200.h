@@ -34,9 +34,6 @@ extern "C" {
                               * the generic kernels always use the exact phases */
 #define VPFP_FORCE_GENERIC 2 /* testing: skip the register-resident kernels */
 #define VPFP_FORCE_THREE_PASS 4 /* testing / A-B timing: skip the single-pass row kernel */
-#define VPFP_ROW_TWO_CTA 8   /* e df/dv at nv = 16384: the two-CTAs-per-SM row kernel (rowfft2.cuh) */
-#define VPFP_ROW_ONE_CTA 16  /* e df/dv at nv = 16384: the one-CTA-per-SM row kernel (rowfft.cuh);
-                              * neither flag: the library default (environment VPFP_ROWFFT2=0/1) */
 
 /* collision operator ids (vlapy/core/collisions.py:292-317) */
 #define VPFP_FP_LB 0
@@ -45,6 +42,16 @@ extern "C" {
 int vpfp_abi_version(void);
 const char *vpfp_last_error(void);
 int vpfp_shutdown(void);
+
+/* Number of kernels this library has enqueued since the last reset (all devices, all streams; kernels replayed
+ * by a CUDA graph are counted once, at capture).  bench.py reports it as gpu_launches. */
+long vpfp_launch_count(int reset);
+
+/* Counts reallocations of the library's reduction scratch (x-mode partials, fused density partials).  Outgrown
+ * blocks are retired, never freed before vpfp_shutdown, so a CUDA graph captured earlier stays valid; callers
+ * that want their graphs to use the current block re-capture when this number has changed.  The scratch is
+ * shared by the streams of a device: calls that use it must not run concurrently on two streams. */
+unsigned long vpfp_scratch_generation(void);
 
 /* Per-launch timing for benchmarking: when enabled, every kernel launch of this library is
  * bracketed by CUDA events on its stream.  vpfp_profile_report() synchronises the device, writes

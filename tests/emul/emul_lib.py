@@ -12,7 +12,7 @@ CSRC = os.path.join(os.path.dirname(os.path.dirname(HERE)), "vlapy_b200", "csrc"
 
 
 def build(force=False):
-    deps = [SRC] + [os.path.join(CSRC, n) for n in ("advect.h", "rowops.h", "vpfp_common.h", "butterflies.h", "rowfft.cuh", "rowfft4.cuh", "rowfft2.cuh")]
+    deps = [SRC] + [os.path.join(CSRC, n) for n in ("advect.h", "rowops.h", "vpfp_common.h", "butterflies.h", "rowfft.cuh")]
     if force or not os.path.exists(SO) or any(os.path.getmtime(d) > os.path.getmtime(SO) for d in deps):
         subprocess.check_call(["g++", "-O2", "-ffp-contract=off", "-std=c++17", "-shared", "-fPIC",
                                "-o", SO, SRC])

@@ -196,8 +196,6 @@ extern "C" int emul_butterfly(double* xy, int radix, int dir) {
 
 // ---- single-pass row kernel (vlapy_b200/csrc/rowfft.cuh): per-thread registers persist across phases
 #include "../../vlapy_b200/csrc/rowfft.cuh"
-#include "../../vlapy_b200/csrc/rowfft4.cuh"
-#include "../../vlapy_b200/csrc/rowfft2.cuh"
 template <class P>
 static void run_rowfft(const P& prog) {
   std::vector<typename P::Regs> regs((size_t)P::T);
@@ -237,11 +235,7 @@ extern "C" int emul_edfdv_rowfft(const double* f_in, long ld_in, double* f_out, 
   memset(&a, 0, sizeof(a));
   a.fin = f_in; a.ld_in = ld_in; a.fout = f_out; a.ld_out = ld_out; a.kvec = kv; a.cvec = e; a.dt = dt;
   a.nrows = rows; a.twN = tw.data();
-  const char* v4 = getenv("VPFP_EMUL_ROWFFT4");
-  const char* v2 = getenv("VPFP_EMUL_ROWFFT2");
-  if (nv == 16384 && v4 && atoi(v4)) { rowfft4::Prog p; p.a = a; run_rowfft(p); }      // rowfft4.cuh
-  else if (nv == 16384 && v2 && atoi(v2)) { rowfft2::Prog p; p.a = a; run_rowfft(p); }   // rowfft2.cuh
-  else if (nv == 16384) { rowfft::Prog<32, 16> p; p.a = a; run_rowfft(p); }
+  if (nv == 16384) { rowfft::Prog<32, 16> p; p.a = a; run_rowfft(p); }
   else if (nv == 8192) { rowfft::Prog<16, 16> p; p.a = a; run_rowfft(p); }
   else if (nv == 4096) { rowfft::Prog<8, 16> p; p.a = a; run_rowfft(p); }
   else return 1;

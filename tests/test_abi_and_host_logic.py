@@ -91,9 +91,9 @@ def test_flag_constants_match_the_header():
     from vlapy_b200 import ops
     hdr = open(os.path.join(ROOT, "include", "vpfp_b200.h")).read()
     macros = {m: int(v) for m, v in re.findall(r"#define\s+(VPFP_[A-Z0-9_]+)\s+(\d+)\b", hdr)}
-    for name in ("PHASE_EXACT", "PHASE_TABLE", "FORCE_GENERIC", "FORCE_THREE_PASS", "ROW_TWO_CTA", "ROW_ONE_CTA"):
+    for name in ("PHASE_EXACT", "PHASE_TABLE", "FORCE_GENERIC", "FORCE_THREE_PASS"):
         assert macros["VPFP_" + name] == getattr(ops, name), name
-    flags = [macros["VPFP_" + n] for n in ("PHASE_TABLE", "FORCE_GENERIC", "FORCE_THREE_PASS", "ROW_TWO_CTA", "ROW_ONE_CTA")]
+    flags = [macros["VPFP_" + n] for n in ("PHASE_TABLE", "FORCE_GENERIC", "FORCE_THREE_PASS")]
     assert len(set(flags)) == len(flags) and all(f & (f - 1) == 0 for f in flags)      # distinct single bits
 
 

@@ -67,6 +67,9 @@ class OracleBackend:
     def zeros(self, shape):
         return torch.zeros(shape, dtype=torch.float64)
 
+    def upload(self, a):
+        return a if isinstance(a, torch.Tensor) else torch.from_numpy(a)
+
 
 def _worker(rank, world, port, integ, fp_type, nsteps, q):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
@@ -137,3 +140,83 @@ def test_topology_rejects_uneven_shards():
         vd.Topology(10, 32, rank=0, world=4)
     with pytest.raises(NotImplementedError):
         vd.Topology(16, 6, rank=0, world=2)      # 3 columns per rank: odd
+
+
+# ---------------------------------------------------------------------------------------------
+# the sharded inner loop BEHIND THE REFERENCE API (vlapy_b200.outer_loop.get_sim_config_and_inner_loop_step
+# under an initialised process group), against the reference's own outer_loop outputs (golden nlepw_c2 small_*)
+# ---------------------------------------------------------------------------------------------
+RULES = {"time": "first-last", "space": ["k0", "k1"]}
+
+
+def _inner_loop_worker(rank, world, port, gather, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from vlapy_b200 import outer_loop
+        cfg = O.nlepw_config(nx=16, nv=128, k0=0.35, log_nu=-2)
+        params = {"backend": {"core": "b200", "gather": gather,
+                              "shard_backend": lambda topo, stuff, fp: OracleBackend(topo, cfg, fp)},
+                  "nu": cfg["nu"],
+                  "vlasov-poisson": {"time": "leapfrog", "vdfdx": "exponential", "edfdv": "exponential",
+                                     "poisson": "spectral"},
+                  "fokker-planck": {"type": "lb", "solver": "batched_tridiagonal"}}
+        stuff = {k: cfg[k] for k in ("kx", "x", "one_over_kx", "v", "kv", "nv", "nx", "dv", "dt", "nu",
+                                     "driver_function")}
+        stuff.update(e=cfg["e0"], f=cfg["f0"], rules_to_store_f=RULES)
+        nt = 24
+        sim, inner = outer_loop.get_sim_config_and_inner_loop_step(params, stuff, nt, RULES)
+        assert inner.topology.world == world
+        outs = []
+        for li in range(2):
+            t = cfg["dt"] * np.arange(li * nt, (li + 1) * nt)
+            drv = np.stack([cfg["driver_function"](ti) for ti in t])
+            sim = inner(time_array=t, driver_array=drv, temp_storage=sim)
+            outs.append({"fields": {k: np.array(v) for k, v in sim["fields"].items()},
+                         "series": {k: np.array(v) for k, v in sim["series"].items()},
+                         "stored_f": np.array(sim["stored_f"]), "f": np.array(sim["f"]), "e": np.array(sim["e"]),
+                         "f_slab": sim["f_slab"]})
+        q.put((rank, outs))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("gather", ["rank0", "slab"])
+def test_sharded_inner_loop_behind_the_reference_api(gather):
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29571 + (gather == "slab")
+    procs = [ctx.Process(target=_inner_loop_worker, args=(r, world, port, gather, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = dict(q.get(timeout=300) for _ in range(world))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    g = np.load(os.path.join(ROOT, "tests", "golden", "nlepw_c2.npz"))
+    nx = 16
+    for li in range(2):
+        for rank in range(world):
+            o = res[rank][li]
+            for k in ("e", "driver", "n", "j", "T", "q", "fv4", "vN"):          # every rank holds the global rows
+                ref = g["small_fields_%s_%d" % (k, li)]
+                assert o["fields"][k].shape == ref.shape
+                # a v^p moment amplifies rounding differences of f by int |v|^p dv
+                pw = {"n": 0, "j": 1, "T": 2, "q": 3, "fv4": 4, "vN": 5}.get(k, 0)
+                assert np.max(np.abs(o["fields"][k] - ref)) < 1e-13 * 2 * 6.4 ** (pw + 1) / (pw + 1), (k, li)
+            for k in O.SERIES_KEYS + ("mean_cum_de2", "mean_t_plus_e2_minus_cum_de2", "mean_t_plus_e2_plus_cum_de2"):
+                np.testing.assert_allclose(o["series"][k], g["small_series_%s_%d" % (k, li)], rtol=1e-9, atol=1e-13,
+                                           err_msg=k)
+            assert o["stored_f"].dtype == np.complex64
+            ref = g["small_stored_f_%d" % li]
+            assert np.max(np.abs(o["stored_f"] - ref)) < 1e-6 * np.max(np.abs(ref))
+            assert np.max(np.abs(o["e"] - g["small_e_%d" % li])) < 1e-12
+        fref = g["small_f_%d" % li]
+        if gather == "rank0":
+            assert res[0][li]["f_slab"] == (0, nx)
+            assert np.max(np.abs(res[0][li]["f"] - fref)) / np.max(np.abs(fref)) < 1e-12
+            assert res[1][li]["f_slab"] == (nx // 2, nx)
+        f = np.concatenate([res[0][li]["f"][:nx // 2] if gather == "rank0" else res[0][li]["f"], res[1][li]["f"]])
+        assert np.max(np.abs(f - fref)) / np.max(np.abs(fref)) < 1e-12

@@ -238,48 +238,3 @@ def test_fp_reg_stiffness_and_nan_semantics():
     out, mom = E.fp_simt(1, g, v, 0.0, 0.1, dv, "lb")
     assert rel_err(out, g) < 1e-15            # nu = 0: identity matrix
     assert np.isfinite(mom[7, 0]) and np.isnan(mom[7, 1])
-
-
-def test_rowfft4_program(monkeypatch):
-    """rowfft4.cuh (512 threads x 16 points, radix 16 x 8 x 8 x 8, one in-place exchange layout) against
-    the oracle, in three thread orders (a race inside a phase would make the result order dependent)."""
-    nv = 16384
-    rng = np.random.default_rng(4)
-    dv, v, kv = O.velocity_grid(6.4, nv)
-    f = rng.standard_normal((5, nv))
-    f[1] = np.exp(-v ** 2 / 2) * (1 + 1e-3 * rng.standard_normal(nv))
-    e = np.array([0.05, -0.7, 1.3, 0.0, 2.5])
-    monkeypatch.setenv("VPFP_EMUL_ROWFFT4", "1")
-    outs = []
-    for order in ("0", "1", "2"):
-        monkeypatch.setenv("VPFP_EMUL_ORDER", order)
-        for dt in (0.37, -0.066):
-            out = E.edfdv_rowfft(f, e, kv, dt)
-            assert rel_err(out, O.edfdv_exponential(f, e, dt, kv)) < TOL
-            outs.append(out)
-    assert np.array_equal(outs[0], outs[2]) and np.array_equal(outs[0], outs[4])
-
-
-def test_rowfft2_program(monkeypatch):
-    """rowfft2.cuh (128 threads, one parity of the spectrum at a time, half-size exchanges, parity 0 parked
-    in shared memory; two CTAs per SM on the GPU) against the oracle and against rowfft.cuh, in three
-    thread orders (a race inside a phase would make the result order dependent)."""
-    nv = 16384
-    rng = np.random.default_rng(5)
-    dv, v, kv = O.velocity_grid(6.4, nv)
-    f = rng.standard_normal((5, nv))
-    f[1] = np.exp(-v ** 2 / 2) * (1 + 1e-3 * rng.standard_normal(nv))
-    f[3] = 0.0
-    f[3, 4097] = 1.0                       # a single cell: every bin carries the same magnitude
-    e = np.array([0.05, -0.7, 1.3, 0.0, 2.5])
-    one_cta = {dt: E.edfdv_rowfft(f, e, kv, dt) for dt in (0.37, -0.066)}
-    monkeypatch.setenv("VPFP_EMUL_ROWFFT2", "1")
-    outs = []
-    for order in ("0", "1", "2"):
-        monkeypatch.setenv("VPFP_EMUL_ORDER", order)
-        for dt in (0.37, -0.066):
-            out = E.edfdv_rowfft(f, e, kv, dt)
-            assert rel_err(out, O.edfdv_exponential(f, e, dt, kv)) < TOL
-            assert rel_err(out, one_cta[dt]) < TOL
-            outs.append(out)
-    assert np.array_equal(outs[0], outs[2]) and np.array_equal(outs[0], outs[4])

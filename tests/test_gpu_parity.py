@@ -491,32 +491,6 @@ def test_single_pass_row_kernel(dev, nv, rows):
         assert rel_err(one.cpu().numpy(), three.cpu().numpy()) < TOL
 
 
-@pytest.mark.parametrize("rows", [257, 1024])
-def test_two_cta_row_kernel(dev, rows):
-    """e df/dv at nv = 16384 as the two-CTAs-per-SM row kernel (csrc/rowfft2.cuh: one parity of the spectrum at a
-    time, half-size exchanges) against the oracle and against the one-CTA-per-SM kernel (csrc/rowfft.cuh);
-    smooth + noise rows, both signs of dt, a row pitch larger than the row, more rows than resident CTAs."""
-    from vlapy_b200 import ops
-    nv = 16384
-    rng = np.random.default_rng(nv + rows + 1)
-    dv, v, kv = O.velocity_grid(6.4, nv)
-    f = np.exp(-v ** 2 / 2)[None, :] * (1 + 0.1 * rng.standard_normal((rows, nv)))
-    f[::7] = rng.standard_normal((len(f[::7]), nv))
-    e = 0.3 * rng.standard_normal(rows)
-    big = torch.zeros((rows, nv + 16), dtype=torch.float64, device=dev)
-    big[:, :nv] = torch.from_numpy(f).to(dev)
-    fd, ed, kd = big[:, :nv], torch.from_numpy(e).to(dev), torch.from_numpy(kv).to(dev)
-    for dt in (0.125, -0.033):
-        ref = O.edfdv_exponential(f, e, dt, kv)
-        two = ops.edfdv_exp(fd, ed, kd, dt, flags=ops.PHASE_TABLE | ops.ROW_TWO_CTA).cpu().numpy()
-        one = ops.edfdv_exp(fd, ed, kd, dt, flags=ops.PHASE_TABLE | ops.ROW_ONE_CTA).cpu().numpy()
-        assert rel_err(two, ref) < TOL
-        assert rel_err(one, ref) < TOL
-        assert rel_err(two, one) < 1e-13
-        assert not np.array_equal(two, one)        # the two kernels round differently: both really ran
-
-
-
 @pytest.mark.parametrize("graph", [True, False])
 def test_run_loops_with_two_pinned_sets_equals_sequential_calls(dev, graph):
     """outer_loop.run_loops (storage hand-off overlapped with the next inner loop, backend.pinned_sets = 2): what

@@ -11,7 +11,7 @@ flags.  On the GPU box:
     VPFP_B200_LIB=$PWD/vlapy_b200/lib/libvpfp_b200_base.so python tools/time_ops.py 16384 16384 "<ops>"   # any operator
     python tools/time_ops.py 16384 16384 "<ops>"
 
-(`tools/gpu_session20.sh` ... `27.sh` are examples; a call of this kind costs 30-80 s of GPU time.)  Also prints the
+(stage `ab:<ops>` of `tools/gpu_session.sh` runs exactly this; a call of this kind costs 30-80 s of GPU time.)  Also prints the
 ptxas register / spill summary of the kernels whose numbers changed between the two builds -- the first thing to look
 at before spending GPU time (a jump in spill bytes has so far always meant a slower kernel).  Delete the base library
 before committing measurements: only libvpfp_b200.so is the product."""

@@ -11,7 +11,7 @@ ROOT = os.path.dirname(PKG)
 # VPFP_B200_LIB: another build of the same CUDA library (A/B timing of two revisions in one GPU session)
 SO = os.environ.get("VPFP_B200_LIB") or os.path.join(PKG, "lib", "libvpfp_b200.so")
 SRC = os.path.join(PKG, "csrc", "vpfp_cuda.cu")
-HEADERS = [os.path.join(PKG, "csrc", n) for n in ("vpfp_common.h", "advect.h", "rowops.h", "butterflies.h", "rowfft.cuh", "rowfft4.cuh", "rowfft2.cuh",
+HEADERS = [os.path.join(PKG, "csrc", n) for n in ("vpfp_common.h", "advect.h", "rowops.h", "butterflies.h", "rowfft.cuh",
                                                     "advect_fast.cuh", "fp_fast.cuh", "fp_reg.cuh")] + [
     os.path.join(ROOT, "include", "vpfp_b200.h")]
 
@@ -42,6 +42,8 @@ _SIGS = {
     "vpfp_abi_version": ([], _I),
     "vpfp_last_error": ([], _c.c_char_p),
     "vpfp_shutdown": ([], _I),
+    "vpfp_launch_count": ([_I], _L),
+    "vpfp_scratch_generation": ([], _c.c_ulong),
     "vpfp_profile_enable": ([_I], _I),
     "vpfp_profile_report": ([_c.c_char_p, _I], _I),
     "vpfp_edfdv_exp": ([_P, _L, _P, _L, _P, _P, _D, _I, _I, _I, _P], _I),

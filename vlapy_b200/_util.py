@@ -27,3 +27,19 @@ def const(x):
 def back(t, to_host):
     """return the same kind the caller passed in"""
     return t.cpu().numpy() if to_host else t
+
+
+def attach_density(f, n):
+    """remember the charge density n = trapz_v f that the producing kernel already reduced, together with
+    the tensor version it belongs to: an in-place change of f afterwards invalidates it"""
+    f._vpfp_density = (n, f._version)
+    return f
+
+
+def cached_density(f):
+    """the density attached by ``attach_density`` if f has not been modified in place since, else None
+    (the caller then integrates f itself, as vlapy/core/field.py:27-36 always does)"""
+    c = getattr(f, "_vpfp_density", None)
+    if c is None or c[1] != f._version:
+        return None
+    return c[0]

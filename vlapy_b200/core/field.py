@@ -2,7 +2,7 @@
 import torch
 
 from .. import ops
-from .._util import back, const, to_dev
+from .._util import back, cached_density, const, to_dev
 
 
 def compute_charges(f, dv):
@@ -29,7 +29,7 @@ def get_spectral_solver(dv, one_over_kx):
     def solve_total_electric_field(driver_field, f):
         f_d, host = to_dev(f)
         drv, _ = to_dev(driver_field)
-        n = getattr(f, "_vpfp_density", None)       # reduced by the v df/dx epilogue that produced f
+        n = cached_density(f) if isinstance(f, torch.Tensor) else None   # reduced by the v df/dx epilogue that produced f
         if n is None:
             n = compute_charges(f_d, dv)
         o = ook if ook.shape == n.shape else ook.expand_as(n).contiguous()

@@ -10,7 +10,7 @@ import os
 import numpy as np
 
 from .. import ops
-from .._util import back, const, to_dev
+from .._util import attach_density, back, const, to_dev
 
 
 def _check_wavenumbers(k, what):
@@ -36,7 +36,11 @@ def _phase_flags(k):
     n = k.shape[-1]
     m = np.arange(n // 2 + 1)
     lin = m * k[..., 1:2]
-    if n >= 4 and np.all(np.abs(np.abs(k[..., : n // 2 + 1]) - np.abs(lin)) <= 8 * np.finfo(float).eps * np.abs(lin)):
+    half = k[..., : n // 2 + 1].copy()
+    half[..., n // 2] = -half[..., n // 2] if n % 2 == 0 else half[..., n // 2]   # fftfreq stores the Nyquist bin as -N/2
+    # signed comparison: the table kernels assume k[m] = m k[1] (the antisymmetric upper half follows from
+    # _check_wavenumbers)
+    if n >= 4 and np.all(np.abs(half - lin) <= 8 * np.finfo(float).eps * np.abs(lin)):
         return ops.PHASE_TABLE
     return ops.PHASE_EXACT
 
@@ -46,8 +50,9 @@ def get_vdfdx_exponential(kx, v, dv=None):
 
     kx may be (nx,) or (batch, nx) for ensembles of simulations with their own box length.
     With ``dv`` the charge density of the result is reduced in the kernel's epilogue and attached
-    to the returned device tensor (``_vpfp_density``) for the field solve that always follows
-    (vlapy/core/vlasov_poisson.py:54-55); the tensor must not be modified in place in between."""
+    to the returned device tensor (``_util.attach_density``) for the field solve that always follows
+    (vlapy/core/vlasov_poisson.py:54-55); an in-place change of the tensor in between invalidates it
+    (the tensor's version is recorded) and the field solve integrates f itself."""
     kx_d = const(_check_wavenumbers(kx, "v df/dx"))
     v_d = const(v)
     flags = _phase_flags(kx)
@@ -58,8 +63,7 @@ def get_vdfdx_exponential(kx, v, dv=None):
             return back(ops.vdfdx_exp(f_d.contiguous(), kx_d, v_d, dt, flags=flags), host)
         n = f_d.new_empty(f_d.shape[:-1])
         out = ops.vdfdx_exp(f_d.contiguous(), kx_d, v_d, dt, flags=flags, density_out=n, dv=dv)
-        out._vpfp_density = n
-        return out
+        return attach_density(out, n)
 
     return step_vdfdx_exponential
 

@@ -5,6 +5,7 @@
 // stream and returns; failures are reported through the return code + vpfp_last_error().
 #include <cuda_runtime.h>
 
+#include <atomic>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -19,8 +20,6 @@
 #include "fp_fast.cuh"
 #include "fp_reg.cuh"
 #include "rowfft.cuh"
-#include "rowfft4.cuh"
-#include "rowfft2.cuh"
 #include "rowops.h"
 
 // ------------------------------------------------------------------------------------------
@@ -47,9 +46,11 @@ static bool is_pow2(long n) { return n > 0 && (n & (n - 1)) == 0; }
 struct ProfRec { const char* label; cudaEvent_t a, b; };
 static bool g_prof_on = false;
 static std::vector<ProfRec> g_prof;
+static std::atomic<long> g_launches{0};   // kernels enqueued by this library (vpfp_launch_count)
 struct ProfScope {
   cudaStream_t st; bool on; size_t idx;
-  ProfScope(const char* label, cudaStream_t s) : st(s), on(g_prof_on), idx(0) {
+  ProfScope(const char* label, cudaStream_t s, int nlaunch = 1) : st(s), on(g_prof_on), idx(0) {
+    g_launches += nlaunch;
     if (!on) return;
     ProfRec r; r.label = label;
     cudaEventCreate(&r.a); cudaEventCreate(&r.b);
@@ -104,8 +105,9 @@ struct DeviceCache {
   std::map<int, cplx*> tw;
   void* scratch[4] = {nullptr, nullptr, nullptr, nullptr};   // grow-only, one per purpose
   size_t scratch_bytes[4] = {0, 0, 0, 0};
+  std::vector<void*> retired;   // outgrown scratch blocks: kept until vpfp_shutdown (a captured CUDA graph may hold them)
 };
-enum { SCR_XMODES = 0, SCR_PHANTOM = 1, SCR_DENSITY = 2 };
+enum { SCR_XMODES = 0, SCR_PHANTOM = 1, SCR_DENSITY = 2, SCR_TRIDIAG = 3 };
 static std::map<int, DeviceCache> g_cache;
 static std::mutex g_cache_mu;
 
@@ -138,17 +140,25 @@ static int get_twiddles(int N, const cplx** out) {
   return VPFP_OK;
 }
 
+// Reduction scratch: one grow-only block per device and purpose.  A block that has become too small is RETIRED, not
+// freed (no cudaFree, hence no implicit device synchronisation and no dangling pointer): a CUDA graph captured
+// earlier keeps writing to the block it was captured with, which nobody else uses any more.  Growing needs a
+// cudaMalloc, which is illegal during stream capture: callers that capture a graph run the same calls once before
+// (vlapy_b200/outer_loop.py _GraphStep.capture does).  The blocks are shared by all streams of a device: calls that
+// use scratch (x-modes, fused density, odd row counts) must not run concurrently on two streams of one device.
+static unsigned long g_scratch_generation = 0;
 static int get_scratch(int slot, size_t bytes, void** out) {
   int dev = 0;
   CUDA_TRY(cudaGetDevice(&dev));
   std::lock_guard<std::mutex> lk(g_cache_mu);
   DeviceCache& c = g_cache[dev];
   if (c.scratch_bytes[slot] < bytes) {
-    if (c.scratch[slot]) CUDA_TRY(cudaFree(c.scratch[slot]));   // implicit device sync: safe
-    c.scratch[slot] = nullptr;
-    c.scratch_bytes[slot] = 0;
-    CUDA_TRY(cudaMalloc(&c.scratch[slot], bytes));
+    void* fresh = nullptr;
+    CUDA_TRY(cudaMalloc(&fresh, bytes));
+    if (c.scratch[slot]) c.retired.push_back(c.scratch[slot]);
+    c.scratch[slot] = fresh;
     c.scratch_bytes[slot] = bytes;
+    ++g_scratch_generation;
   }
   *out = c.scratch[slot];
   return VPFP_OK;
@@ -158,9 +168,21 @@ static int get_scratch(int slot, size_t bytes, void** out) {
 // advection / Poisson launcher
 // ------------------------------------------------------------------------------------------
 // ---- fast register-resident path (advect_fast.cuh): N1, N2 in {64, 128}
+// dynamic shared memory above 48 KB is an opt-in per kernel AND per device (function attributes belong to
+// the device's context): remembered per (kernel, device)
 template <class Kern>
 static int opt_in_smem(Kern kern, size_t smem) {
-  if (smem > 48 * 1024) CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  if (smem <= 48 * 1024) return VPFP_OK;
+  int dev = 0;
+  CUDA_TRY(cudaGetDevice(&dev));
+  static std::mutex mu;
+  static std::map<std::pair<const void*, int>, size_t> done;
+  std::lock_guard<std::mutex> lk(mu);
+  size_t& have = done[{(const void*)kern, dev}];
+  if (have < smem) {
+    CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    have = smem;
+  }
   return VPFP_OK;
 }
 
@@ -181,23 +203,18 @@ static int launch_pass13(const fast::FastArgs& fa, cudaStream_t st) {
   return VPFP_OK;
 }
 
-static int g_pass2_prefetch = 2;   // pass2_kernel PFM (advect_fast.cuh): 0 direct loads, 2 prefetch into the exchange buffer
-
-template <int L, int MODE, int PFM, bool EX>
+// pass 2 prefetches its next tile with cp.async into the exchange buffer (PFM 2, advect_fast.cuh); a CTA walks
+// 8 consecutive group-pair tiles (measured: 4 and 16 are slower)
+template <int L, int MODE, bool EX>
 static int launch_pass2_pf(const fast::FastArgs& fa, cudaStream_t st) {
+  constexpr int PFM = 2;
   constexpr int CB = (L == 128) ? 8 : (L == 64 ? 16 : 32);
   constexpr int threads = CB * 2 * fast::Geo<L>::TPC;
   const size_t smem = fast::pass2_smem<L, CB>(MODE, PFM);
-  static bool configured = false;
-  if (!configured) {
-    int rc = opt_in_smem(fast::pass2_kernel<L, MODE, CB, PFM, EX>, smem);
-    if (rc) return rc;
-    configured = true;
-  }
+  int rc = opt_in_smem(fast::pass2_kernel<L, MODE, CB, PFM, EX>, smem);
+  if (rc) return rc;
   const int T1 = fa.N1 / 2;
-  static int chunk_env = -1;               // VPFP_PASS2_CHUNK: group-pair tiles per CTA (A/B; default 8)
-  if (chunk_env < 0) { const char* e = getenv("VPFP_PASS2_CHUNK"); chunk_env = (e && atoi(e) > 0) ? atoi(e) : 8; }
-  const int t1_chunk = chunk_env;
+  const int t1_chunk = 8;
   const int nchunks = (T1 + t1_chunk - 1) / t1_chunk;
   const long grid = (long)(MODE == ADV_COLS ? fa.nsim : 1) * ((fa.seq_cnt + CB - 1) / CB) * nchunks;
   if (grid > 2147483647L) return fail(VPFP_ERR_UNSUPPORTED, "grid too large");
@@ -211,15 +228,7 @@ static int launch_pass2_pf(const fast::FastArgs& fa, cudaStream_t st) {
 
 template <int L, int MODE>
 static int launch_pass2(const fast::FastArgs& fa, cudaStream_t st) {
-  static int init = 0;
-  if (!init) {
-    const char* e = getenv("VPFP_PASS2_PREFETCH");      // 0: direct loads, 2 (default): own-slot cp.async prefetch
-    if (e) g_pass2_prefetch = atoi(e);
-    init = 1;
-  }
-  if (g_pass2_prefetch == 0)
-    return fa.exact ? launch_pass2_pf<L, MODE, 0, true>(fa, st) : launch_pass2_pf<L, MODE, 0, false>(fa, st);
-  return fa.exact ? launch_pass2_pf<L, MODE, 2, true>(fa, st) : launch_pass2_pf<L, MODE, 2, false>(fa, st);
+  return fa.exact ? launch_pass2_pf<L, MODE, true>(fa, st) : launch_pass2_pf<L, MODE, false>(fa, st);
 }
 
 template <int MODE>
@@ -248,60 +257,11 @@ static int run_three_passes(const fast::FastArgs& fa, cudaStream_t st) {
   return rc;
 }
 
-// L2-slab execution: the three passes run slab by slab (a slab = a range of packed sequences
-// whose footprint fits the 126 MB L2 several times over), slabs round-robin over a few internal
-// streams, so passes 2 and 3 find their input in L2 and only one read and one write of f reach HBM.
-struct SlabStreams {
-  static const int MAXS = 4;
-  cudaStream_t s[MAXS];
-  cudaEvent_t fork, join[MAXS];
-  bool ready = false;
-};
-static std::map<int, SlabStreams> g_slab_streams;
-static long g_slab_bytes = -1;
-static int g_slab_nstreams = 3;
-
 template <int MODE>
 static int run_fast_mode(fast::FastArgs fa, cudaStream_t st) {
-  if (g_slab_bytes < 0) {
-    const char* e = getenv("VPFP_SLAB_MB");
-    g_slab_bytes = e ? atol(e) * (1L << 20) : 0;
-    const char* n = getenv("VPFP_SLAB_STREAMS");
-    if (n) g_slab_nstreams = atoi(n);
-    if (g_slab_nstreams < 1) g_slab_nstreams = 1;
-    if (g_slab_nstreams > SlabStreams::MAXS) g_slab_nstreams = SlabStreams::MAXS;
-  }
-  const long per_seq = (long)(MODE == ADV_COLS ? fa.nsim : 1) * fa.N * 16;
-  long seqs = g_slab_bytes > 0 ? (g_slab_bytes / per_seq) / 32 * 32 : 0;
-  if (seqs < 32) seqs = (g_slab_bytes > 0) ? 32 : 0;
+  // (slab-by-slab execution of the three passes out of L2 was measured slower and is gone: DESIGN.md section 4)
   fa.seq_off = 0; fa.seq_cnt = fa.nseq;
-  if (seqs == 0 || seqs >= fa.nseq) return run_three_passes<MODE>(fa, st);
-  int dev = 0;
-  CUDA_TRY(cudaGetDevice(&dev));
-  SlabStreams& ss = g_slab_streams[dev];
-  if (!ss.ready) {
-    for (int i = 0; i < SlabStreams::MAXS; ++i) {
-      CUDA_TRY(cudaStreamCreateWithFlags(&ss.s[i], cudaStreamNonBlocking));
-      CUDA_TRY(cudaEventCreateWithFlags(&ss.join[i], cudaEventDisableTiming));
-    }
-    CUDA_TRY(cudaEventCreateWithFlags(&ss.fork, cudaEventDisableTiming));
-    ss.ready = true;
-  }
-  const int ns = g_slab_nstreams;
-  CUDA_TRY(cudaEventRecord(ss.fork, st));
-  for (int i = 0; i < ns; ++i) CUDA_TRY(cudaStreamWaitEvent(ss.s[i], ss.fork, 0));
-  int k = 0;
-  for (long off = 0; off < fa.nseq; off += seqs, ++k) {
-    fa.seq_off = (int)off;
-    fa.seq_cnt = (int)((off + seqs <= fa.nseq) ? seqs : fa.nseq - off);
-    int rc = run_three_passes<MODE>(fa, ss.s[k % ns]);
-    if (rc) return rc;
-  }
-  for (int i = 0; i < ns; ++i) {
-    CUDA_TRY(cudaEventRecord(ss.join[i], ss.s[i]));
-    CUDA_TRY(cudaStreamWaitEvent(st, ss.join[i], 0));
-  }
-  return VPFP_OK;
+  return run_three_passes<MODE>(fa, st);
 }
 
 static bool fast_eligible(const AdvectProg& a, const AdvectPlan& pl) {
@@ -381,8 +341,8 @@ static int run_advect(AdvectProg a, cudaStream_t st, int flags = VPFP_PHASE_EXAC
     if (fa.dens_partial) {
       const long n = (long)a.nsim * a.N;
       {
-        ProfScope ps("vdfdx.density_reduce", st);
         const int groups = (dens_tiles >= 64 && dens_tiles % 8 == 0) ? 8 : 1;
+        ProfScope ps("vdfdx.density_reduce", st, groups > 1 ? 2 : 1);
         const unsigned gx = (unsigned)((n + 255) / 256);
         if (groups > 1) {
           fast::dens_reduce_kernel<<<dim3(gx, groups), 256, 0, st>>>(fa.dens_partial, dens_tiles / groups, 1, n, nullptr);
@@ -479,11 +439,9 @@ static int get_logtab(int n, const double2** out) {
 template <int M, int T>
 static int launch_fp_fast(const fpfast::Args& a, cudaStream_t st) {
   const size_t smem = fpfast::smem_bytes<M, T>();
-  static bool configured = false;
-  if (!configured) {
-    if (smem > 48 * 1024)
-      CUDA_TRY(cudaFuncSetAttribute(fpfast::fp_kernel<M, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured = true;
+  {
+    int rc = opt_in_smem(fpfast::fp_kernel<M, T>, smem);
+    if (rc) return rc;
   }
   int per_sm = (int)((227 * 1024) / smem);
   if (per_sm > 2048 / T) per_sm = 2048 / T;
@@ -498,15 +456,8 @@ static int launch_fp_fast(const fpfast::Args& a, cudaStream_t st) {
   return VPFP_OK;
 }
 
-// register-resident Fokker-Planck kernel (fp_reg.cuh): nv = 32 T, next row prefetched with cp.async.
-// VPFP_NO_FP_REG=1 keeps the shared-memory kernel of fp_fast.cuh (A/B measurements).
-static int g_fp_reg_on = -1;
+// register-resident Fokker-Planck kernel (fp_reg.cuh): nv = 32 T, next row prefetched with cp.async
 static bool fp_reg_eligible(const fpfast::Args& a) {
-  if (g_fp_reg_on < 0) {
-    const char* e = getenv("VPFP_NO_FP_REG");
-    g_fp_reg_on = (e && atoi(e)) ? 0 : 1;
-  }
-  if (!g_fp_reg_on) return false;
   if (a.nv != 4096 && a.nv != 8192 && a.nv != 16384) return false;
   if ((a.ld_in & 1) || (a.ld_out & 1)) return false;                      // 16-byte row alignment
   return (((uintptr_t)a.fin | (uintptr_t)a.fout) & 15) == 0;
@@ -515,10 +466,9 @@ static bool fp_reg_eligible(const fpfast::Args& a) {
 template <int M, int T, int OP>
 static int launch_fp_reg_op(const fpfast::Args& a, cudaStream_t st) {
   const size_t smem = fpreg::Geo<M, T>::SMEM;
-  static bool configured = false;
-  if (!configured) {
-    CUDA_TRY(cudaFuncSetAttribute(fpreg::fp_reg_kernel<M, T, OP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured = true;
+  {
+    int rc = opt_in_smem(fpreg::fp_reg_kernel<M, T, OP>, smem);
+    if (rc) return rc;
   }
   int per_sm = (int)((227 * 1024) / (smem + 1024));
   if (per_sm > 512 / T) per_sm = 512 / T;
@@ -542,21 +492,9 @@ static int launch_fp_reg(const fpfast::Args& a, cudaStream_t st) {
 // C ABI
 // ------------------------------------------------------------------------------------------
 // ---- single-pass row kernel (rowfft.cuh): e df/dv with one HBM read and one write of f
-#ifndef VPFP_ROWFFT2_DEFAULT
-#define VPFP_ROWFFT2_DEFAULT 0      // rowfft2.cuh is opt-in until it is measured faster on the GPU
-#endif
-#ifndef VPFP_ROWFFT2_HINTS_DEFAULT
-#define VPFP_ROWFFT2_HINTS_DEFAULT 0
-#endif
-static int g_rowfft_on = -1;   // VPFP_NO_ROWFFT=1 keeps the three-pass kernels (A/B measurements)
-
 static bool rowfft_eligible(const double* f_in, long ld_in, const double* f_out, long ld_out, int rows, int nv,
                             int flags) {
-  if (g_rowfft_on < 0) {
-    const char* e = getenv("VPFP_NO_ROWFFT");
-    g_rowfft_on = (e && atoi(e)) ? 0 : 1;
-  }
-  if (!g_rowfft_on || !(flags & VPFP_PHASE_TABLE) || (flags & (VPFP_FORCE_GENERIC | VPFP_FORCE_THREE_PASS))) return false;
+  if (!(flags & VPFP_PHASE_TABLE) || (flags & (VPFP_FORCE_GENERIC | VPFP_FORCE_THREE_PASS))) return false;
   if (nv != 4096 && nv != 8192 && nv != 16384) return false;
   if ((long)rows * nv < (1L << 22)) return false;
   if ((ld_in & 1) || (ld_out & 1) || ((uintptr_t)f_in & 15) || ((uintptr_t)f_out & 15)) return false;
@@ -593,104 +531,19 @@ static int launch_rowfft(const rowfft::Args& ra, cudaStream_t st) {
   return VPFP_OK;
 }
 
-// 512-thread radix 16x8x8x8 variant for nv = 16384 (rowfft4.cuh)
-static int launch_rowfft4(const rowfft::Args& ra, cudaStream_t st) {
-  rowfft4::Prog prog;
-  prog.a = ra;
-  int dev = 0;
-  CUDA_TRY(cudaGetDevice(&dev));
-  static std::map<int, int> grid_for;
-  {
-    static std::mutex mu;
-    std::lock_guard<std::mutex> lk(mu);
-    if (!grid_for.count(dev)) {
-      CUDA_TRY(cudaFuncSetAttribute(rowfft4::rowfft4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                    (int)rowfft4::Prog::SMEM_BYTES));
-      int nsm = 0;
-      CUDA_TRY(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev));
-      grid_for[dev] = nsm;
-    }
-  }
-  int grid = grid_for[dev];
-  if (grid > ra.nrows) grid = ra.nrows;
-  {
-    ProfScope ps("edfdv.row", st);
-    rowfft4::rowfft4_kernel<<<grid, rowfft4::Prog::T, rowfft4::Prog::SMEM_BYTES, st>>>(prog);
-  }
-  CUDA_TRY(cudaGetLastError());
-  return VPFP_OK;
-}
-
-// 128-thread two-CTAs-per-SM variant for nv = 16384 (rowfft2.cuh)
-template <class P>
-static int launch_rowfft2_t(const rowfft::Args& ra, cudaStream_t st) {
-  P prog;
-  prog.a = ra;
-  int dev = 0;
-  CUDA_TRY(cudaGetDevice(&dev));
-  static std::map<int, int> grid_for;   // per device: SMs x resident CTAs
-  {
-    static std::mutex mu;
-    std::lock_guard<std::mutex> lk(mu);
-    if (!grid_for.count(dev)) {
-      CUDA_TRY(cudaFuncSetAttribute(rowfft2::rowfft2_kernel<P>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                    (int)P::SMEM_BYTES));
-      CUDA_TRY(cudaFuncSetAttribute(rowfft2::rowfft2_kernel<P>, cudaFuncAttributePreferredSharedMemoryCarveout,
-                                    cudaSharedmemCarveoutMaxShared));
-      int nsm = 0, occ = 0;
-      CUDA_TRY(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev));
-      CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, rowfft2::rowfft2_kernel<P>, P::T, P::SMEM_BYTES));
-      if (occ < 1) return fail(VPFP_ERR_CUDA, "rowfft2 kernel does not fit an SM");
-      grid_for[dev] = nsm * occ;
-    }
-  }
-  int grid = grid_for[dev];
-  if (grid > ra.nrows) grid = ra.nrows;
-  {
-    ProfScope ps("edfdv.row2", st);
-    rowfft2::rowfft2_kernel<P><<<grid, P::T, P::SMEM_BYTES, st>>>(prog);
-  }
-  CUDA_TRY(cudaGetLastError());
-  return VPFP_OK;
-}
-
-static int launch_rowfft2(const rowfft::Args& ra, cudaStream_t st) {
-  static int hints = -1;                 // VPFP_ROWFFT2_HINTS=0..3: cache hints of rowfft2.cuh (A/B)
-  if (hints < 0) { const char* e = getenv("VPFP_ROWFFT2_HINTS"); hints = e ? (atoi(e) & 3) : VPFP_ROWFFT2_HINTS_DEFAULT; }
-  switch (hints) {
-    case 1: return launch_rowfft2_t<rowfft2::ProgT<1>>(ra, st);
-    case 2: return launch_rowfft2_t<rowfft2::ProgT<2>>(ra, st);
-    case 3: return launch_rowfft2_t<rowfft2::ProgT<3>>(ra, st);
-    default: return launch_rowfft2_t<rowfft2::ProgT<0>>(ra, st);
-  }
-}
-
 static int run_rowfft(const double* f_in, long ld_in, double* f_out, long ld_out, const double* e, const double* kv,
                       double dt, int rows, int nv, const ScatterReq* scat, cudaStream_t st, int flags = 0) {
   rowfft::Args ra;
   memset(&ra, 0, sizeof(ra));
   ra.fin = f_in; ra.ld_in = ld_in; ra.fout = f_out; ra.ld_out = ld_out; ra.kvec = kv; ra.cvec = e; ra.dt = dt;
   ra.nrows = rows;
-  {
-    static int pf = -1;                  // VPFP_ROWFFT_L2PF=n: rows of L2 prefetch ahead (default 0 = off: the cp.async of rowfft.cuh already runs a phase ahead)
-    if (pf < 0) { const char* e = getenv("VPFP_ROWFFT_L2PF"); pf = e ? atoi(e) : 0; }
-    ra.l2_prefetch = pf;
-  }
+  ra.l2_prefetch = 0;
   int rc = get_twiddles(nv, &ra.twN);
   if (rc) return rc;
   if (scat && scat->mode) {
     ra.peer_mode = scat->mode; ra.nparts = scat->nparts; ra.my_rank = scat->my_rank;
     ra.lpart = ilog2(nv / scat->nparts);
     for (int i = 0; i < scat->nparts; ++i) ra.peer[i] = scat->peer[i];
-  }
-  if (nv == 16384) {
-    static int v4 = -1;                  // VPFP_ROWFFT4=1 selects the 512-thread radix 16x8x8x8 kernel (measured slower: shared-memory bound)
-    if (v4 < 0) { const char* e = getenv("VPFP_ROWFFT4"); v4 = e ? atoi(e) : 0; }
-    if (v4) return launch_rowfft4(ra, st);
-    static int v2 = -1;                  // library default of the two-CTAs-per-SM kernel (rowfft2.cuh): VPFP_ROWFFT2=0/1
-    if (v2 < 0) { const char* e = getenv("VPFP_ROWFFT2"); v2 = e ? atoi(e) : VPFP_ROWFFT2_DEFAULT; }
-    const bool two = (flags & VPFP_ROW_TWO_CTA) || (v2 && !(flags & VPFP_ROW_ONE_CTA));
-    if (two && !ra.peer_mode) return launch_rowfft2(ra, st);
   }
   if (ra.peer_mode) {
     switch (nv) {
@@ -723,9 +576,21 @@ int vpfp_shutdown(void) {
       if (g_logtab.count({kv.first, n})) { cudaFree(g_logtab[{kv.first, n}]); g_logtab.erase({kv.first, n}); }
     for (int i = 0; i < 4; ++i)
       if (kv.second.scratch[i]) cudaFree(kv.second.scratch[i]);
+    for (void* r : kv.second.retired) cudaFree(r);
   }
   g_cache.clear();
   return VPFP_OK;
+}
+
+long vpfp_launch_count(int reset) {
+  const long n = g_launches.load();
+  if (reset) g_launches = 0;
+  return n;
+}
+
+unsigned long vpfp_scratch_generation(void) {
+  std::lock_guard<std::mutex> lk(g_cache_mu);
+  return g_scratch_generation;
 }
 
 int vpfp_profile_enable(int on) {
@@ -1008,16 +873,8 @@ int vpfp_xmodes_partial(const double* f, long ld, double* out, int nmodes, int b
   XmodesProg p;
   p.f = f; p.ld = ld; p.nmodes = nmodes; p.batch = batch; p.nx = nx; p.ncols = ncols;
   p.x_offset = x_offset; p.nx_total = nx_total;
-  // A/B knobs (defaults = the measured configuration): VPFP_XMODES_THREADS (threads per CTA: a CTA reads
-  // threads x 16 contiguous bytes of every row), VPFP_XMODES_XCH (upper limit of the number of row chunks)
-  static int env_threads = -1, env_xch = -1;
-  if (env_threads < 0) {
-    const char* e1 = getenv("VPFP_XMODES_THREADS");
-    const char* e2 = getenv("VPFP_XMODES_XCH");
-    env_threads = (e1 && (atoi(e1) == 64 || atoi(e1) == 256 || atoi(e1) == 512)) ? atoi(e1) : 128;
-    env_xch = (e2 && atoi(e2) >= 1 && atoi(e2) <= 256) ? atoi(e2) : 32;
-  }
-  const int threads = env_threads;
+  // measured configuration: a CTA of 128 threads reads 128 x 16 contiguous bytes of every row; at most 32 row chunks
+  const int threads = 128, env_xch = 32;
   p.cblocks = (ncols + threads - 1) / threads;
   int xch = nx / 128;
   if (xch < 1) xch = 1;

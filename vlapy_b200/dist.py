@@ -17,6 +17,8 @@ import numpy as np
 import torch
 import torch.distributed as dist
 
+from ._util import attach_density, cached_density
+
 
 class Sharded:
     """A shard of f together with its layout: 'x' = rows [r*nx/P, (r+1)*nx/P) x all v,
@@ -170,11 +172,11 @@ class DeviceBackend:
         n = fv.new_empty(fv.shape[0])            # partial density over the local columns, fused epilogue
         out = self.ops.vdfdx_exp(fv, self.kx, self.v_loc, dt, flags=self.flags_x, density_out=n, dv=self.dv,
                                  edge_flags=self.edge)
-        out._vpfp_density = n
+        attach_density(out, n)
         return out
 
     def density_partial(self, fv):
-        n = getattr(fv, "_vpfp_density", None)
+        n = cached_density(fv)
         if n is not None:
             return n
         return self.ops.moments(fv, self.v_loc, self.dv, nmom=1, edge_flags=self.edge)[0].contiguous()
@@ -200,6 +202,11 @@ class DeviceBackend:
 
     def zeros(self, shape):
         return torch.zeros(shape, dtype=torch.float64, device=self.x.device)
+
+    def upload(self, a):
+        """host array (pinned or not) -> device tensor on this rank's GPU"""
+        t = a if isinstance(a, torch.Tensor) else torch.from_numpy(a)
+        return t.to(self.x.device, non_blocking=True)
 
 
 def make_sharded_operators(topo, backend):
@@ -262,7 +269,6 @@ def get_sharded_timestep(all_params, stuff_for_time_loop, topo, backend=None):
     collide = all_params["nu"] > 0.0
     if all_params["nu"] < 0.0:
         raise NotImplementedError
-    nmodes = 2
 
     def timestep(state, t, de=None, store=None):
         e, f = vp_step(e=state["e"], f=state["f"], t=t)
@@ -289,7 +295,7 @@ def get_sharded_timestep(all_params, stuff_for_time_loop, topo, backend=None):
             store["series_sum"][i, 3] = (el * el).sum()
             store["series_sum"][i, 4] = (de[sl] * de[sl]).sum() if de is not None else 0.0
             store["series_sum"][i, 5:7] = mom[6:8].sum(dim=1)
-            store["modes_partial"][i] = backend.xmodes_partial(f.t, nmodes)
+            store["modes_partial"][i] = backend.xmodes_partial(f.t, store["modes_partial"].shape[1])
             store["i"] = i + 1
         return {"e": e, "f": f}
 
@@ -297,7 +303,7 @@ def get_sharded_timestep(all_params, stuff_for_time_loop, topo, backend=None):
     return timestep
 
 
-def make_store(topo, backend, nsteps):
+def make_store(topo, backend, nsteps, nmodes=2):
     return {
         "i": 0,
         "moments": backend.zeros((8, topo.nxl)),
@@ -305,7 +311,7 @@ def make_store(topo, backend, nsteps):
         "fields_driver": backend.zeros((nsteps, topo.nxl)),
         "fields_mom": backend.zeros((nsteps, 6, topo.nxl)),
         "series_sum": backend.zeros((nsteps, 7)),
-        "modes_partial": backend.zeros((nsteps, 2, topo.nv, 2)),
+        "modes_partial": backend.zeros((nsteps, nmodes, topo.nv, 2)),
     }
 
 
@@ -346,7 +352,7 @@ def bench_sharded(cfg, params, rules, K, W, dev, barrier):
     barrier()
     sampler = _bench.ClockSampler(dev.index)
     sampler.start()
-    ops.launch_count = 0
+    ops.launch_count(reset=True)
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
     for i in range(W, W + K):
@@ -354,7 +360,7 @@ def bench_sharded(cfg, params, rules, K, W, dev, barrier):
     ev1.record()
     barrier()
     ms = ev0.elapsed_time(ev1)
-    launches = ops.launch_count
+    launches = ops.launch_count()
     clocks = sampler.summary()
     series, modes = finish_store(topo, store)
     mean_n = float(series[total - 1, 0])

@@ -9,7 +9,7 @@ import numpy as np
 import torch
 
 from . import ops
-from ._util import const, device
+from ._util import cached_density, const, device
 from .core import vlasov, vlasov_poisson
 
 
@@ -51,11 +51,10 @@ def get_ensemble_timestep(all_params, stuff):
             ops._lib.check(ops._lib.lib().vpfp_driver_batch(
                 x_d.data_ptr(), float(t), None, None, 0, pulses_d.data_ptr(), npulse, out.data_ptr(), nx, batch,
                 ops._stream()))
-        ops._count(1)
         return out
 
     def field_solve(driver_field, f):
-        n = getattr(f, "_vpfp_density", None)
+        n = cached_density(f)
         if n is None:
             n = ops.moments(f, v_d, dv, nmom=1)[0].reshape(batch, nx)
         return ops.poisson(n.contiguous(), ook_d, driver_field)
@@ -82,7 +81,6 @@ def get_ensemble_timestep(all_params, stuff):
         de = driver_function(t)
         ops._lib.check(ops._lib.lib().vpfp_series_batch(mom.data_ptr(), mom.stride(0), e.data_ptr(), de.data_ptr(),
                                                          ser.data_ptr(), nx, batch, ops._stream()))
-        ops._count(1)
         return {"e": e, "f": f, "moments": mom, "series": ser}
 
     return timestep

@@ -12,15 +12,17 @@ from . import _lib
 
 FP_OPS = {"lb": 0, "dg": 1}
 PHASE_EXACT, PHASE_TABLE, FORCE_GENERIC, FORCE_THREE_PASS = 0, 1, 2, 4
-ROW_TWO_CTA, ROW_ONE_CTA = 8, 16     # e df/dv at nv = 16384: rowfft2.cuh / rowfft.cuh (neither: library default)
-
-# number of kernels of this library launched since the last reset (bench.py's gpu_launches claim)
-launch_count = 0
 
 
-def _count(n):
-    global launch_count
-    launch_count += n
+def launch_count(reset=False):
+    """kernels this library has enqueued since the last reset, counted at the launch sites inside the
+    library (vpfp_launch_count); kernels replayed by a CUDA graph are counted once, at capture"""
+    return int(_lib.lib().vpfp_launch_count(1 if reset else 0))
+
+
+def scratch_generation():
+    """number of reallocations of the library's reduction scratch so far (vpfp_scratch_generation)"""
+    return int(_lib.lib().vpfp_scratch_generation())
 
 
 def _stream():
@@ -55,12 +57,6 @@ def _is_pow2(n):
     return n > 0 and (n & (n - 1)) == 0
 
 
-def adv_launches(mode, n, cells=1 << 30):
-    """kernels per advection call: one when the sequence fits a CTA (short sequences, or small
-    problems of up to 2048 points), else the three passes"""
-    return 1 if (n <= 128 or (cells < (1 << 22) and n <= 2048)) else 3
-
-
 def edfdv_exp(f, e, kv, dt, out=None, flags=PHASE_EXACT):
     """vlapy/core/vlasov.py:123-138 on device. f: (..., nx, nv); e: (..., nx); kv: (nv)."""
     rows, ld = _chk_f(f)
@@ -71,7 +67,6 @@ def edfdv_exp(f, e, kv, dt, out=None, flags=PHASE_EXACT):
     _vec(e, rows, "e"); _vec(kv, nv, "kv")
     _lib.check(_lib.lib().vpfp_edfdv_exp(f.data_ptr(), ld, out.data_ptr(), ldo, e.data_ptr(), kv.data_ptr(),
                                          float(dt), rows, nv, flags, _stream()))
-    _count(1 if rowfft_serves(rows, nv, flags) else adv_launches("rows", nv, rows * nv))
     return out
 
 
@@ -96,14 +91,9 @@ def vdfdx_exp(f, kx, v, dt, out=None, flags=PHASE_EXACT, density_out=None, dv=No
         _lib.check(_lib.lib().vpfp_vdfdx_exp_density(f.data_ptr(), ld, out.data_ptr(), ldo, kx.data_ptr(),
                                                      v.data_ptr(), float(dt), batch, nx, ncols, flags,
                                                      density_out.data_ptr(), float(dv), edge_flags, _stream()))
-        # + the reduction of the per-tile density partials (two stages when there are >= 64 column tiles;
-        # the tile width mirrors launch_pass13 only approximately -- this is a count, not a control path)
-        tiles = -(-(ncols // 2) // (16 if nx >= 8192 else 32 if nx >= 2048 else 64))
-        _count(adv_launches("cols", nx, batch * nx * ncols) + (2 if tiles >= 64 and tiles % 8 == 0 else 1))
         return out
     _lib.check(_lib.lib().vpfp_vdfdx_exp(f.data_ptr(), ld, out.data_ptr(), ldo, kx.data_ptr(), v.data_ptr(),
                                          float(dt), batch, nx, ncols, flags, _stream()))
-    _count(adv_launches("cols", nx, batch * nx * ncols))
     return out
 
 
@@ -161,7 +151,6 @@ def edfdv_exp_scatter(f, e, kv, dt, scratch, peer_ptrs, my_rank, flags=PHASE_EXA
     _lib.check(_lib.lib().vpfp_edfdv_exp_scatter(f.data_ptr(), ld, scratch.data_ptr(), lds, e.data_ptr(),
                                                  kv.data_ptr(), float(dt), rows, nv, flags, _ptr_array(peer_ptrs),
                                                  len(peer_ptrs), int(my_rank), _stream()))
-    _count(3)
 
 
 def vdfdx_exp_scatter(f, kx, v, dt, scratch, peer_ptrs, my_rank, flags=PHASE_EXACT, density_out=None, dv=0.0,
@@ -180,7 +169,6 @@ def vdfdx_exp_scatter(f, kx, v, dt, scratch, peer_ptrs, my_rank, flags=PHASE_EXA
                                                  density_out.data_ptr() if density_out is not None else None,
                                                  float(dv), edge_flags, _ptr_array(peer_ptrs), len(peer_ptrs),
                                                  int(my_rank), _stream()))
-    _count(3 + (1 if density_out is not None else 0))
 
 
 def edfdv_cd2(f, e, dt, dv, out=None):
@@ -193,7 +181,6 @@ def edfdv_cd2(f, e, dt, dv, out=None):
     _vec(e, rows, "e")
     _lib.check(_lib.lib().vpfp_edfdv_cd2(f.data_ptr(), ld, out.data_ptr(), ldo, e.data_ptr(), float(dt),
                                          float(dv), rows, nv, _stream()))
-    _count(1)
     return out
 
 
@@ -206,7 +193,6 @@ def moments(f, v, dv, nmom=8, out=None, edge_flags=3):
         out = torch.empty((nmom, rows), dtype=f.dtype, device=f.device)
     _lib.check(_lib.lib().vpfp_moments(f.data_ptr(), ld, v.data_ptr(), float(dv), out.data_ptr(),
                                        out.stride(0), nmom, rows, ncols, edge_flags, _stream()))
-    _count(1)
     return out
 
 
@@ -222,7 +208,6 @@ def poisson(n, one_over_kx, driver=None, out=None):
     _lib.check(_lib.lib().vpfp_poisson(n.data_ptr(), one_over_kx.data_ptr(),
                                        driver.data_ptr() if driver is not None else None,
                                        out.data_ptr(), batch, nx, _stream()))
-    _count(adv_launches("rows", nx) if _is_pow2(nx) else 1)
     return out
 
 
@@ -255,11 +240,9 @@ def fp_step(f, v, nu, dt, dv, op="lb", out=None, moments_out=None, vgrid=None):
         _lib.check(_lib.lib().vpfp_fp_step_linspace(f.data_ptr(), ld, out.data_ptr(), ldo, vgrid[0], vgrid[1],
                                                     vgrid[2], float(nu), float(dt), float(dv), FP_OPS[op], mp, mld,
                                                     rows, nv, _stream()))
-        _count(1)
         return out
     _lib.check(_lib.lib().vpfp_fp_step(f.data_ptr(), ld, out.data_ptr(), ldo, v.data_ptr(), float(nu), float(dt),
                                        float(dv), FP_OPS[op], mp, mld, rows, nv, _stream()))
-    _count(1)
     return out
 
 
@@ -273,7 +256,6 @@ def xmodes(f, nmodes=2, out=None, x_offset=0, nx_total=None):
         out = torch.empty((batch, nmodes, ncols, 2), dtype=f.dtype, device=f.device)
     _lib.check(_lib.lib().vpfp_xmodes_partial(f.data_ptr(), ld, out.data_ptr(), nmodes, batch, nx, ncols,
                                               int(x_offset), int(nx_total or nx), _stream()))
-    _count(2)
     return torch.view_as_complex(out)
 
 
@@ -284,7 +266,6 @@ def driver(x, t, pulses, out=None):
         out = torch.empty_like(x)
     _lib.check(_lib.lib().vpfp_driver(x.data_ptr(), float(t), pulses.ctypes.data_as(ctypes.c_void_p),
                                       pulses.shape[0], out.data_ptr(), x.numel(), _stream()))
-    _count(1)
     return out
 
 
@@ -312,7 +293,6 @@ def driver_dev(x, t, pulses, out=None):
     _lib.check(_lib.lib().vpfp_driver_dev(x.data_ptr(), t.base.data_ptr(), incs.ctypes.data_as(ctypes.c_void_p),
                                           incs.size, pulses.ctypes.data_as(ctypes.c_void_p), pulses.shape[0],
                                           out.data_ptr(), x.numel(), _stream()))
-    _count(1)
     return out
 
 
@@ -323,7 +303,6 @@ def series(mom, e, de, out=None):
     _lib.check(_lib.lib().vpfp_series(mom.data_ptr(), mom.stride(0), e.data_ptr(),
                                       de.data_ptr() if de is not None else None, out.data_ptr(),
                                       e.numel(), _stream()))
-    _count(1)
     return out
 
 

@@ -21,7 +21,11 @@ def get_sim_config_and_inner_loop_step(all_params, stuff_for_time_loop, nt_in_lo
     if all_params["backend"]["core"] != BACKEND:
         raise NotImplementedError(
             "The backend <" + all_params["backend"]["core"] + "> has not yet been implemented")
-    do_inner_loop = get_inner_loop_stepper(all_params, stuff_for_time_loop, nt_in_loop)
+    if sharded_world(all_params) > 1:
+        # launched under torchrun (one process per GPU): the same call returns the x/v-sharded inner loop
+        do_inner_loop = get_sharded_inner_loop_stepper(all_params, stuff_for_time_loop, nt_in_loop)
+    else:
+        do_inner_loop = get_inner_loop_stepper(all_params, stuff_for_time_loop, nt_in_loop)
     sim_config = get_arrays_for_inner_loop(stuff_for_time_loop, nt_in_loop, store_f_rules, this_np=np)
     return sim_config, do_inner_loop
 
@@ -84,13 +88,14 @@ def _device_storage(temp_storage, nt, nx, nv, dev, pinned_sets=1):
     p = temp_storage.get("_pin")
     if p is None or p["nt"] != nt or len(p["sets"]) != pinned_sets:
         sf = d["stored_f"]
+        pin_it = dev.type == "cuda"
         p = {"nt": nt, "next": 0, "sets": [{
-            "fields": torch.empty(d["fields"].shape, dtype=torch.float64, pin_memory=True),
-            "series_rows": torch.empty((nt, 7), dtype=torch.float64, pin_memory=True),
+            "fields": torch.empty(d["fields"].shape, dtype=torch.float64, pin_memory=pin_it),
+            "series_rows": torch.empty((nt, 7), dtype=torch.float64, pin_memory=pin_it),
             "stored_f": torch.empty(sf.shape, dtype=torch.complex64 if sf.is_complex() else torch.float64,
-                                    pin_memory=True),
-            "e": torch.empty(nx, dtype=torch.float64, pin_memory=True),
-            "f": torch.empty((nx, nv), dtype=torch.float64, pin_memory=True),
+                                    pin_memory=pin_it),
+            "e": torch.empty(nx, dtype=torch.float64, pin_memory=pin_it),
+            "f": torch.empty((nx, nv), dtype=torch.float64, pin_memory=pin_it),
         } for _ in range(pinned_sets)]}
         temp_storage["_pin"] = p
     pin = p["sets"][p["next"]]
@@ -154,6 +159,9 @@ class _GraphStep:
             self._body()
         self.e.copy_(e0)
         self.f.copy_(f0)
+        # the library's reduction scratch the graph was captured with (outgrown blocks stay allocated, so the graph
+        # remains valid; a changed generation only means that a re-capture would use the current block)
+        self.scratch_generation = ops.scratch_generation()
 
 
 GRAPH_MAX_CELLS = 1 << 22      # above this a step is no longer launch bound (and the extra copy of f would cost)
@@ -181,6 +189,8 @@ def get_inner_loop_stepper(all_params, stuff_for_time_loop, steps_in_loop):
 
     def run_graph(time_array, drv, d, nx, nv):
         gs = graph_state.get("gs")
+        if gs is not None and gs.scratch_generation != ops.scratch_generation():
+            gs = None                                   # a larger problem ran in between: capture again
         if gs is None:
             gs = _GraphStep(all_params, stuff_for_time_loop, nx, nv, tuple(d["stored_f"].shape[1:]),
                             d["stored_f"].is_complex(), drv.device)
@@ -236,7 +246,8 @@ def get_inner_loop_stepper(all_params, stuff_for_time_loop, steps_in_loop):
         pin["stored_f"].copy_(sf.to(torch.complex64) if sf.is_complex() else sf, non_blocking=True)
         pin["e"].copy_(d["e"], non_blocking=True)
         pin["f"].copy_(d["f"], non_blocking=True)
-        torch.cuda.current_stream().synchronize()
+        if dev.type == "cuda":
+            torch.cuda.current_stream().synchronize()
         temp_storage["time_batch"] = np.asarray(time_array)
         temp_storage["driver_array_batch"] = np.asarray(driver_array)
         fields = pin["fields"].numpy()
@@ -253,6 +264,127 @@ def get_inner_loop_stepper(all_params, stuff_for_time_loop, steps_in_loop):
 
     return inner_loop
 
+
+
+def sharded_world(all_params):
+    """Number of ranks the inner loop is sharded over: the size of the default process group when
+    torch.distributed is initialised (torchrun, one process per GPU) and ``backend.sharded`` is not False."""
+    import torch.distributed as tdist
+    if all_params["backend"].get("sharded", "auto") is False:
+        return 1
+    if not (tdist.is_available() and tdist.is_initialized()):
+        return 1
+    return tdist.get_world_size()
+
+
+def get_sharded_inner_loop_stepper(all_params, stuff_for_time_loop, steps_in_loop):
+    """vlapy/outer_loop.py:248-281 for one simulation sharded over the ranks of the default process group
+    (rows x-sharded, v df/dx v-sharded, vlapy_b200/dist.py).  SPMD: every rank makes the same call
+    with the same arguments (the reference's setup is deterministic, so every rank holds the same host arrays);
+    a rank uploads only its x-slab of ``temp_storage["f"]``.  On return every rank holds the same host
+    dictionary as the single-GPU inner loop returns -- time_batch, driver_array_batch, series, fields,
+    stored_f, e (the per-loop buffers are all-gathered / all-reduced on the device once per loop, at the
+    storage cadence of vlapy/manager.py:138-150) -- except ``f``:
+
+      backend.gather = "rank0" (default): rank 0 receives the full f (nx, nv), as the storage layer of the
+                       reference expects; the other ranks receive their x-slab;
+      backend.gather = "slab":  every rank receives its x-slab only (parallel downloads, one PCIe link each).
+
+    ``temp_storage["f_slab"] = (x_begin, x_end)`` says which rows ``f`` holds.  The device-resident slab is
+    kept under the private key for the next call.  ``backend.shard_backend`` (tests): a factory
+    (topology, stuff, fp_type) -> per-shard operators replacing the CUDA kernels (dist.DeviceBackend)."""
+    import torch.distributed as tdist
+    from . import dist as vd
+    if all_params["backend"]["core"] != BACKEND:
+        raise NotImplementedError(
+            "The backend: <" + all_params["backend"]["core"] + "> has not yet been implemented")
+    nx, nv = int(stuff_for_time_loop["nx"]), int(stuff_for_time_loop["nv"])
+    topo = vd.Topology(nx, nv)
+    factory = all_params["backend"].get("shard_backend")
+    fp_type = all_params["fokker-planck"]["type"]
+    backend = factory(topo, stuff_for_time_loop, fp_type) if factory else vd.DeviceBackend(topo, stuff_for_time_loop, fp_type)
+    one_step = vd.get_sharded_timestep(all_params, stuff_for_time_loop, topo, backend=backend)
+    gather = all_params["backend"].get("gather", "rank0")
+    if gather not in ("rank0", "slab"):
+        raise ValueError("backend.gather must be 'rank0' or 'slab'")
+    nmodes = len(stuff_for_time_loop["rules_to_store_f"])       # the reference's quirk (vlapy/core/step.py:133)
+    if stuff_for_time_loop["rules_to_store_f"]["space"] == "all":
+        raise NotImplementedError("rules_to_store_f space = 'all' has not been implemented for the sharded inner loop")
+    pins = {}
+
+    def pinned(name, shape, dtype=torch.float64):
+        t = pins.get(name)
+        if t is None or tuple(t.shape) != tuple(shape):
+            t = torch.empty(shape, dtype=dtype, pin_memory=torch.cuda.is_available())
+            pins[name] = t
+        return t
+
+    def gather_x(t):
+        """(nt, ..., nxl) slabs -> (nt, ..., nx) on every rank"""
+        parts = [torch.empty_like(t) for _ in range(topo.world)]
+        tdist.all_gather(parts, t.contiguous(), group=topo.group)
+        return torch.cat(parts, dim=-1)
+
+    def inner_loop(time_array, driver_array, temp_storage):
+        nt = steps_in_loop
+        d = temp_storage.get("_dev")
+        if d is None:
+            f_host = np.asarray(temp_storage["f"], dtype=np.float64)
+            if f_host.shape[0] == nx:
+                f_host = f_host[topo.x0: topo.x0 + topo.nxl]
+            elif f_host.shape[0] != topo.nxl:
+                raise ValueError("temp_storage['f'] must be the full grid or this rank's x-slab")
+            d = {"f": vd.Sharded(backend.upload(np.ascontiguousarray(f_host)), "x"),
+                 "e": backend.upload(np.ascontiguousarray(temp_storage["e"], dtype=np.float64))}
+            temp_storage["_dev"] = d
+        drv = backend.upload(np.ascontiguousarray(driver_array, dtype=np.float64))
+        store = vd.make_store(topo, backend, nt, nmodes)
+        state = {"e": d["e"], "f": d["f"]}
+        times = np.asarray(time_array, dtype=np.float64)
+        for it in range(nt):
+            state = one_step(state, float(times[it]), drv[it], store)
+        d["e"], d["f"] = state["e"], vd.Sharded(vd.ops_to_x(state["f"], topo), "x")
+        # storage cadence: per-loop buffers become global on the device, then one download
+        series, modes = vd.finish_store(topo, store)
+        fe = gather_x(store["fields_e"])
+        fd = gather_x(store["fields_driver"])
+        fm = gather_x(store["fields_mom"])
+        fx = d["f"].t
+        if gather == "rank0" and topo.world > 1:
+            parts = [torch.empty_like(fx) for _ in range(topo.world)] if topo.rank == 0 else None
+            tdist.gather(fx.contiguous(), parts, dst=0, group=topo.group)
+            f_dev = torch.cat(parts, dim=0) if topo.rank == 0 else fx
+        else:
+            f_dev = fx
+        outs = {"fe": fe, "fd": fd, "fm": fm, "series": series, "e": d["e"], "f": f_dev,
+                "modes": torch.view_as_real(modes.to(torch.complex64)) if modes.is_complex() else modes}
+        host = {}
+        for k, t in outs.items():
+            h = pinned(k, t.shape, t.dtype)
+            h.copy_(t, non_blocking=True)
+            host[k] = h
+        if torch.cuda.is_available():
+            torch.cuda.current_stream().synchronize()
+        temp_storage["time_batch"] = np.asarray(time_array)
+        temp_storage["driver_array_batch"] = np.asarray(driver_array)
+        temp_storage["fields"]["e"] = host["fe"].numpy()
+        temp_storage["fields"]["driver"] = host["fd"].numpy()
+        fm_h = host["fm"].numpy()
+        for j, k in enumerate(("n", "j", "T", "q", "fv4", "vN")):
+            temp_storage["fields"][k] = fm_h[:, j]
+        rows = host["series"].numpy()
+        for j, k in enumerate(step.SERIES_KEYS):
+            temp_storage["series"][k] = rows[:, j].copy()
+        temp_storage["stored_f"] = torch.view_as_complex(host["modes"]).numpy()
+        temp_storage["e"] = host["e"].numpy()
+        temp_storage["f"] = host["f"].numpy()
+        full = f_dev.shape[0] == nx
+        temp_storage["f_slab"] = (0, nx) if full else (topo.x0, topo.x0 + topo.nxl)
+        post_inner_loop_update(temp_storage, np)
+        return temp_storage
+
+    inner_loop.topology, inner_loop.shard_backend = topo, backend
+    return inner_loop
 
 
 def run_loops(inner_loop, temp_storage, batches, consume):
