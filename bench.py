@@ -268,14 +268,20 @@ class ClockSampler(threading.Thread):
                 "power_w_max": max(pw) if pw else None, "reasons": reasons, "samples": len(self.rows)}
 
 
+# algorithmic bytes per cell and launch: 16 = one fp64 read + one write of f; read-only passes 8
+ALGO_BYTES = {"xmodes": 8.0, "moments": 8.0}
+
+
 def ncu_traffic():
-    """DRAM bytes per launch of each kernel from the committed ncu --set full capture
-    (profiles/ncu_traffic_r01.json, written by tools/ncu_traffic.py); {} when absent."""
-    path = os.path.join(ROOT, "profiles", "ncu_traffic_r01.json")
-    if not os.path.exists(path):
-        return {}, None
-    d = json.load(open(path))
-    return d.get("kernels", {}), d.get("source")
+    """DRAM bytes per launch of each kernel from the latest committed ncu --set full capture
+    (profiles/ncu_traffic_r*.json, written by tools/ncu_traffic.py); {} when absent.  STATIC provenance: it is
+    attached to the kernels of the same name, it is not measured by this run."""
+    for name in ("ncu_traffic_r02.json", "ncu_traffic_r01.json"):
+        path = os.path.join(ROOT, "profiles", name)
+        if os.path.exists(path):
+            d = json.load(open(path))
+            return d.get("kernels", {}), "profiles/%s: %s" % (name, d.get("source"))
+    return {}, None
 
 
 def peaks():
@@ -289,23 +295,23 @@ def peaks():
 # reference arm / cpu baseline: the oracle port on the host cores, bounded sample
 # ---------------------------------------------------------------------------------------------
 
-def cpu_sample_grid(total_steps, budget_s=100.0):
-    """largest sample grid whose (warmup + steps) fits the time budget; ~0.4 us per cell-update
-    per core for the numpy/scipy path."""
+def cpu_sample_grid(workload, total_steps, budget_s=100.0):
+    """(nx, nv) of the grid the CPU arm times: the workload's own grid when (warmup + steps) of it fit the time
+    budget (C1, C2: same configuration as the GPU arm), else the largest square sub-grid of the same physics that
+    does; ~0.4 us per cell-update per core for the numpy/scipy path."""
+    nx, nv, _ = WORKLOADS[workload]
+    if nx * nv * 0.4e-6 * total_steps <= budget_s:
+        return nx, nv
     for n in (4096, 2048, 1024, 512):
         if n * n * 0.4e-6 * total_steps <= budget_s:
-            return n
-    return 512
+            return n, n
+    return 512, 512
 
 
-def run_cpu_steps(workload, n, steps, warmup, workers):
+def run_cpu_steps(workload, snx, snv, steps, warmup, workers):
     import scipy.fft as sfft
     from oracle import vpfp_oracle as O
-    if workload == "c4":
-        cfg = O.landau_config(256, 512)          # one member of the ensemble; n is ignored
-        n = int(np.sqrt(256 * 512))
-    else:
-        cfg = O.landau_config(n, n) if workload == "c1" else O.nlepw_config(n, n)
+    cfg = O.landau_config(snx, snv) if workload in ("c1", "c4") else O.nlepw_config(snx, snv)
     e = 0.01 * np.cos(cfg["k0"] * cfg["x"])
     f = cfg["f0"] * (1.0 + 0.05 * np.sin(cfg["k0"] * cfg["x"]))[:, None]
     kw = dict(integrator="leapfrog", dt=cfg["dt"], kx=cfg["kx"], kv=cfg["kv"], v=cfg["v"], dv=cfg["dv"],
@@ -323,23 +329,39 @@ def run_cpu_steps(workload, n, steps, warmup, workers):
 
 
 def reference_arm(args):
+    """The reference's CPU implementation of the path (the oracle port: the reference is pure Python and cannot
+    travel to the GPU box) on all host cores.  A step of this arm is a BOUNDED SAMPLE of the workload -- a smaller
+    grid of the same physics, named in ``config.sample`` -- and ``value`` is its size-normalised rate; ``ms_per_step``
+    is the time of one sample step (NOT of a full-size step).  The reference's own default (scipy.fft workers=1) is
+    timed beside it on the same sample (``cpu_baseline_workers1``)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     cores = os.cpu_count() or 1
-    n = cpu_sample_grid(args.steps + args.warmup)
-    value, sec = run_cpu_steps(args.workload, n, args.steps, args.warmup, workers=cores)
+    snx, snv = cpu_sample_grid(args.workload, args.steps + args.warmup)
+    value, sec = run_cpu_steps(args.workload, snx, snv, args.steps, args.warmup, workers=cores)
+    v1, s1 = run_cpu_steps(args.workload, snx, snv, max(1, min(3, args.steps)), 1, workers=1)
     nx, nv, desc = WORKLOADS[args.workload]
-    sample = ("%dx%d sub-grid of the same physics; scipy.fft workers=%d (numpy Thomas loop is single-threaded), "
-              "cell-updates/s is size-normalised" % (n, n, cores))
+    same = (snx, snv) == (nx, nv)
+    sample = ("%dx%d %s; scipy.fft workers=%d (numpy Thomas loop is single-threaded), cell-updates/s is size-normalised"
+              % (snx, snv, ("one member of the ensemble" if args.workload == "c4" else "grid of the workload") if same
+                 else "sub-grid of the same physics", cores))
     line = {
         "impl": "reference", "metric": "phase-space cell-updates/s (full collisional VPFP timestep)",
         "value": value, "unit": "cell-updates/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
-        "config": {"workload": desc, "nx": nx, "nv": nv, "integrator": "leapfrog", "collisions": "lb",
+        "config": {"workload": desc, "nx": nx, "nv": nv, "integrator": "leapfrog",
+                   "collisions": "none" if args.workload in ("c1", "c4") else "lb",
+                   "sample": {"nx": snx, "nv": snv, "workers": cores,
+                              "what": "every step of this arm runs on this grid; ms_per_step is the time of such a step, "
+                                      "value its size-normalised rate"},
+                   "same_config_as_gpu_arm": bool(same and args.workload != "c4"),
                    "reference_kind": "oracle port of the pure-Python reference (numpy/scipy), see oracle/"},
         "cpu_baseline": {"value": value, "unit": "cell-updates/s", "cores": cores, "kind": "port", "sample": sample},
+        "cpu_baseline_workers1": {"value": v1, "unit": "cell-updates/s", "cores": 1, "kind": "port",
+                                  "sample": "the same sub-grid with scipy.fft workers=1, the reference's own default",
+                                  "ms_per_sample_step": s1 * 1e3},
         "e2e": {"value": value, "unit": "cell-updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line))
@@ -348,6 +370,182 @@ def reference_arm(args):
 # ---------------------------------------------------------------------------------------------
 # GPU arm
 # ---------------------------------------------------------------------------------------------
+
+PARITY_STEPS = 3
+
+
+def make_work(cfg, e_dev, f_dev, total, dev, drv_rows, times):
+    """device-resident storage dictionary of vlapy_b200.core.step.get_timestep for `total` steps"""
+    import torch
+    from vlapy_b200.core import step
+    nx, nv = cfg["nx"], cfg["nv"]
+    return {
+        "time_batch": times, "driver_array_batch": drv_rows, "e": e_dev, "f": f_dev,
+        "stored_f": torch.zeros((total, 2, nv), dtype=torch.complex128, device=dev),
+        "fields": {k: torch.zeros((total, nx), dtype=torch.float64, device=dev) for k in step.FIELD_KEYS},
+        "series": {"_rows": torch.zeros((total, 7), dtype=torch.float64, device=dev)},
+        "_moment_scratch": torch.zeros((8, nx), dtype=torch.float64, device=dev),
+    }
+
+
+def checks_of(f, e, series_row):
+    """a small checksum set of a state, comparable between runs with different numbers of GPUs (all taken after
+    PARITY_STEPS steps from the same synthetic initial state)"""
+    nx, nv = f.shape
+    return {"sum_f": float(f.sum()), "max_f": float(f.max()), "f_probe": float(f[nx // 3, nv // 2 + 5]),
+            "e0": float(e[0]), "max_abs_e": float(e.abs().max()), "mean_n": float(series_row[0]),
+            "mean_T": float(series_row[2]), "mean_e2": float(series_row[3])}
+
+
+def single_gpu_parity_run(cfg, params, stuff, e0, f0, dev, drv_fn):
+    """PARITY_STEPS eager timesteps of the single-GPU path from (e0, f0); returns the final work dictionary"""
+    import torch
+    from vlapy_b200.core import step
+    one_step = step.get_timestep(all_params=params, stuff_for_time_loop=stuff)
+    times = cfg["dt"] * np.arange(PARITY_STEPS)
+    drv_rows = torch.from_numpy(np.stack([drv_fn(t) for t in times])).to(dev)
+    work = make_work(cfg, e0.clone(), f0.clone(), PARITY_STEPS, dev, drv_rows, times)
+    for i in range(PARITY_STEPS):
+        work, _ = one_step(work, i)
+    return work
+
+
+def sharded_arm(args, cfg, params, rules, dev, barrier):
+    """N > 1: the same nx x nv grid sharded over the ranks (strong scaling), vlapy_b200/dist.py.
+    Phases: (1) parity -- PARITY_STEPS steps on the sharded path and, on EVERY rank, on the single-GPU path of the
+    same library from the same state, compared cell by cell; (2) W warm-up + K timed steps; (3) per-kernel
+    durations; (4) end to end through the public inner-loop API (vlapy_b200.outer_loop under torchrun)."""
+    import copy
+    import torch
+    import torch.distributed as dist
+    from vlapy_b200 import dist as vd, ops, outer_loop
+    K, W = args.steps, args.warmup
+    nx, nv = cfg["nx"], cfg["nv"]
+    drv_fn = host_driver(cfg)
+    topo = vd.Topology(nx, nv)
+    stuff = {k: cfg[k] for k in ("kx", "x", "one_over_kx", "v", "kv", "nv", "nx", "dv", "dt", "nu")}
+    stuff.update(rules_to_store_f=rules, driver_function=drv_fn, pulse_dictionary=cfg["pulses"])
+    step_fn = vd.get_sharded_timestep(params, stuff, topo)
+    backend = step_fn.backend
+    # this rank's x-slab of the synthetic state, built on the host (pinned) and uploaded
+    fv = np.exp(-cfg["v"] ** 2 / 2.0)
+    fv /= (cfg["dv"] * (fv[1:] + fv[:-1]) / 2.0).sum()
+    xs = cfg["x"][topo.x0: topo.x0 + topo.nxl]
+    f_host = torch.empty((topo.nxl, nv), dtype=torch.float64, pin_memory=True)
+    np.multiply((1.0 + 0.05 * np.sin(cfg["k0"] * xs))[:, None], fv[None, :], out=f_host.numpy())
+    e_host = torch.empty(nx, dtype=torch.float64, pin_memory=True)
+    e_host.numpy()[:] = 0.01 * np.cos(cfg["k0"] * cfg["x"])
+    e0, f0_slab = e_host.to(dev), f_host.to(dev)
+
+    # ---- (1) parity of the sharded path against the single-GPU path, full grid, every rank checks its slab
+    parts = [torch.empty_like(f0_slab) for _ in range(topo.world)]
+    dist.all_gather(parts, f0_slab)
+    f0_full = torch.cat(parts, dim=0)
+    del parts
+    work = single_gpu_parity_run(cfg, params, stuff, e0, f0_full, dev, drv_fn)
+    del f0_full
+    state = {"e": e0.clone(), "f": vd.Sharded(f0_slab.clone(), "x")}
+    store = vd.make_store(topo, backend, PARITY_STEPS)
+    for i in range(PARITY_STEPS):
+        t = cfg["dt"] * i
+        state = step_fn(state, t, backend.driver(t), store)
+    series, modes = vd.finish_store(topo, store)
+    fx = vd.ops_to_x(state["f"], topo)
+    f1, e1 = work["f"], work["e"]
+    sl = slice(topo.x0, topo.x0 + topo.nxl)
+    s1 = work["series"]["_rows"]
+    m1 = torch.stack([work["fields"][k] for k in ("n", "j", "T", "q", "fv4", "vN")], dim=1)     # (steps, 6, nx)
+    errs = torch.stack([
+        (fx - f1[sl]).abs().max() / f1.abs().max(),
+        (state["e"] - e1).abs().max() / e1.abs().max(),
+        ((series - s1).abs() / s1.abs().clamp_min(1e-300))[:, [0, 2, 3, 5]].max(),
+        (modes - work["stored_f"]).abs().max() / work["stored_f"].abs().max(),
+        ((store["fields_mom"] - m1[:, :, sl]).abs().amax(dim=(0, 2)) / m1.abs().amax(dim=(0, 2))).max(),
+    ])
+    dist.all_reduce(errs, op=dist.ReduceOp.MAX)
+    # (the sharded checksum needs the full f: gathered from the slabs)
+    parts = [torch.empty_like(fx) for _ in range(topo.world)]
+    dist.all_gather(parts, fx.contiguous())
+    f_sh = torch.cat(parts, dim=0)
+    parity = {"vs": "single-GPU path of this library run on every rank from the same state, whole grid compared "
+                    "(each rank its x-slab, max over ranks)",
+              "steps": PARITY_STEPS, "max_rel_err_f_vs_single": float(errs[0]), "max_rel_err_e_vs_single": float(errs[1]),
+              "max_rel_err_series_vs_single": float(errs[2]), "max_rel_err_xmodes_vs_single": float(errs[3]),
+              "max_rel_err_moments_vs_single": float(errs[4]),
+              "checks_single": checks_of(f1, e1, s1[PARITY_STEPS - 1]),
+              "checks_sharded": checks_of(f_sh, state["e"], series[PARITY_STEPS - 1])}
+    del work, f1, e1, f_sh, parts, store, state, fx
+    torch.cuda.empty_cache()
+
+    # ---- (2) timed steps
+    state = {"e": e0.clone(), "f": vd.Sharded(f0_slab.clone(), "x")}
+    total = W + K
+    drv = [backend.driver(cfg["dt"] * i) for i in range(total)]
+    store = vd.make_store(topo, backend, total)
+    for i in range(W):
+        state = step_fn(state, cfg["dt"] * i, drv[i], store)
+    barrier()
+    sampler = ClockSampler(dev.index)
+    sampler.start()
+    ops.launch_count(reset=True)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for i in range(W, W + K):
+        state = step_fn(state, cfg["dt"] * i, drv[i], store)
+    ev1.record()
+    barrier()
+    ms = ev0.elapsed_time(ev1)
+    launches = ops.launch_count()
+    clocks = sampler.summary()
+    # ---- (3) per-kernel durations
+    ops.profile_enable(True)
+    store["i"] = W
+    for i in range(W, W + K):
+        state = step_fn(state, cfg["dt"] * i, drv[i], store)
+    prof = ops.profile_report()
+    ops.profile_enable(False)
+    P = topo.world
+    how = ("layout changes fused into the last advection pass (stores over NVLink into peer shards), "
+           "1 all-reduce + 1 barrier per step") if backend.can_scatter else "2 NCCL all-to-all + 1 all-reduce per step"
+    del store, state, drv
+    backend.close()
+    torch.cuda.empty_cache()
+
+    # ---- (4) end to end through the public API: the SAME call as on one GPU, under the process group
+    e2e = None
+    if not args.no_e2e:
+        Ke = args.e2e_steps or steps_in_loop(cfg)
+        p2 = copy.deepcopy(params)
+        p2["backend"]["gather"] = "slab"          # every rank downloads its own x-slab (one PCIe link each)
+        stuff_api = dict(stuff)
+        stuff_api.update(e=e_host.numpy(), f=f_host.numpy())
+        sim, inner = outer_loop.get_sim_config_and_inner_loop_step(p2, stuff_api, Ke, rules)
+        t_arr = cfg["dt"] * np.arange(Ke)
+        d_arr = torch.empty((Ke, nx), dtype=torch.float64, pin_memory=True)
+        d_arr.numpy()[:] = np.stack([drv_fn(t) for t in t_arr])
+        sim = inner(time_array=t_arr, driver_array=d_arr.numpy(), temp_storage=sim)      # warm-up: allocations, pinned mirrors
+        sim.pop("_dev", None)                                                            # next call uploads again
+        sim["f"], sim["e"] = f_host.numpy(), e_host.numpy()
+        barrier()
+        t0 = time.perf_counter()
+        sim = inner(time_array=t_arr, driver_array=d_arr.numpy(), temp_storage=sim)
+        barrier()
+        sec = time.perf_counter() - t0
+        tsec = torch.tensor([sec], dtype=torch.float64, device=dev)
+        dist.all_reduce(tsec, op=dist.ReduceOp.MAX)
+        sec = float(tsec.item())
+        h2d = (topo.nxl * nv * 8 + nx * 8 + Ke * nx * 8) / Ke
+        d2h = (topo.nxl * nv * 8 + nx * 8 + 8 * Ke * nx * 8 + 7 * Ke * 8 + Ke * 2 * nv * 8) / Ke
+        e2e = {"value": nx * nv * Ke / sec, "unit": "cell-updates/s", "h2d_bytes_per_step": h2d * P,
+               "d2h_bytes_per_step": d2h * P, "ms_per_step": sec * 1e3 / Ke, "steps": Ke,
+               "note": "one call of the public inner loop (vlapy_b200.outer_loop.get_sim_config_and_inner_loop_step under "
+                       "torchrun, backend.gather='slab') of %d steps (steps_in_loop of vlapy/manager.py:61-83): every rank "
+                       "uploads its x-slab, e and the driver rows from pinned host memory, runs the steps, downloads its "
+                       "slab and the all-gathered fields / series / stored modes; wall clock, max over ranks" % Ke}
+        inner.shard_backend.close()
+    return dict(ms=ms, launches=launches, clocks=clocks, prof=prof, e2e=e2e, scaling="strong", parity=parity,
+                parallelism="x-sharded rows / v-sharded columns over %d GPUs, %s" % (P, how))
+
 
 def gpu_arm(args):
     import torch
@@ -379,25 +577,23 @@ def gpu_arm(args):
         torch.cuda.synchronize()
 
     if world > 1:
-        from vlapy_b200 import dist as vdist
-        result = vdist.bench_sharded(cfg, params, rules, K, W, dev, barrier)
+        result = sharded_arm(args, cfg, params, rules, dev, barrier)
     else:
         f_host, e_host = initial_state(cfg, pinned=True)
         stuff = {k: cfg[k] for k in ("kx", "x", "one_over_kx", "v", "kv", "nv", "nx", "dv", "dt", "nu")}
         stuff.update(e=e_host.numpy(), f=f_host.numpy(), rules_to_store_f=rules, driver_function=drv_fn,
                      pulse_dictionary=cfg["pulses"])
+        # ---- parity block: the checksum set that the N > 1 lines compare against (same state, same step count)
+        pw = single_gpu_parity_run(cfg, params, stuff, e_host.to(dev), f_host.to(dev), dev, drv_fn)
+        parity = {"steps": PARITY_STEPS,
+                  "checks_single": checks_of(pw["f"], pw["e"], pw["series"]["_rows"][PARITY_STEPS - 1]),
+                  "note": "N > 1 lines run this same single-GPU path on every rank and report max_rel_err_*_vs_single"}
+        del pw
         one_step = step.get_timestep(all_params=params, stuff_for_time_loop=stuff)
         total = W + K
         times = cfg["dt"] * np.arange(total)
         drv_rows = torch.from_numpy(np.stack([drv_fn(t) for t in times])).to(dev)
-        work = {
-            "time_batch": times, "driver_array_batch": drv_rows,
-            "e": e_host.to(dev), "f": f_host.to(dev),
-            "stored_f": torch.zeros((total, 2, nv), dtype=torch.complex128, device=dev),
-            "fields": {k: torch.zeros((total, nx), dtype=torch.float64, device=dev) for k in step.FIELD_KEYS},
-            "series": {"_rows": torch.zeros((total, 7), dtype=torch.float64, device=dev)},
-            "_moment_scratch": torch.zeros((8, nx), dtype=torch.float64, device=dev),
-        }
+        work = make_work(cfg, e_host.to(dev), f_host.to(dev), total, dev, drv_rows, times)
         use_graph = nx * nv <= outer_loop.GRAPH_MAX_CELLS
         if use_graph:
             # launch-bound grids: the product path replays one captured step (vlapy_b200/outer_loop.py)
@@ -411,7 +607,6 @@ def gpu_arm(args):
                 gs.inp.copy_(inputs[i])
                 gs.graph.replay()
                 rows[i].copy_(gs.stage)
-            n_launch_per_step = None
         else:
             def run_step(i):
                 nonlocal work
@@ -440,18 +635,15 @@ def gpu_arm(args):
         ops.profile_enable(False)
         if use_graph:
             launches = ops.launch_count()    # kernels per step are the same in the captured graph
-            mean_n = float(rows[W + K - 1, 8 * nx])
-        else:
-            mean_n = float(work["series"]["_rows"][W + K - 1, 0])
         del work, drv_rows
         torch.cuda.empty_cache()
         # ---- end to end through the public inner-loop API with host buffers
         e2e = None
         if not args.no_e2e:
-            Kb, K = K, (args.e2e_steps or steps_in_loop(cfg))      # one inner loop as the manager issues it
-            sim, inner = outer_loop.get_sim_config_and_inner_loop_step(params, stuff, K, rules)
-            t_arr = cfg["dt"] * np.arange(K)
-            d_arr = torch.empty((K, nx), dtype=torch.float64, pin_memory=True)
+            Ke = args.e2e_steps or steps_in_loop(cfg)      # one inner loop as the manager issues it
+            sim, inner = outer_loop.get_sim_config_and_inner_loop_step(params, stuff, Ke, rules)
+            t_arr = cfg["dt"] * np.arange(Ke)
+            d_arr = torch.empty((Ke, nx), dtype=torch.float64, pin_memory=True)
             d_arr.numpy()[:] = np.stack([drv_fn(t) for t in t_arr])
             sim = inner(time_array=t_arr, driver_array=d_arr.numpy(), temp_storage=sim)   # warm-up (allocations)
             sim.pop("_dev", None)                      # force the next call to upload f and e again
@@ -461,17 +653,16 @@ def gpu_arm(args):
             sim = inner(time_array=t_arr, driver_array=d_arr.numpy(), temp_storage=sim)
             torch.cuda.synchronize()
             sec = time.perf_counter() - t0
-            h2d = (nx * nv * 8 + nx * 8 + K * nx * 8) / K
-            d2h = (8 * K * nx * 8 + 7 * K * 8 + K * 2 * nv * 16 + nx * nv * 8 + nx * 8) / K
-            e2e = {"value": nx * nv * K / sec, "unit": "cell-updates/s", "h2d_bytes_per_step": h2d,
-                   "d2h_bytes_per_step": d2h, "ms_per_step": sec * 1e3 / K,
-                   "steps": K,
+            h2d = (nx * nv * 8 + nx * 8 + Ke * nx * 8) / Ke
+            d2h = (8 * Ke * nx * 8 + 7 * Ke * 8 + Ke * 2 * nv * 8 + nx * nv * 8 + nx * 8) / Ke
+            e2e = {"value": nx * nv * Ke / sec, "unit": "cell-updates/s", "h2d_bytes_per_step": h2d,
+                   "d2h_bytes_per_step": d2h, "ms_per_step": sec * 1e3 / Ke,
+                   "steps": Ke,
                    "note": "one inner-loop call of %d steps (steps_in_loop of vlapy/manager.py:61-83 for this grid): "
                            "uploads f,e,driver rows; downloads fields, series, stored modes, f, e (storage cadence "
-                           "of vlapy/manager.py:138-150)" % K}
-            K = Kb
-        result = dict(ms=ms, launches=launches, clocks=clocks, prof=prof, e2e=e2e, mean_n=mean_n, scaling="strong",
-                      parallelism="1 GPU", graph=use_graph)
+                           "of vlapy/manager.py:138-150)" % Ke}
+        result = dict(ms=ms, launches=launches, clocks=clocks, prof=prof, e2e=e2e, scaling="strong",
+                      parallelism="1 GPU", graph=use_graph, parity=parity)
 
     if world > 1:
         t = torch.tensor([result["ms"]], dtype=torch.float64, device=dev)
@@ -488,15 +679,16 @@ def gpu_arm(args):
             opname = label.split(".")[0]
             ops_ms[opname] = ops_ms.get(opname, 0.0) + tot / K
         kernels = {label: {"launches_per_step": n / K, "ms_per_launch": tot / n,
-                           "gbs_algorithmic": 16.0 * cells / (tot / n * 1e-3) / 1e9}
+                           "gbs_algorithmic": ALGO_BYTES.get(label, 16.0) * cells / (tot / n * 1e-3) / 1e9}
                    for label, (n, tot) in prof.items() if tot / n > 0.02}
         traffic, traffic_src = ncu_traffic()
-        if world == 1 and (nx, nv) == (16384, 16384):        # the capture is of this configuration
+        full_size = world == 1 and (nx, nv) == (16384, 16384)     # the capture is of this configuration
+        if full_size:
             for label, k in kernels.items():
                 if label in traffic:
                     k["dram_bytes_ncu"] = traffic[label]["dram_bytes"]
-        dom = max(prof.items(), key=lambda kv: kv[1][1])
-        dom_label, (dom_n, dom_tot) = dom
+        heavy = {k: v for k, v in prof.items() if ALGO_BYTES.get(k, 16.0) == 16.0}
+        dom_label, (dom_n, dom_tot) = max(heavy.items(), key=lambda kv: kv[1][1])
         achieved = 16.0 * cells / (dom_tot / dom_n * 1e-3) / 1e9
         step_bytes = (64.0 if cfg["nu"] > 0 else 48.0) * nx * nv
         line = {
@@ -504,33 +696,37 @@ def gpu_arm(args):
             "value": value, "unit": "cell-updates/s", "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": ms / K, "higher_is_better": True, "scaling": result["scaling"], "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
-            "config": {"workload": cfg["desc"], "nx": nx, "nv": nv, "integrator": "leapfrog", "collisions": "lb",
+            "config": {"workload": cfg["desc"], "nx": nx, "nv": nv, "integrator": "leapfrog",
+                       "collisions": "lb" if cfg["nu"] > 0 else "none",
                        "per_step": "edfdv(dt/2), vdfdx(dt), density+Poisson, edfdv(dt/2), FP solve + 8 moments, "
                                    "series, 2 x-modes",
-                       "l2": "state (%.2f GB) exceeds the 126 MB L2; no flush needed" % (nx * nv * 8 / 1e9),
+                       "l2": ("state (%.2f GB) exceeds the 126 MB L2; no flush needed" % (nx * nv * 8 / 1e9)) if nx * nv * 8 > 2.5e8
+                             else "state (%.1f MB) fits the L2: an L2-resident, launch-bound configuration (no flush; the "
+                                  "reference workload is this size)" % (nx * nv * 8 / 1e6),
                        "parallelism": result["parallelism"], "phase_factors": "geometric tables (VPFP_PHASE_TABLE)",
                        "cuda_graph": bool(result.get("graph", False))},
             "clocks": result["clocks"], "gpu_launches": result["launches"],
             "roofline": {"bound": "hbm", "kernel": dom_label, "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak,
-                         "traffic": (traffic.get(dom_label, {}).get("dram_bytes")
-                                     if world == 1 and (nx, nv) == (16384, 16384) else None),
-                         "traffic_source": traffic_src, "peak_source": peak_src,
+                         "traffic": (traffic.get(dom_label, {}).get("dram_bytes") if full_size else None),
+                         "traffic_kind": "static: dram__bytes_read+write per launch from the committed ncu --set full "
+                                         "capture (%s), not measured in this run" % traffic_src,
+                         "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": 16.0 * cells,
                          "step": {"bytes_per_cell_update": step_bytes / (nx * nv),
                                   "achieved": step_bytes / (ms / K * 1e-3) / 1e9 / world,
                                   "frac": step_bytes / (ms / K * 1e-3) / 1e9 / world / peak},
                          "operators_ms_per_step": ops_ms, "kernels": kernels},
-            "e2e": result["e2e"], "mean_n_last_step": result["mean_n"],
+            "e2e": result["e2e"], "parity": result["parity"],
         }
         if world == 1 and not args.no_cpu:
             cores = os.cpu_count() or 1
-            n = cpu_sample_grid(3, budget_s=30.0)
-            v1, s1 = run_cpu_steps(args.workload, n, 2, 1, workers=1)
+            snx, snv = cpu_sample_grid(args.workload, 3, budget_s=30.0)
+            v1, s1 = run_cpu_steps(args.workload, snx, snv, 2, 1, workers=1)
             line["cpu_baseline"] = {"value": v1, "unit": "cell-updates/s", "cores": 1, "kind": "port",
                                     "sample": "oracle port (numpy/scipy, scipy.fft workers=1 as the reference runs it) on a "
-                                              "%dx%d sub-grid of the same physics, 2 steps after 1 warm-up; host has %d cores"
-                                              % (n, n, cores)}
+                                              "%dx%d grid of the same physics, 2 steps after 1 warm-up; host has %d cores"
+                                              % (snx, snv, cores)}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

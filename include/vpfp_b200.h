@@ -118,6 +118,20 @@ int vpfp_fp_step_linspace(const double *f_in, long ld_in, double *f_out, long ld
                           double vstep, double vlast, double nu, double dt, double dv, int op,
                           double *moments_out, long mom_ld, int rows, int nv, void *stream);
 
+/* The reference's explicit two-stage collision interface (the product step fuses both stages and never
+ * materialises the diagonals; these serve callers of get_batched_array_maker / get_matrix_solver).
+ * vpfp_fp_diagonals: f -> (a, b, c), replaces vlapy/core/collisions.py:26-83 (lb) and :86-160 (dg) as returned by
+ *   get_batched_array_maker (:292-317).  a, c: (rows, nv-1) with pitches lda, ldc; b: (rows, nv).
+ * vpfp_tridiag_solve: x = solve(tridiag(a, b, c), d) per row, general diagonals, no pivoting; replaces
+ *   vlapy/core/collisions.py:222-265 (_batched_tridiag_solver_ behind get_matrix_solver :268-289).
+ *   a[i-1] couples row i to x[i-1], c[i] couples row i to x[i+1] (the reference's storage). 8 <= nv <= 16384.
+ *   x may alias d. */
+int vpfp_fp_diagonals(const double *f, long ld, const double *v, double nu, double dt, double dv, int op,
+                      double *a, long lda, double *b, long ldb, double *c, long ldc, int rows, int nv,
+                      void *stream);
+int vpfp_tridiag_solve(const double *a, long lda, const double *b, long ldb, const double *c, long ldc,
+                       const double *d, long ldd, double *x, long ldx, int rows, int nv, void *stream);
+
 /* First nmodes x-Fourier modes of f per v: out[(b*nmodes + m)*ncols + j] = sum_x f[b,x,j] w^(m x)
  * as interleaved (re, im) doubles.  Replaces vlapy/core/step.py:130-135 (get_f_to_store). */
 int vpfp_xmodes(const double *f, long ld, double *out, int nmodes, int batch, int nx, int ncols,

@@ -12,7 +12,7 @@ CSRC = os.path.join(os.path.dirname(os.path.dirname(HERE)), "vlapy_b200", "csrc"
 
 
 def build(force=False):
-    deps = [SRC] + [os.path.join(CSRC, n) for n in ("advect.h", "rowops.h", "vpfp_common.h", "butterflies.h", "rowfft.cuh")]
+    deps = [SRC] + [os.path.join(CSRC, n) for n in ("advect.h", "rowops.h", "tridiag.h", "vpfp_common.h", "butterflies.h", "rowfft.cuh")]
     if force or not os.path.exists(SO) or any(os.path.getmtime(d) > os.path.getmtime(SO) for d in deps):
         subprocess.check_call(["g++", "-O2", "-ffp-contract=off", "-std=c++17", "-shared", "-fPIC",
                                "-o", SO, SRC])
@@ -130,6 +130,22 @@ def fp_step(f, v, nu, dt, dv, op, want_moments=False, m=0):
                        c_double(dt), c_double(dv), c_int(0 if op == "lb" else 1), _p(mom), c_long(rows),
                        c_int(rows), c_int(nv), c_int(m))
     return (out, mom) if want_moments else out
+
+
+def fp_diagonals(f, v, nu, dt, dv, op):
+    f = np.ascontiguousarray(f); rows, nv = f.shape
+    a, b, c = np.empty((rows, nv - 1)), np.empty((rows, nv)), np.empty((rows, nv - 1))
+    lib().emul_fp_diagonals(_p(f), c_long(nv), _p(np.ascontiguousarray(v)), c_double(nu), c_double(dt), c_double(dv),
+                            c_int(0 if op == "lb" else 1), _p(a), _p(b), _p(c), c_int(rows), c_int(nv))
+    return a, b, c
+
+
+def tridiag_solve(a, b, c, d, m=0):
+    a, b, c, d = (np.ascontiguousarray(t, dtype=np.float64) for t in (a, b, c, d))
+    rows, nv = d.shape
+    x = np.empty_like(d)
+    lib().emul_tridiag_solve(_p(a), _p(b), _p(c), _p(d), _p(x), c_int(rows), c_int(nv), c_int(m))
+    return x
 
 
 def xmodes(f, nmodes=2):

@@ -13,6 +13,7 @@
 
 #include "../../vlapy_b200/csrc/advect.h"
 #include "../../vlapy_b200/csrc/rowops.h"
+#include "../../vlapy_b200/csrc/tridiag.h"
 
 template <class Prog>
 static void run_prog(const Prog& prog, long nblocks, int threads, long smem_bytes, int nph) {
@@ -132,6 +133,35 @@ int emul_fp_step(const double* f_in, long ld_in, double* f_out, long ld_out, con
   int threads = ((p.P + 31) / 32) * 32;
   if (threads > 1024) threads = 1024;
   run_prog(p, rows, threads, p.smem_bytes(threads), p.nphases(threads));
+  return 0;
+}
+
+// launch geometry as vpfp_fp_diagonals / vpfp_tridiag_solve (vlapy_b200/csrc/vpfp_cuda.cu)
+int emul_fp_diagonals(const double* f, long ld, const double* v, double nu, double dt, double dv, int op,
+                      double* a, double* b, double* c, int rows, int nv) {
+  DiagProg p;
+  p.f = f; p.ld = ld; p.v = v; p.nu = nu; p.dt = dt; p.dv = dv; p.op = op;
+  p.a = a; p.lda = nv - 1; p.b = b; p.ldb = nv; p.c = c; p.ldc = nv - 1; p.rows = rows; p.nv = nv;
+  int threads = 256;
+  while (threads > 32 && threads * 2 > nv) threads >>= 1;
+  run_prog(p, rows, threads, p.smem_bytes(threads), p.nphases(threads));
+  return 0;
+}
+
+int emul_tridiag_solve(const double* a, const double* b, const double* c, const double* d, double* x, int rows,
+                       int nv, int m_override) {
+  TridiagProg p;
+  p.a = a; p.lda = nv - 1; p.b = b; p.ldb = nv; p.c = c; p.ldc = nv - 1; p.d = d; p.ldd = nv; p.x = x; p.ldx = nv;
+  p.rows = rows; p.nv = nv;
+  int m = nv / 256;
+  if (m < 4) m = 4;
+  if (m > 16) m = 16;
+  if (m_override > 0) m = m_override;
+  p.m = m;
+  p.P = nv / m;
+  int threads = ((p.P + 31) / 32) * 32;
+  if (threads > 1024) threads = 1024;
+  run_prog(p, rows, threads, p.smem_bytes(threads), p.nphases());
   return 0;
 }
 

@@ -149,6 +149,41 @@ def test_fp_program_sizes_and_stiffness(op, nu, nv, m):
     assert rel_err(out, truth) < 4 * rel_err(ref, truth) + TOL
 
 
+@pytest.mark.parametrize("op", ["lb", "dg"])
+def test_two_stage_collision_programs_vs_reference(op):
+    """csrc/tridiag.h: DiagProg against the diagonals the REFERENCE's get_batched_array_maker returned (golden
+    ops_small lb_a/lb_b/lb_c, dg_*), TridiagProg on those diagonals against the reference's solve"""
+    g = golden("ops_small")
+    nu, dt, dv = float(g["nu"]), float(g["dt"]), float(g["dv"])
+    a, b, c = E.fp_diagonals(g["fpos"], g["v"], nu, dt, dv, op)
+    for got, name in ((a, "_a"), (b, "_b"), (c, "_c")):
+        ref = g[op + name]
+        assert got.shape == ref.shape
+        assert np.max(np.abs(got - ref)) <= 1e-13 * np.max(np.abs(ref)), name
+    assert rel_err(E.tridiag_solve(g[op + "_a"], g[op + "_b"], g[op + "_c"], g["fpos"]), g[op + "_solve"]) < TOL
+    assert rel_err(E.tridiag_solve(a, b, c, g["fpos"]), g[op + "_solve"]) < TOL
+
+
+@pytest.mark.parametrize("nv,m", [(8, 4), (24, 4), (100, 7), (1000, 0), (1024, 0), (4096, 0), (16384, 0)])
+def test_tridiag_program_general_diagonals(nv, m):
+    """general (non-constant, non-symmetric) diagonally dominant diagonals, ragged sizes, against the reference's
+    Thomas sweep (oracle thomas_batched = vlapy/core/collisions.py:232-263)"""
+    rng = np.random.default_rng(nv)
+    rows = 3
+    a = rng.uniform(-1, 1, (rows, nv - 1))
+    c = rng.uniform(-1, 1, (rows, nv - 1))
+    b = 2.5 + rng.uniform(0, 1, (rows, nv))
+    d = rng.standard_normal((rows, nv))
+    ref = O.thomas_batched(a, b, c, d)
+    out = E.tridiag_solve(a, b, c, d, m=m)
+    assert rel_err(out, ref) < TOL
+    # the system is solved: residual of the tridiagonal product
+    res = b * out
+    res[:, 1:] += a * out[:, :-1]
+    res[:, :-1] += c * out[:, 1:]
+    assert rel_err(res, d) < 1e-13
+
+
 def test_fp_collision_unit_cases_16_steps():
     g = golden("collisions_unit")
     v, dv, nu, dt = g["v"], float(g["dv"]), float(g["nu"]), float(g["dt"])

@@ -80,13 +80,13 @@ def _worker_scatter(rank, world, port, nx, nv, nsteps, integrator, q):
         from vlapy_b200 import dist as vd
         cfg = O.nlepw_config(nx=nx, nv=nv, log_nu=-2)
         topo = vd.Topology(cfg["nx"], cfg["nv"])
-        params = {"nu": cfg["nu"], "vlasov-poisson": {"time": integrator}, "fokker-planck": {"type": "lb"}}
         stuff = {k: cfg[k] for k in ("kx", "x", "one_over_kx", "v", "kv", "nv", "nx", "dv", "dt", "nu")}
         stuff.update(pulse_dictionary=cfg["pulses"], driver_function=cfg["driver_function"])
         dev = torch.device("cuda", rank)
         res = {}
         for mode in ("a2a", "scatter"):
-            os.environ["VPFP_NO_SCATTER"] = "1" if mode == "a2a" else "0"
+            params = {"nu": cfg["nu"], "vlasov-poisson": {"time": integrator}, "fokker-planck": {"type": "lb"},
+                      "backend": {"peer_scatter": mode == "scatter"}}
             step = vd.get_sharded_timestep(params, stuff, topo)
             assert step.backend.can_scatter == (mode == "scatter")
             f0 = torch.from_numpy(cfg["f0"][topo.x0: topo.x0 + topo.nxl].copy()).to(dev)
@@ -131,3 +131,91 @@ def test_peer_scatter_matches_all_to_all_and_oracle(world, nx, nv, integrator):
     e_ref, f_ref = O.run_steps(cfg, nsteps, integrator, "lb")
     assert np.max(np.abs(f["scatter"] - f_ref)) / np.max(np.abs(f_ref)) < 1e-12
     assert np.max(np.abs(e["scatter"] - e_ref)) / np.max(np.abs(e_ref)) < 1e-10
+
+
+def _worker_api(rank, world, port, nx, nv, q):
+    """the public inner loop under a process group (vlapy_b200.outer_loop.get_sim_config_and_inner_loop_step),
+    and on rank 0 the single-GPU inner loop of the same call with backend.sharded = False"""
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        import copy
+        from oracle import vpfp_oracle as O
+        from vlapy_b200 import outer_loop
+        cfg = O.nlepw_config(nx=nx, nv=nv, log_nu=-2)
+        rules = {"time": "first-last", "space": ["k0", "k1"]}
+        params = {"backend": {"core": "b200"}, "nu": cfg["nu"],
+                  "vlasov-poisson": {"time": "leapfrog", "vdfdx": "exponential", "edfdv": "exponential",
+                                     "poisson": "spectral"},
+                  "fokker-planck": {"type": "lb", "solver": "batched_tridiagonal"}}
+        stuff = {k: cfg[k] for k in ("kx", "x", "one_over_kx", "v", "kv", "nv", "nx", "dv", "dt", "nu",
+                                     "driver_function")}
+        stuff.update(e=cfg["e0"], f=cfg["f0"], rules_to_store_f=rules, pulse_dictionary=cfg["pulses"])
+        nt, loops = 4, 2
+
+        def run(p):
+            sim, inner = outer_loop.get_sim_config_and_inner_loop_step(p, stuff, nt, rules)
+            outs = []
+            for li in range(loops):
+                t = cfg["dt"] * np.arange(li * nt, (li + 1) * nt)
+                drv = np.stack([cfg["driver_function"](ti) for ti in t])
+                sim = inner(time_array=t, driver_array=drv, temp_storage=sim)
+                outs.append({k: ({kk: np.array(vv) for kk, vv in v.items()} if isinstance(v, dict) else
+                                 (v if isinstance(v, (tuple, float)) else np.array(v)))
+                             for k, v in sim.items() if not k.startswith("_")})
+            return outs, inner
+        sharded, inner = run(params)
+        assert inner.topology.world == world and inner.shard_backend.can_scatter
+        single = None
+        if rank == 0:
+            p1 = copy.deepcopy(params)
+            p1["backend"]["sharded"] = False
+            single, _ = run(p1)
+        inner.shard_backend.close()
+        q.put((rank, sharded, single))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_sharded_inner_loop_api_equals_single_gpu_inner_loop():
+    """every key the storage layer reads (vlapy/storage.py:78-91) from the sharded inner loop behind the
+    reference API equals what the single-GPU inner loop returns for the same call"""
+    world, nx, nv = 2, 2048, 4096
+    if not torch.cuda.is_available() or torch.cuda.device_count() < world:
+        pytest.skip("needs %d GPUs" % world)
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker_api, args=(r, world, 29671, nx, nv, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    outs = sorted([q.get(timeout=900) for _ in range(world)], key=lambda o: o[0])
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    single = outs[0][2]
+    for rank in range(world):
+        for li, (a, b) in enumerate(zip(single, outs[rank][1])):
+            assert set(a) <= set(b)
+            for k in a:
+                if isinstance(a[k], dict):
+                    assert set(a[k]) == set(b[k])
+                    for kk in a[k]:
+                        ra, rb = a[k][kk], b[k][kk]
+                        assert ra.shape == rb.shape and ra.dtype == rb.dtype, (k, kk)
+                        scale = max(np.max(np.abs(ra)), 1e-300)
+                        assert np.max(np.abs(ra - rb)) / scale < 1e-11, (rank, li, k, kk)
+                elif k == "f":
+                    x0, x1 = b["f_slab"]
+                    assert rb_shape_ok(b[k], x1 - x0, nv)
+                    assert np.max(np.abs(a[k][x0:x1] - b[k])) / np.max(np.abs(a[k])) < 1e-12, (rank, li)
+                elif isinstance(a[k], np.ndarray):
+                    assert a[k].shape == b[k].shape and a[k].dtype == b[k].dtype, k
+                    tol = 1e-6 if k == "stored_f" else 1e-11
+                    assert np.max(np.abs(a[k] - b[k])) <= tol * max(np.max(np.abs(a[k])), 1e-300), (rank, li, k)
+    assert outs[0][1][0]["f_slab"] == (0, nx) and outs[1][1][0]["f_slab"] == (nx // 2, nx)
+
+
+def rb_shape_ok(f, rows, nv):
+    return f.shape == (rows, nv) and f.dtype == np.float64

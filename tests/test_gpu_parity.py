@@ -265,6 +265,59 @@ def test_fp_sizes_vs_oracle(dev, op, nv, linspace_kernel):
     assert torch.equal(out, out2)          # with and without the fused moments: same bits
 
 
+@pytest.mark.parametrize("op", ["lb", "dg"])
+def test_tridiag_two_stage_interface_vs_reference(dev, op):
+    """the reference's explicit two-stage collision interface (vlapy/core/collisions.py:268-317) on the device:
+    get_batched_array_maker against the diagonals the REFERENCE returned (golden ops_small), get_matrix_solver on
+    them against the reference's solve; numpy in -> numpy out, CUDA in -> CUDA out, arguments untouched"""
+    from vlapy_b200.core import collisions
+    g = golden("ops_small")
+    nu, dt, dv, v, f = float(g["nu"]), float(g["dt"]), float(g["dv"]), g["v"], g["fpos"]
+    nx, nv = f.shape
+    maker = collisions.get_batched_array_maker(v, nv, nx, nu, dt, dv, operator=op)
+    a, b, c = maker(f)
+    assert isinstance(a, np.ndarray)
+    for got, name in ((a, "_a"), (b, "_b"), (c, "_c")):
+        ref = g[op + name]
+        assert got.shape == ref.shape
+        assert np.max(np.abs(got - ref)) <= 1e-13 * np.max(np.abs(ref)), name
+    for solver_name in ("batched_tridiagonal", "naive"):
+        solve = collisions.get_matrix_solver(nx, nv, solver_name)
+        keep = [t.copy() for t in (a, b, c, f)]
+        x = solve(a, b, c, f)
+        assert rel_err(x, g[op + "_solve"]) < TOL
+        assert all(np.array_equal(k, t) for k, t in zip(keep, (a, b, c, f)))
+    fd = torch.from_numpy(f).to(dev)
+    ad, bd, cd = maker(fd)
+    assert ad.is_cuda and rel_err(ad.cpu().numpy(), g[op + "_a"]) < 1e-13
+    xd = collisions.get_matrix_solver(nx, nv)(ad, bd, cd, fd)
+    assert xd.is_cuda and rel_err(xd.cpu().numpy(), g[op + "_solve"]) < TOL
+    with pytest.raises(NotImplementedError):
+        collisions.get_matrix_solver(nx, nv, "cholesky")
+    with pytest.raises(NotImplementedError):
+        collisions.get_batched_array_maker(v, nv, nx, nu, dt, dv, operator="krook")
+
+
+@pytest.mark.parametrize("nv", [8, 100, 1000, 2048, 16384])
+def test_tridiag_general_diagonals_vs_thomas(dev, nv):
+    """general (non-constant, non-symmetric) diagonally dominant systems, ragged sizes, against the reference's
+    Thomas sweep restated in the oracle (vlapy/core/collisions.py:232-263)"""
+    from vlapy_b200 import ops
+    rng = np.random.default_rng(nv)
+    rows = 37
+    a = rng.uniform(-1, 1, (rows, nv - 1))
+    c = rng.uniform(-1, 1, (rows, nv - 1))
+    b = 2.5 + rng.uniform(0, 1, (rows, nv))
+    d = rng.standard_normal((rows, nv))
+    ref = O.thomas_batched(a, b, c, d)
+    t = [torch.from_numpy(z).to(dev) for z in (a, b, c, d)]
+    out = ops.tridiag_solve(*t).cpu().numpy()
+    assert rel_err(out, ref) < TOL
+    with pytest.raises(NotImplementedError):            # nv = 4 < 8
+        ops.tridiag_solve(t[0][:, :3].contiguous(), t[1][:, :4].contiguous(), t[2][:, :3].contiguous(),
+                          t[3][:, :4].contiguous())
+
+
 def field_tolerances(cfg, fmax):
     """Per-field absolute tolerance that follows from 1e-12 relative parity on f (norm max|f|):
     a v-moment of order p is a linear functional of f with L1 weight int |v|^p dv, and E is the

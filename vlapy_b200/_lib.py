@@ -11,7 +11,7 @@ ROOT = os.path.dirname(PKG)
 # VPFP_B200_LIB: another build of the same CUDA library (A/B timing of two revisions in one GPU session)
 SO = os.environ.get("VPFP_B200_LIB") or os.path.join(PKG, "lib", "libvpfp_b200.so")
 SRC = os.path.join(PKG, "csrc", "vpfp_cuda.cu")
-HEADERS = [os.path.join(PKG, "csrc", n) for n in ("vpfp_common.h", "advect.h", "rowops.h", "butterflies.h", "rowfft.cuh",
+HEADERS = [os.path.join(PKG, "csrc", n) for n in ("vpfp_common.h", "advect.h", "rowops.h", "butterflies.h", "rowfft.cuh", "tridiag.h",
                                                     "advect_fast.cuh", "fp_fast.cuh", "fp_reg.cuh")] + [
     os.path.join(ROOT, "include", "vpfp_b200.h")]
 
@@ -54,6 +54,8 @@ _SIGS = {
     "vpfp_poisson": ([_P, _P, _P, _P, _I, _I, _P], _I),
     "vpfp_fp_step": ([_P, _L, _P, _L, _P, _D, _D, _D, _I, _P, _L, _I, _I, _P], _I),
     "vpfp_fp_step_linspace": ([_P, _L, _P, _L, _D, _D, _D, _D, _D, _D, _I, _P, _L, _I, _I, _P], _I),
+    "vpfp_fp_diagonals": ([_P, _L, _P, _D, _D, _D, _I, _P, _L, _P, _L, _P, _L, _I, _I, _P], _I),
+    "vpfp_tridiag_solve": ([_P, _L, _P, _L, _P, _L, _P, _L, _P, _L, _I, _I, _P], _I),
     "vpfp_xmodes": ([_P, _L, _P, _I, _I, _I, _I, _P], _I),
     "vpfp_xmodes_partial": ([_P, _L, _P, _I, _I, _I, _I, _I, _I, _P], _I),
     "vpfp_driver": ([_P, _D, _P, _I, _P, _I, _P], _I),

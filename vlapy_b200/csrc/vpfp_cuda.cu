@@ -21,6 +21,7 @@
 #include "fp_reg.cuh"
 #include "rowfft.cuh"
 #include "rowops.h"
+#include "tridiag.h"
 
 // ------------------------------------------------------------------------------------------
 // error plumbing
@@ -856,6 +857,40 @@ int vpfp_fp_step_linspace(const double* f_in, long ld_in, double* f_out, long ld
     case 128: return launch_fp_fast<4, 32>(a, st);
     default: return fail(VPFP_ERR_UNSUPPORTED, "vpfp_fp_step_linspace: nv must be a power of two in [128, 16384]");
   }
+}
+
+int vpfp_fp_diagonals(const double* f, long ld, const double* v, double nu, double dt, double dv, int op,
+                      double* a, long lda, double* b, long ldb, double* c, long ldc, int rows, int nv, void* stream) {
+  if (!f || !v || !a || !b || !c || rows <= 0 || nv < 2 || ld < nv || lda < nv - 1 || ldb < nv || ldc < nv - 1)
+    return fail(VPFP_ERR_ARG, "vpfp_fp_diagonals: bad argument");
+  if (op != VPFP_FP_LB && op != VPFP_FP_DG)
+    return fail(VPFP_ERR_UNSUPPORTED, "Collision Operator: unknown operator id");
+  DiagProg p;
+  p.f = f; p.ld = ld; p.v = v; p.nu = nu; p.dt = dt; p.dv = dv; p.op = op;
+  p.a = a; p.lda = lda; p.b = b; p.ldb = ldb; p.c = c; p.ldc = ldc; p.rows = rows; p.nv = nv;
+  int threads = 256;
+  while (threads > 32 && threads * 2 > nv) threads >>= 1;
+  return launch_prog(p, rows, threads, p.smem_bytes(threads), p.nphases(threads), (cudaStream_t)stream, "fp_diagonals");
+}
+
+int vpfp_tridiag_solve(const double* a, long lda, const double* b, long ldb, const double* c, long ldc,
+                       const double* d, long ldd, double* x, long ldx, int rows, int nv, void* stream) {
+  if (!a || !b || !c || !d || !x || rows <= 0 || nv <= 0 || lda < nv - 1 || ldb < nv || ldc < nv - 1 || ldd < nv ||
+      ldx < nv)
+    return fail(VPFP_ERR_ARG, "vpfp_tridiag_solve: bad argument");
+  if (nv < 8 || nv > 16384)
+    return fail(VPFP_ERR_UNSUPPORTED, "batched tridiagonal solver needs 8 <= nv <= 16384 on the b200 backend");
+  TridiagProg p;
+  p.a = a; p.lda = lda; p.b = b; p.ldb = ldb; p.c = c; p.ldc = ldc; p.d = d; p.ldd = ldd; p.x = x; p.ldx = ldx;
+  p.rows = rows; p.nv = nv;
+  int m = nv / 256;
+  if (m < 4) m = 4;
+  if (m > 16) m = 16;
+  p.m = m;
+  p.P = nv / m;
+  int threads = ((p.P + 31) / 32) * 32;
+  if (threads > 1024) threads = 1024;
+  return launch_prog(p, rows, threads, p.smem_bytes(threads), p.nphases(), (cudaStream_t)stream, "tridiag_solve");
 }
 
 int vpfp_xmodes_partial(const double* f, long ld, double* out, int nmodes, int batch, int nx, int ncols,

@@ -108,7 +108,7 @@ class PeerShards:
 class DeviceBackend:
     """Per-shard operators on the CUDA kernels (vlapy_b200.ops)."""
 
-    def __init__(self, topo, stuff, fp_type):
+    def __init__(self, topo, stuff, fp_type, peer_scatter=True):
         from . import ops
         from ._util import const
         from .core.vlasov import _phase_flags
@@ -128,14 +128,12 @@ class DeviceBackend:
         self.edge = (1 if topo.rank == 0 else 0) | (2 if topo.rank == topo.world - 1 else 0)
         # layout changes fused into the operators' last pass (stores over NVLink into the peers'
         # shards) when the register-resident kernels apply; otherwise NCCL all-to-all transposes
-        import os
-
         def pow2(n):
             return n > 0 and (n & (n - 1)) == 0
         P = topo.world
         self.can_scatter = (P > 1 and P <= 8 and pow2(P) and pow2(topo.nx) and pow2(topo.nv)
                             and 256 <= topo.nx <= 16384 and 256 <= topo.nv <= 16384
-                            and topo.nxl * topo.nv >= (1 << 22) and os.environ.get("VPFP_NO_SCATTER", "0") == "0")
+                            and topo.nxl * topo.nv >= (1 << 22) and bool(peer_scatter))
         self.peers = PeerShards(topo, self.x.device) if self.can_scatter else None
         self.scratch_x = self.scratch_v = None
 
@@ -260,7 +258,9 @@ def get_sharded_timestep(all_params, stuff_for_time_loop, topo, backend=None):
     ``store`` (optional) receives the per-step stored quantities of this rank's x-slab."""
     from .core import vlasov_poisson
     if backend is None:
-        backend = DeviceBackend(topo, stuff_for_time_loop, all_params["fokker-planck"]["type"])
+        # backend.peer_scatter = False keeps the NCCL all-to-all transposes (tests compare the two)
+        backend = DeviceBackend(topo, stuff_for_time_loop, all_params["fokker-planck"]["type"],
+                                peer_scatter=all_params.get("backend", {}).get("peer_scatter", True))
     ops_ = make_sharded_operators(topo, backend)
     stuff = dict(stuff_for_time_loop)
     stuff["driver_function"] = backend.driver
@@ -320,91 +320,6 @@ def finish_store(topo, store):
     series = topo.all_reduce_sum(store["series_sum"].clone()) / topo.nx
     modes = topo.all_reduce_sum(store["modes_partial"].clone())
     return series, torch.view_as_complex(modes.contiguous())
-
-
-# ---------------------------------------------------------------------------------------------
-# bench.py --gpus N
-# ---------------------------------------------------------------------------------------------
-
-def bench_sharded(cfg, params, rules, K, W, dev, barrier):
-    """Strong scaling: the same nx x nv grid sharded over the ranks; K timed full timesteps."""
-    import bench as _bench
-    from . import ops
-    nx, nv = cfg["nx"], cfg["nv"]
-    topo = Topology(nx, nv)
-    stuff = {k: cfg[k] for k in ("kx", "x", "one_over_kx", "v", "kv", "nv", "nx", "dv", "dt", "nu")}
-    stuff.update(rules_to_store_f=rules, driver_function=_bench.host_driver(cfg), pulse_dictionary=cfg["pulses"])
-    step = get_sharded_timestep(params, stuff, topo)
-    backend = step.backend
-    # this rank's x-slab of the synthetic state, built on the host and uploaded
-    fv = np.exp(-cfg["v"] ** 2 / 2.0)
-    fv /= (cfg["dv"] * (fv[1:] + fv[:-1]) / 2.0).sum()
-    xs = cfg["x"][topo.x0: topo.x0 + topo.nxl]
-    f_host = torch.empty((topo.nxl, nv), dtype=torch.float64, pin_memory=True)
-    np.multiply((1.0 + 0.05 * np.sin(cfg["k0"] * xs))[:, None], fv[None, :], out=f_host.numpy())
-    e = torch.from_numpy(0.01 * np.cos(cfg["k0"] * cfg["x"])).to(dev)
-    state = {"e": e, "f": Sharded(f_host.to(dev), "x")}
-    total = W + K
-    drv = [backend.driver(cfg["dt"] * i) for i in range(total)]
-    store = make_store(topo, backend, total)
-    for i in range(W):
-        state = step(state, cfg["dt"] * i, drv[i], store)
-    barrier()
-    sampler = _bench.ClockSampler(dev.index)
-    sampler.start()
-    ops.launch_count(reset=True)
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    ev0.record()
-    for i in range(W, W + K):
-        state = step(state, cfg["dt"] * i, drv[i], store)
-    ev1.record()
-    barrier()
-    ms = ev0.elapsed_time(ev1)
-    launches = ops.launch_count()
-    clocks = sampler.summary()
-    series, modes = finish_store(topo, store)
-    mean_n = float(series[total - 1, 0])
-    # per-kernel durations
-    ops.profile_enable(True)
-    store["i"] = W
-    for i in range(W, W + K):
-        state = step(state, cfg["dt"] * i, drv[i], store)
-    prof = ops.profile_report()
-    ops.profile_enable(False)
-    # end to end: upload the slab from pinned host memory, K steps, download slab + stored rows
-    import time
-    Kb, K = K, _bench.steps_in_loop(cfg)           # one inner loop as vlapy/manager.py:61-83 sizes it
-    del store
-    store = make_store(topo, backend, K)
-    drv_host = torch.empty((K, nx), dtype=torch.float64, pin_memory=True)
-    drv_host.numpy()[:] = np.stack([_bench.host_driver(cfg)(cfg["dt"] * i) for i in range(K)])
-    barrier()
-    t0 = time.perf_counter()
-    st2 = {"e": e, "f": Sharded(f_host.to(dev, non_blocking=True), "x")}
-    drv2 = drv_host.to(dev, non_blocking=True)
-    store["i"] = 0
-    for i in range(K):
-        st2 = step(st2, cfg["dt"] * i, drv2[i], store)
-    f_back = torch.empty((topo.nxl, nv), dtype=torch.float64, pin_memory=True)
-    f_back.copy_(ops_to_x(st2["f"], topo), non_blocking=True)
-    fields_back = store["fields_mom"][:K].cpu()
-    s2, m2 = finish_store(topo, store)
-    s2.cpu(); m2.cpu()
-    barrier()
-    sec = time.perf_counter() - t0
-    h2d = (topo.nxl * nv * 8 + K * nx * 8) / K
-    d2h = (topo.nxl * nv * 8 + 8 * K * topo.nxl * 8 + 7 * K * 8 + K * 2 * nv * 16) / K
-    e2e = {"value": nx * nv * K / sec, "unit": "cell-updates/s", "h2d_bytes_per_step": h2d * topo.world,
-           "d2h_bytes_per_step": d2h * topo.world, "ms_per_step": sec * 1e3 / K, "steps": K,
-           "note": "one inner loop of %d steps (steps_in_loop of vlapy/manager.py:61-83): every rank uploads its "
-                   "x-slab and the driver rows, runs the steps, downloads slab + stored rows" % K}
-    K = Kb
-    P = topo.world
-    how = ("layout changes fused into the last advection pass (stores over NVLink into peer shards), "
-           "1 all-reduce + 1 barrier per step") if backend.can_scatter else "2 NCCL all-to-all + 1 all-reduce per step"
-    backend.close()
-    return dict(ms=ms, launches=launches, clocks=clocks, prof=prof, e2e=e2e, mean_n=mean_n, scaling="strong",
-                parallelism="x-sharded rows / v-sharded columns over %d GPUs, %s" % (P, how))
 
 
 def ops_to_x(f, topo):

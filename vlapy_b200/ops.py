@@ -246,6 +246,39 @@ def fp_step(f, v, nu, dt, dv, op="lb", out=None, moments_out=None, vgrid=None):
     return out
 
 
+def fp_diagonals(f, v, nu, dt, dv, op="lb"):
+    """vlapy/core/collisions.py:44-81 / 104-158 on device: f (rows, nv) -> a (rows, nv-1), b (rows, nv), c (rows, nv-1)."""
+    rows, ld = _chk_f(f)
+    nv = f.shape[-1]
+    if op not in FP_OPS:
+        raise NotImplementedError("Collision Operator: <" + str(op) + "> has not yet been implemented on the b200 backend")
+    _vec(v, nv, "v")
+    a = torch.empty((rows, nv - 1), dtype=f.dtype, device=f.device)
+    b = torch.empty((rows, nv), dtype=f.dtype, device=f.device)
+    c = torch.empty((rows, nv - 1), dtype=f.dtype, device=f.device)
+    _lib.check(_lib.lib().vpfp_fp_diagonals(f.data_ptr(), ld, v.data_ptr(), float(nu), float(dt), float(dv), FP_OPS[op],
+                                            a.data_ptr(), nv - 1, b.data_ptr(), nv, c.data_ptr(), nv - 1, rows, nv,
+                                            _stream()))
+    return a, b, c
+
+
+def tridiag_solve(a, b, c, d, out=None):
+    """vlapy/core/collisions.py:232-263 on device: one tridiagonal system per row, general diagonals.
+    a, c: (rows, nv-1); b, d: (rows, nv); returns a new (rows, nv) tensor."""
+    rows, ldd = _chk_f(d, "d")
+    nv = d.shape[-1]
+    for t, n, name in ((a, nv - 1, "a"), (b, nv, "b"), (c, nv - 1, "c")):
+        if not (isinstance(t, torch.Tensor) and t.is_cuda and t.dtype == torch.float64 and t.dim() == 2
+                and t.shape == (rows, n) and t.stride(1) == 1):
+            raise ValueError("%s must be a CUDA float64 tensor of shape (%d, %d) with a contiguous last axis" % (name, rows, n))
+    if out is None:
+        out = torch.empty((rows, nv), dtype=d.dtype, device=d.device)
+    _, ldx = _chk_f(out, "out")
+    _lib.check(_lib.lib().vpfp_tridiag_solve(a.data_ptr(), a.stride(0), b.data_ptr(), b.stride(0), c.data_ptr(),
+                                             c.stride(0), d.data_ptr(), ldd, out.data_ptr(), ldx, rows, nv, _stream()))
+    return out
+
+
 def xmodes(f, nmodes=2, out=None, x_offset=0, nx_total=None):
     """fft_x(f)[:nmodes] per v as (batch, nmodes, ncols) complex128 (vlapy/core/step.py:130-135).
     With x_offset / nx_total: the partial sums of an x-slab of a larger grid."""

@@ -302,7 +302,8 @@ def get_sharded_inner_loop_stepper(all_params, stuff_for_time_loop, steps_in_loo
     topo = vd.Topology(nx, nv)
     factory = all_params["backend"].get("shard_backend")
     fp_type = all_params["fokker-planck"]["type"]
-    backend = factory(topo, stuff_for_time_loop, fp_type) if factory else vd.DeviceBackend(topo, stuff_for_time_loop, fp_type)
+    backend = factory(topo, stuff_for_time_loop, fp_type) if factory else vd.DeviceBackend(
+        topo, stuff_for_time_loop, fp_type, peer_scatter=all_params["backend"].get("peer_scatter", True))
     one_step = vd.get_sharded_timestep(all_params, stuff_for_time_loop, topo, backend=backend)
     gather = all_params["backend"].get("gather", "rank0")
     if gather not in ("rank0", "slab"):
