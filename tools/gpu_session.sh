@@ -52,7 +52,7 @@ for st in "$@"; do
       SEL="test_fp_sizes_vs_oracle and 4096 or test_single_pass_row_kernel and 257 or test_vdfdx_fused_density and 4096 or test_cluster_vdfdx and small or test_tridiag"
       ( timeout 900 compute-sanitizer --tool racecheck --racecheck-report all --print-limit 20 python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "$SEL" 2>&1 | tail -40 ) > ${O}_racecheck.txt
       ( timeout 900 compute-sanitizer --tool memcheck --print-limit 20 python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "$SEL" 2>&1 | tail -25 ) > ${O}_memcheck.txt
-      tail -4 ${O}_racecheck.txt ${O}_memcheck.txt ;;
+      tail -n 4 ${O}_racecheck.txt; tail -n 4 ${O}_memcheck.txt ;;
     fp64peak)
       timeout 120 python tools/fp64_peak.py > ${O}_fp64_peak.txt 2>&1; cat ${O}_fp64_peak.txt ;;
     smoke)
