@@ -88,6 +88,18 @@ int vpfp_vdfdx_exp_density(const double *f_in, long ld_in, double *f_out, long l
 int vpfp_edfdv_cd2(const double *f_in, long ld_in, double *f_out, long ld_out, const double *e,
                    double dt, double dv, int rows, int nv, void *stream);
 
+/* Semi-Lagrangian advection (backward characteristics + cubic-spline interpolation).
+ * vpfp_vdfdx_sl replaces vlapy/core/vlasov.py:42-80 (get_vdfdx_sl): f_out[i, j] = S_j(x_i - v_j dt) with S_j the
+ *   not-a-knot cubic spline of column j padded with one periodic ghost row on either side; feet outside the padded
+ *   axis are clamped to its ends (what scipy's RectBivariateSpline / FITPACK does for the reference).
+ * vpfp_edfdv_sl replaces vlapy/core/vlasov.py:168-210 (get_edfdv_sl): f_out[i, j] = S_i(v_j - e_i dt) along v.
+ * x: (nx), v: (nv) the axes (uniform, spacing dx / dv = ax[2] - ax[1] as the reference takes it); e: (nx).
+ * nx >= 4; 10 <= nv <= 16386 for the v direction.  Uses library scratch of (nx + 2) * nv doubles. */
+int vpfp_vdfdx_sl(const double *f_in, long ld_in, double *f_out, long ld_out, const double *x, const double *v,
+                  double dt, double dx, int nx, int nv, void *stream);
+int vpfp_edfdv_sl(const double *f_in, long ld_in, double *f_out, long ld_out, const double *e, const double *v,
+                  double dt, double dv, int nx, int nv, void *stream);
+
 /* v-moments per row: out[k*out_ld + row], k = 0..nmom-1:
  *   k<6: trapz_v(f v^k)   (n, j, T, q, fv4, vN; vlapy/core/step.py:164-171, field.py:27-36)
  *   k=6: trapz_v(f^2), k=7: trapz_v(f ln f)   (step.py:216-224; NaN where f <= 0 like numpy)
@@ -125,7 +137,7 @@ int vpfp_fp_step_linspace(const double *f_in, long ld_in, double *f_out, long ld
  * vpfp_tridiag_solve: x = solve(tridiag(a, b, c), d) per row, general diagonals, no pivoting; replaces
  *   vlapy/core/collisions.py:222-265 (_batched_tridiag_solver_ behind get_matrix_solver :268-289).
  *   a[i-1] couples row i to x[i-1], c[i] couples row i to x[i+1] (the reference's storage). 8 <= nv <= 16384.
- *   x may alias d. */
+ *   x may alias d.  A pitch of 0 for a, b or c broadcasts one set of diagonals to every row. */
 int vpfp_fp_diagonals(const double *f, long ld, const double *v, double nu, double dt, double dv, int op,
                       double *a, long lda, double *b, long ldb, double *c, long ldc, int rows, int nv,
                       void *stream);

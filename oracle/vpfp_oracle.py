@@ -149,6 +149,106 @@ def edfdv_cd2(f, e, dt, dv):
 
 
 # --------------------------------------------------------------------------------------------
+# N4: semi-Lagrangian advection operators  (vlapy/core/vlasov.py:27-80, 168-210)
+# --------------------------------------------------------------------------------------------
+
+
+def padded_grid(ax):
+    """vlasov.py:27-39 -- the axis with one periodic ghost point on either side (spacing ax[2] - ax[1])."""
+    ax_pad = np.zeros(ax.size + 2)
+    ax_pad[1:-1] = ax
+    ax_pad[0] = ax[0] - (ax[2] - ax[1])
+    ax_pad[-1] = ax[-1] + (ax[2] - ax[1])
+    return ax_pad
+
+
+def vdfdx_sl(f, dt, x, v):
+    """vlasov.py:42-80 -- backward semi-Lagrangian x advection: bicubic RectBivariateSpline of f padded with ONE
+    periodic ghost row on either side, evaluated at (x - v dt, v); FITPACK clamps points outside the padded
+    axis to its ends (bispeu -> fpbisp), so shifts beyond one cell are not periodic."""
+    from scipy import interpolate
+    xm, vm = np.meshgrid(x, v, indexing="ij")
+    xm, vm = xm.flatten(), vm.flatten()
+    f_pad = np.zeros((x.size + 2, v.size))
+    f_pad[1:-1, :] = f
+    f_pad[0, :] = f[-1, :]
+    f_pad[-1, :] = f[0, :]
+    interp = interpolate.RectBivariateSpline(padded_grid(x), v, f_pad)
+    return interp(xm - vm * dt, vm, grid=False).reshape((x.size, v.size))
+
+
+def edfdv_sl(f, e, dt, x, v):
+    """vlasov.py:168-210 -- backward semi-Lagrangian v advection: the field is passed through a cubic interp1d
+    evaluated at its own nodes, f is padded with one periodic ghost column on either side and the bicubic spline
+    is evaluated at (x, v - e dt)."""
+    from scipy import interpolate
+    xm, vm = np.meshgrid(x, v, indexing="ij")
+    xm, vm = xm.flatten(), vm.flatten()
+    f_pad = np.zeros((x.size, v.size + 2))
+    f_pad[:, 1:-1] = f
+    f_pad[:, 0] = f[:, -1]
+    f_pad[:, -1] = f[:, 0]
+    em = interpolate.interp1d(x, e, kind="cubic")(xm)
+    interp = interpolate.RectBivariateSpline(x, padded_grid(v), f_pad)
+    return interp(xm, vm - em * dt, grid=False).reshape((x.size, v.size))
+
+
+def nak_spline_shift(y, ax, shift):
+    """What the two operators above reduce to, line by line (the algorithm of csrc/spline.h): the bicubic
+    interpolating spline restricted to a grid line of the OTHER axis is the 1-D not-a-knot cubic spline of that line
+    (tensor-product interpolation), so every line y (last axis, already padded with its two ghost points, uniform
+    spacing h = ax[2] - ax[1]) is interpolated on its own and evaluated at ax[1:-1] - shift, clamped to
+    [ax[0], ax[-1]].  Not-a-knot on a uniform grid: M_0 - 2 M_1 + M_2 = 0 turns the first interior equation into
+    6 M_1 = r_1 (likewise at the other end), the rest is the (1, 4, 1) system in the second derivatives M.
+    y: (..., n + 2); shift: broadcastable to (..., n)."""
+    n2 = y.shape[-1]
+    h = ax[2] - ax[1]
+    r = 6.0 * (y[..., 2:] - 2.0 * y[..., 1:-1] + y[..., :-2]) / (h * h)          # r_1 .. r_{n2-2}
+    M = np.zeros_like(y)
+    M[..., 1] = r[..., 0] / 6.0
+    M[..., n2 - 2] = r[..., -1] / 6.0
+    m = n2 - 4                                                                    # unknowns M_2 .. M_{n2-3}
+    if m > 0:
+        rhs = r[..., 1:-1].copy()
+        rhs[..., 0] -= M[..., 1]
+        rhs[..., -1] -= M[..., n2 - 2]
+        cp = np.zeros(m)
+        dp = np.zeros(rhs.shape)
+        cp[0] = 1.0 / 4.0
+        dp[..., 0] = rhs[..., 0] / 4.0
+        for k in range(1, m):
+            den = 4.0 - cp[k - 1]
+            cp[k] = 1.0 / den
+            dp[..., k] = (rhs[..., k] - dp[..., k - 1]) / den
+        M[..., n2 - 3] = dp[..., m - 1]
+        for k in range(m - 2, -1, -1):
+            M[..., k + 2] = dp[..., k] - cp[k] * M[..., k + 3]
+    M[..., 0] = 2.0 * M[..., 1] - M[..., 2]
+    M[..., n2 - 1] = 2.0 * M[..., n2 - 2] - M[..., n2 - 3]
+    xq = np.clip(ax[1:-1] - shift, ax[0], ax[-1])
+    c = np.clip(np.floor((xq - ax[0]) / h).astype(np.int64), 0, n2 - 2)
+    s = (xq - (ax[0] + c * h)) / h
+    yc, yn = np.take_along_axis(y, c, -1), np.take_along_axis(y, c + 1, -1)
+    Mc, Mn = np.take_along_axis(M, c, -1), np.take_along_axis(M, c + 1, -1)
+    u = 1.0 - s
+    return u * yc + s * yn + (h * h / 6.0) * ((u * u * u - u) * Mc + (s * s * s - s) * Mn)
+
+
+def vdfdx_sl_lines(f, dt, x, v):
+    """vdfdx_sl through nak_spline_shift (one spline per v column along the padded x axis)."""
+    fp = np.concatenate([f[-1:, :], f, f[:1, :]], axis=0).T                      # (nv, nx + 2)
+    shift = np.broadcast_to((v * dt)[:, None], (v.size, x.size))
+    return nak_spline_shift(np.ascontiguousarray(fp), padded_grid(x), shift).T
+
+
+def edfdv_sl_lines(f, e, dt, x, v):
+    """edfdv_sl through nak_spline_shift (one spline per x row along the padded v axis)."""
+    fp = np.concatenate([f[:, -1:], f, f[:, :1]], axis=1)                        # (nx, nv + 2)
+    shift = np.broadcast_to((e * dt)[:, None], (x.size, v.size))
+    return nak_spline_shift(fp, padded_grid(v), shift)
+
+
+# --------------------------------------------------------------------------------------------
 # A3/A4: charge density and spectral Poisson  (vlapy/core/field.py)
 # --------------------------------------------------------------------------------------------
 
@@ -294,7 +394,7 @@ def schedule(name, dt):
 
 
 def vp_step(e, f, t, *, integrator, dt, kx, kv, v, dv, one_over_kx, driver_function,
-            edfdv="exponential"):
+            edfdv="exponential", vdfdx="exponential", x=None):
     """One Vlasov-Poisson step (e, f, t) -> (e, f).  Every x sub-step is followed by a field
     solve at the scheduled driver time (vlasov_poisson.py:54-55, 115-116, 205-206)."""
     for sub in schedule(integrator, dt):
@@ -303,10 +403,17 @@ def vp_step(e, f, t, *, integrator, dt, kx, kv, v, dv, one_over_kx, driver_funct
                 f = edfdv_exponential(f, e, sub[1], kv)
             elif edfdv == "cd2":
                 f = edfdv_cd2(f, e, sub[1], dv)
+            elif edfdv == "sl":
+                f = edfdv_sl(f, e, sub[1], x, v)
             else:
                 raise NotImplementedError(edfdv)
         else:
-            f = vdfdx_exponential(f, sub[1], kx, v)
+            if vdfdx == "exponential":
+                f = vdfdx_exponential(f, sub[1], kx, v)
+            elif vdfdx == "sl":
+                f = vdfdx_sl(f, sub[1], x, v)
+            else:
+                raise NotImplementedError(vdfdx)
             td = t
             for inc in sub[2]:
                 td = td + inc
@@ -413,14 +520,14 @@ def nlepw_config(nx=256, nv=2048, k0=0.35, log_nu=-4):
 
 
 def run_steps(cfg, nsteps, integrator="leapfrog", fp_operator="lb", edfdv="exponential",
-              collect=False):
+              collect=False, vdfdx="exponential"):
     """Drive ``nsteps`` full timesteps from the config's initial state the way
     outer_loop.py:265-272 + step.py:302-326 do (time of step i is i*dt, driver row is the
     driver at that time)."""
     e, f = cfg["e0"].copy(), cfg["f0"].copy()
     kw = dict(integrator=integrator, dt=cfg["dt"], kx=cfg["kx"], kv=cfg["kv"], v=cfg["v"],
               dv=cfg["dv"], one_over_kx=cfg["one_over_kx"], driver_function=cfg["driver_function"],
-              edfdv=edfdv)
+              edfdv=edfdv, vdfdx=vdfdx, x=cfg["x"])
     hist = {"e": [], "mom": [], "series": []}
     for i in range(nsteps):
         t = cfg["dt"] * i

@@ -12,7 +12,7 @@ CSRC = os.path.join(os.path.dirname(os.path.dirname(HERE)), "vlapy_b200", "csrc"
 
 
 def build(force=False):
-    deps = [SRC] + [os.path.join(CSRC, n) for n in ("advect.h", "rowops.h", "tridiag.h", "vpfp_common.h", "butterflies.h", "rowfft.cuh")]
+    deps = [SRC] + [os.path.join(CSRC, n) for n in ("advect.h", "rowops.h", "tridiag.h", "spline.h", "vpfp_common.h", "butterflies.h", "rowfft.cuh")]
     if force or not os.path.exists(SO) or any(os.path.getmtime(d) > os.path.getmtime(SO) for d in deps):
         subprocess.check_call(["g++", "-O2", "-ffp-contract=off", "-std=c++17", "-shared", "-fPIC",
                                "-o", SO, SRC])
@@ -146,6 +146,22 @@ def tridiag_solve(a, b, c, d, m=0):
     x = np.empty_like(d)
     lib().emul_tridiag_solve(_p(a), _p(b), _p(c), _p(d), _p(x), c_int(rows), c_int(nv), c_int(m))
     return x
+
+
+def vdfdx_sl(f, x, v, dt):
+    f = np.ascontiguousarray(f); out = np.empty_like(f); nx, nv = f.shape
+    rc = lib().emul_vdfdx_sl(_p(f), _p(out), _p(np.ascontiguousarray(x)), _p(np.ascontiguousarray(v)), c_double(dt),
+                             c_double(x[2] - x[1]), c_int(nx), c_int(nv))
+    assert rc == 0
+    return out
+
+
+def edfdv_sl(f, e, v, dt):
+    f = np.ascontiguousarray(f); out = np.empty_like(f); nx, nv = f.shape
+    rc = lib().emul_edfdv_sl(_p(f), _p(out), _p(np.ascontiguousarray(e)), _p(np.ascontiguousarray(v)), c_double(dt),
+                             c_double(v[2] - v[1]), c_int(nx), c_int(nv))
+    assert rc == 0
+    return out
 
 
 def xmodes(f, nmodes=2):

@@ -14,6 +14,7 @@
 #include "../../vlapy_b200/csrc/advect.h"
 #include "../../vlapy_b200/csrc/rowops.h"
 #include "../../vlapy_b200/csrc/tridiag.h"
+#include "../../vlapy_b200/csrc/spline.h"
 
 template <class Prog>
 static void run_prog(const Prog& prog, long nblocks, int threads, long smem_bytes, int nph) {
@@ -162,6 +163,60 @@ int emul_tridiag_solve(const double* a, const double* b, const double* c, const 
   int threads = ((p.P + 31) / 32) * 32;
   if (threads > 1024) threads = 1024;
   run_prog(p, rows, threads, p.smem_bytes(threads), p.nphases());
+  return 0;
+}
+
+// semi-Lagrangian operators: launch geometry as vpfp_vdfdx_sl / vpfp_edfdv_sl (vlapy_b200/csrc/vpfp_cuda.cu)
+static std::vector<double> spline_tab(int n) {
+  std::vector<double> h(3 * (size_t)n);
+  double cp = 0.0;
+  for (int k = 0; k < n; ++k) { cp = 1.0 / (4.0 - cp); h[k] = cp; h[n + k] = 1.0; h[2 * (size_t)n + k] = 4.0; }
+  return h;
+}
+
+int emul_vdfdx_sl(const double* f_in, double* f_out, const double* x, const double* v, double dt, double dx, int nx,
+                  int nv) {
+  std::vector<double> M((size_t)(nx + 2) * nv), tab = spline_tab(nx);
+  SplineColSweepProg sw;
+  sw.f = f_in; sw.ld = nv; sw.M = M.data(); sw.ldm = nv; sw.cp = tab.data(); sw.h = dx; sw.nx = nx; sw.nv = nv;
+  run_prog(sw, (nv + 63) / 64, 64, 0, 1);
+  SplineEvalProg<1> ev;
+  ev.f = f_in; ev.ld = nv; ev.M = M.data(); ev.ldm = nv; ev.out = f_out; ev.ld_out = nv;
+  ev.ax = x; ev.c = v; ev.dt = dt; ev.nx = nx; ev.nv = nv; ev.cblocks = (nv + 255) / 256;
+  run_prog(ev, (long)nx * ev.cblocks, 256, 0, 1);
+  return 0;
+}
+
+int emul_tridiag_solve_ld(const double* a, long lda, const double* b, long ldb, const double* c, long ldc,
+                          const double* d, long ldd, double* x, long ldx, int rows, int nv) {
+  TridiagProg p;
+  p.a = a; p.lda = lda; p.b = b; p.ldb = ldb; p.c = c; p.ldc = ldc; p.d = d; p.ldd = ldd; p.x = x; p.ldx = ldx;
+  p.rows = rows; p.nv = nv;
+  int m = nv / 256;
+  if (m < 4) m = 4;
+  if (m > 16) m = 16;
+  p.m = m;
+  p.P = nv / m;
+  int threads = ((p.P + 31) / 32) * 32;
+  if (threads > 1024) threads = 1024;
+  run_prog(p, rows, threads, p.smem_bytes(threads), p.nphases());
+  return 0;
+}
+
+int emul_edfdv_sl(const double* f_in, double* f_out, const double* e, const double* v, double dt, double dv, int nx,
+                  int nv) {
+  if (nv - 2 < 8) return 1;
+  const long ldm = nv + 2;
+  std::vector<double> M((size_t)nx * ldm), tab = spline_tab(nv);
+  SplineRowRhsProg rh;
+  rh.f = f_in; rh.ld = nv; rh.M = M.data(); rh.ldm = ldm; rh.h = dv; rh.nx = nx; rh.nv = nv; rh.cblocks = (nv + 255) / 256;
+  run_prog(rh, (long)nx * rh.cblocks, 256, 0, 1);
+  emul_tridiag_solve_ld(tab.data() + nv, 0, tab.data() + 2 * (long)nv, 0, tab.data() + nv, 0, M.data() + 2, ldm,
+                        M.data() + 2, ldm, nx, nv - 2);
+  SplineEvalProg<0> ev;
+  ev.f = f_in; ev.ld = nv; ev.M = M.data(); ev.ldm = ldm; ev.out = f_out; ev.ld_out = nv;
+  ev.ax = v; ev.c = e; ev.dt = dt; ev.nx = nx; ev.nv = nv; ev.cblocks = (nv + 255) / 256;
+  run_prog(ev, (long)nx * ev.cblocks, 256, 0, 1);
   return 0;
 }
 

@@ -280,7 +280,68 @@ def nlepw_fixture():
     save("nlepw_c2", **out)
 
 
+def sl_fixture():
+    """N4: the reference's semi-Lagrangian operators (vlapy/core/vlasov.py:42-80, 168-210) in isolation on seeded
+    inputs, and the Landau-damping run of tests/test_landau_damping.py with the sl flavours (leapfrog)."""
+    out = {}
+    for tag, nx, nv, k0, seed in (("small", 16, 64, 0.3, 0), ("c1", 32, 512, 0.3, 1)):
+        rng = np.random.default_rng(seed)
+        xmax = 2 * np.pi / k0
+        dx, x, kx, ook = initializers.initialize_spatial_quantities(0.0, xmax, nx)
+        dv, v, kv = initializers.initialize_velocity_quantities(6.4, nv)
+        f = initializers.initialize_distribution(nx, nv, 6.4) * (1.0 + 0.1 * np.sin(k0 * x))[:, None]
+        f = f + 1e-3 * rng.standard_normal((nx, nv))
+        e = 0.05 * np.cos(k0 * x) + 0.01 * rng.standard_normal(nx)
+        out.update({tag + "_f": f, tag + "_e": e, tag + "_x": x, tag + "_v": v})
+        for name, dt in (("a", 0.16), ("b", -0.0106), ("c", 0.9)):          # c: shifts beyond one cell (clamped feet)
+            out["%s_vdfdx_%s" % (tag, name)] = vlasov.get_vdfdx_sl(x=x, v=v)(f, dt)
+            out["%s_edfdv_%s" % (tag, name)] = vlasov.get_edfdv_sl(x=x, v=v)(f, e, dt)
+        out[tag + "_dts"] = np.array([0.16, -0.0106, 0.9])
+    k0 = 0.3
+    for vdfdx, edfdv in (("sl", "exponential"), ("exponential", "sl"), ("sl", "sl")):
+        p = params_for(k0, 32, 512, 80, 500)
+        p["vlasov-poisson"]["time"] = "leapfrog"
+        p["vlasov-poisson"]["vdfdx"] = vdfdx
+        p["vlasov-poisson"]["edfdv"] = edfdv
+        pulse = pulse_for(p, k0, 1e-7, 20)
+        stuff, outs = run_reference(p, pulse)
+        e_hist = np.concatenate([o["e_hist"] for o in outs])
+        tax = np.concatenate([o["time"] for o in outs])
+        rate = llh.get_damping_rate(Shim(e_hist, tax))
+        key = "%s_%s" % (vdfdx, edfdv)
+        out["rate_" + key] = np.array(rate)
+        out["e_final_" + key] = outs[-1]["e"]
+        out["f_final_sub_" + key] = outs[-1]["f"][::2, ::8].copy()
+        print(key, "damping rate", rate, "nu_ld", p["nu_ld"])
+        out["nu_ld"] = np.array(p["nu_ld"])
+    save("sl_ops", **out)
+
+
+def nlepw_series200_fixture():
+    """C2 exactly as run_nlepw.py sizes it (256 x 2048, k0 = 0.35, lb) through the reference's own inner loop for
+    200 steps: the per-step series (SURVEY 8d integrated acceptance: mean_n / mean_T / mean_e2 to 1e-9) and fields
+    at a few steps.  A separate small file so that it can be regenerated alone (about a minute of CPU)."""
+    k0 = 0.35
+    p = params_for(k0, 256, 2048, 1000, 4000, log_nu=-4)
+    pulse = pulse_for(p, k0, 4e-2, 25)
+    stuff, outs = run_reference(p, pulse, steps_in_loop=200, n_loops=1)
+    o = outs[0]
+    out = {"series_" + k: np.asarray(v) for k, v in o["series"].items()}
+    for k in ("e", "n", "T"):
+        out["fields_%s_sub" % k] = o["fields"][k][::20].copy()
+    out["e_final"] = o["e"]
+    out["f_final_sub"] = o["f"][::8, ::16].copy()
+    out["nu"] = np.array(p["nu"])
+    save("nlepw_c2_series200", **out)
+
+
 if __name__ == "__main__":
+    if len(sys.argv) > 2 and sys.argv[2] == "series200":
+        nlepw_series200_fixture()
+        sys.exit(0)
+    if len(sys.argv) > 2 and sys.argv[2] == "sl":
+        sl_fixture()
+        sys.exit(0)
     operator_fixture("ops_small", nx=16, nv=64, k0=0.3, seed=0, noise=1e-3, diagonals=True)
     operator_fixture("ops_c1", nx=32, nv=512, k0=0.3, seed=1, noise=1e-3)
     operator_fixture("ops_white", nx=64, nv=128, k0=0.35, seed=2, noise=0.3)

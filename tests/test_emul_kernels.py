@@ -273,3 +273,23 @@ def test_fp_reg_stiffness_and_nan_semantics():
     out, mom = E.fp_simt(1, g, v, 0.0, 0.1, dv, "lb")
     assert rel_err(out, g) < 1e-15            # nu = 0: identity matrix
     assert np.isfinite(mom[7, 0]) and np.isnan(mom[7, 1])
+
+
+def test_semi_lagrangian_programs_vs_reference():
+    """csrc/spline.h (column sweep, row right-hand sides + tridiag.h solve with broadcast diagonals, evaluation at
+    the clamped feet of the characteristics) against outputs of the REFERENCE's sl operators (golden sl_ops), and at
+    ragged sizes against the oracle"""
+    g = golden("sl_ops")
+    for tag in ("small", "c1"):
+        f, e, x, v = g[tag + "_f"], g[tag + "_e"], g[tag + "_x"], g[tag + "_v"]
+        for name, dt in zip("abc", g[tag + "_dts"]):
+            assert rel_err(E.vdfdx_sl(f, x, v, dt), g["%s_vdfdx_%s" % (tag, name)]) < TOL
+            assert rel_err(E.edfdv_sl(f, e, v, dt), g["%s_edfdv_%s" % (tag, name)]) < TOL
+    rng = np.random.default_rng(3)
+    for nx, nv in ((5, 10), (7, 33), (100, 130)):
+        x, v = np.linspace(0.3, 20.0, nx), np.linspace(-6.0, 6.0, nv)
+        f = np.exp(-v ** 2 / 2)[None, :] * (1 + 0.1 * np.sin(0.3 * x))[:, None] + 1e-3 * rng.standard_normal((nx, nv))
+        e = 0.7 * np.cos(0.3 * x)
+        for dt in (0.2, -1.3):
+            assert rel_err(E.vdfdx_sl(f, x, v, dt), O.vdfdx_sl(f, dt, x, v)) < TOL
+            assert rel_err(E.edfdv_sl(f, e, v, dt), O.edfdv_sl(f, e, dt, x, v)) < TOL

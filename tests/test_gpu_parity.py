@@ -318,6 +318,30 @@ def test_tridiag_general_diagonals_vs_thomas(dev, nv):
                           t[3][:, :4].contiguous())
 
 
+@pytest.mark.parametrize("ncols", [33, 64, 130, 512, 2048])
+@pytest.mark.parametrize("nmom", [1, 6, 8])
+def test_moments_many_short_rows(dev, ncols, nmom):
+    """the warp-per-row moments kernel (>= 1024 rows of <= 2048 cells: ensembles, C4) against the oracle; odd and
+    even column counts (scalar and 16-byte loads), v-slices with and without the global end cells"""
+    from vlapy_b200 import ops
+    rows = 1500
+    rng = np.random.default_rng(ncols + nmom)
+    dv, v, kv = O.velocity_grid(6.4, ncols) if ncols % 2 == 0 else (0.1, np.linspace(-1.6, 1.6, ncols), None)
+    f = np.exp(-v ** 2 / 2)[None, :] * (1 + 0.1 * rng.random((rows, ncols)))
+    fd, vd = torch.from_numpy(f).to(dev), torch.from_numpy(v).to(dev)
+    for edge in (3, 1, 0):
+        w = np.full(ncols, dv)
+        if edge & 1:
+            w[0] *= 0.5
+        if edge & 2:
+            w[-1] *= 0.5
+        got = ops.moments(fd, vd, dv, nmom=nmom, edge_flags=edge).cpu().numpy()
+        assert got.shape == (nmom, rows)
+        for k in range(nmom):
+            ref = (f * v ** k * w).sum(1) if k < 6 else ((f * f * w).sum(1) if k == 6 else (f * np.log(f) * w).sum(1))
+            assert np.max(np.abs(got[k] - ref)) <= 1e-12 * max(np.max(np.abs(ref)), 1e-30), (k, edge)
+
+
 def field_tolerances(cfg, fmax):
     """Per-field absolute tolerance that follows from 1e-12 relative parity on f (norm max|f|):
     a v-moment of order p is a linear functional of f with L1 weight int |v|^p dv, and E is the
@@ -433,6 +457,90 @@ def test_nlepw_c2_40_steps_vs_reference(dev, op):
     assert rel_err(f[::8, ::16], g["f_sub_" + op]) < TOL
     assert abs(f.sum() / float(g["f_sum_" + op]) - 1) < 1e-13
     assert abs(f[100, 1300] / float(g["f_100_1300_" + op]) - 1) < 1e-12
+
+
+def test_nlepw_c2_200_step_series_vs_reference(dev):
+    """SURVEY 8d integrated acceptance: C2 (256 x 2048, run_nlepw.py, lb), 200 steps through the public inner loop;
+    every per-step series (mean_n, mean_j, mean_T, mean_e2, mean_de2, mean_f2, mean_flogf and the cumulative driver
+    energy) against the REFERENCE's own inner loop (golden nlepw_c2_series200) to 1e-9, fields and final state"""
+    g = golden("nlepw_c2_series200")
+    cfg = O.nlepw_config()
+    outs = run_inner_loops(cfg, make_params(cfg, "leapfrog", "lb"), 200, 1)
+    o = outs[0]
+    for k in O.SERIES_KEYS + ("mean_cum_de2", "mean_t_plus_e2_minus_cum_de2", "mean_t_plus_e2_plus_cum_de2"):
+        np.testing.assert_allclose(o["series"][k], g["series_" + k], rtol=1e-9, atol=1e-14, err_msg=k)
+    tol = field_tolerances(cfg, 0.4)
+    for k in ("e", "n", "T"):
+        err = np.max(np.abs(o["fields"][k][::20] - g["fields_%s_sub" % k]))
+        assert err < 10 * tol[k], (k, err, tol[k])        # 200 steps of accumulated rounding
+    assert rel_err(o["e"], g["e_final"]) < 1e-10
+    assert rel_err(o["f"][::8, ::16], g["f_final_sub"]) < 5e-12
+
+
+def test_c3_three_steps_vs_oracle(dev):
+    """BASELINE config 3 (4096 x 4096, collisional NLEPW): three integrated steps through the public inner loop
+    against the oracle on the full grid (the oracle needs ~7 s per step and ~1 GB: the slowest test of the suite)"""
+    cfg = O.nlepw_config(nx=4096, nv=4096)
+    outs = run_inner_loops(cfg, make_params(cfg, "leapfrog", "lb"), 3, 1)
+    e_ref, f_ref, hist = O.run_steps(cfg, 3, "leapfrog", "lb", collect=True)
+    o = outs[0]
+    assert rel_err(o["f"], f_ref) < TOL
+    assert rel_err(o["e"], e_ref) < 1e-10
+    for j, k in enumerate(O.SERIES_KEYS):
+        np.testing.assert_allclose(o["series"][k], hist["series"][:, j], rtol=1e-9, atol=1e-14, err_msg=k)
+    assert np.max(np.abs(o["fields"]["n"] - hist["mom"][:, 0])) < 1e-12
+
+
+def test_semi_lagrangian_operators_vs_reference(dev):
+    """N4: get_vdfdx(stuff, "sl") / get_edfdv(stuff, "sl") (vlapy/core/vlasov.py:42-80, 168-210, 228-260) against
+    outputs of the REFERENCE's own sl operators (golden sl_ops: seeded noisy states, three time steps incl. shifts
+    beyond one cell where FITPACK clamps the feet); numpy in -> numpy out, CUDA in -> CUDA out; larger and ragged
+    grids against the oracle"""
+    from vlapy_b200.core import vlasov
+    g = golden("sl_ops")
+    for tag in ("small", "c1"):
+        f, e, x, v = g[tag + "_f"], g[tag + "_e"], g[tag + "_x"], g[tag + "_v"]
+        stuff = {"x": x, "v": v}
+        vdfdx, edfdv = vlasov.get_vdfdx(stuff, "sl"), vlasov.get_edfdv(stuff, "sl")
+        for name, dt in zip("abc", g[tag + "_dts"]):
+            keep = f.copy()
+            assert rel_err(vdfdx(f, dt), g["%s_vdfdx_%s" % (tag, name)]) < TOL
+            assert rel_err(edfdv(f, e, dt), g["%s_edfdv_%s" % (tag, name)]) < TOL
+            assert np.array_equal(keep, f)
+        out = vdfdx(torch.from_numpy(f).to(dev), 0.16)
+        assert out.is_cuda and rel_err(out.cpu().numpy(), g[tag + "_vdfdx_a"]) < TOL
+    rng = np.random.default_rng(11)
+    for nx, nv in ((7, 33), (100, 130), (512, 2048), (2048, 1000)):
+        x, v = np.linspace(0.3, 20.0, nx), np.linspace(-6.0, 6.0, nv)
+        f = np.exp(-v ** 2 / 2)[None, :] * (1 + 0.1 * np.sin(0.3 * x))[:, None] + 1e-3 * rng.standard_normal((nx, nv))
+        e = 0.7 * np.cos(0.3 * x)
+        stuff = {"x": x, "v": v}
+        for dt in (0.2, -1.3):
+            # np.linspace axes are uniform only to rounding; FITPACK takes the knots as given, the kernels one spacing
+            # (ax[2] - ax[1], as the reference pads): 1e-11 on white-noise states (SURVEY 8f N4: looser parity)
+            assert rel_err(vlasov.get_vdfdx(stuff, "sl")(f, dt), O.vdfdx_sl(f, dt, x, v)) < 1e-11
+            assert rel_err(vlasov.get_edfdv(stuff, "sl")(f, e, dt), O.edfdv_sl(f, e, dt, x, v)) < 1e-11
+    with pytest.raises(NotImplementedError):
+        vlasov.get_vdfdx({"x": x, "v": v, "kx": x}, "weno")
+
+
+@pytest.mark.parametrize("vdfdx,edfdv", [("sl", "exponential"), ("exponential", "sl"), ("sl", "sl")])
+def test_landau_damping_semi_lagrangian(dev, vdfdx, edfdv):
+    """tests/test_landau_damping.py of the reference with the sl flavours (leapfrog, 800 steps through the public
+    inner loop): the reference's own bar on the damping rate, and its own numbers (golden sl_ops)"""
+    g = golden("sl_ops")
+    cfg = O.landau_config()
+    params = make_params(cfg, "leapfrog", edfdv=edfdv)
+    params["vlasov-poisson"]["vdfdx"] = vdfdx
+    outs = run_inner_loops(cfg, params, 400, 2)
+    e_hist = np.concatenate([o["fields"]["e"] for o in outs])
+    tax = np.concatenate([o["time"] for o in outs])
+    rate = O.damping_rate(e_hist, tax)
+    key = "%s_%s" % (vdfdx, edfdv)
+    assert abs(rate - float(g["nu_ld"])) < 1.5e-4
+    assert abs(rate - float(g["rate_" + key])) < 1e-7
+    assert np.max(np.abs(outs[-1]["e"] - g["e_final_" + key])) < 1e-12
+    assert rel_err(outs[-1]["f"][::2, ::8], g["f_final_sub_" + key]) < 1e-10
 
 
 def test_small_collisional_run_through_inner_loop(dev):

@@ -161,3 +161,30 @@ def test_nlepw_c2_40_steps(op):
     assert abs(np.abs(e).max() / known[0] - 1) < 1e-11
     assert abs(e[0] / known[1] - 1) < 1e-11
     assert abs(f[100, 1300] / known[2] - 1) < 1e-12
+
+
+def test_nlepw_c2_200_step_series():
+    """SURVEY 8d integrated acceptance: the per-step series of C2 (256 x 2048, lb) over 200 steps of the REFERENCE's
+    own inner loop (golden nlepw_c2_series200) against the oracle.  ~40 s of CPU."""
+    g = golden("nlepw_c2_series200")
+    cfg = O.nlepw_config()
+    assert abs(cfg["nu"] / float(g["nu"]) - 1) < 1e-14
+    e, f, hist = O.run_steps(cfg, 200, "leapfrog", "lb", collect=True)
+    for j, k in enumerate(O.SERIES_KEYS):
+        np.testing.assert_allclose(hist["series"][:, j], g["series_" + k], rtol=1e-9, atol=1e-14, err_msg=k)
+    assert rel_err(e, g["e_final"]) < 1e-11
+    assert rel_err(f[::8, ::16], g["f_final_sub"]) < TOL
+
+
+def test_semi_lagrangian_operators_match_reference():
+    """N4: the oracle's restatement of vlapy/core/vlasov.py:42-80, 168-210 (the reference's own scipy calls) and the
+    line-by-line not-a-knot spline form the kernels implement (oracle nak_spline_shift), against outputs of the
+    REFERENCE's get_vdfdx_sl / get_edfdv_sl (golden sl_ops)"""
+    g = golden("sl_ops")
+    for tag in ("small", "c1"):
+        f, e, x, v = g[tag + "_f"], g[tag + "_e"], g[tag + "_x"], g[tag + "_v"]
+        for name, dt in zip("abc", g[tag + "_dts"]):
+            assert rel_err(O.vdfdx_sl(f, dt, x, v), g["%s_vdfdx_%s" % (tag, name)]) < 1e-14
+            assert rel_err(O.edfdv_sl(f, e, dt, x, v), g["%s_edfdv_%s" % (tag, name)]) < 1e-14
+            assert rel_err(O.vdfdx_sl_lines(f, dt, x, v), g["%s_vdfdx_%s" % (tag, name)]) < 1e-12
+            assert rel_err(O.edfdv_sl_lines(f, e, dt, x, v), g["%s_edfdv_%s" % (tag, name)]) < 1e-12

@@ -9,7 +9,8 @@
 #   bench:<w>        python bench.py --workload <w>            (1 GPU; w = c1..c5)
 #   benchN:<n>:<w>   torchrun bench.py --gpus n --workload w   (n GPUs)
 #   ops:<list>       tools/time_ops.py 16384 16384 <list>
-#   ab:<list>        the same on libvpfp_b200_base.so (tools/make_ab.py) and on the current build
+#   ab:<list>        the same on the product library and on every vlapy_b200/lib/libvpfp_b200_<name>.so (candidates
+#                    built with -D flags); AB_TESTS=<expr> also runs the parity tests on each candidate
 #   launches         ncu launch list (gpu__time_duration) of a 2-step C5 bench
 #   full:<regex>     ncu --set full --import-source on of the kernels matching <regex> (tools/prof_one.py)
 #   sanitizer        compute-sanitizer racecheck + memcheck on the kernels with barrier-free prefetch / peer stores
@@ -39,8 +40,13 @@ for st in "$@"; do
     ops)
       timeout 300 python tools/time_ops.py 16384 16384 "$arg" > ${O}_ops.txt 2>&1; cat ${O}_ops.txt ;;
     ab)
-      { echo "== base"; VPFP_B200_LIB=$PWD/vlapy_b200/lib/libvpfp_b200_base.so timeout 120 python tools/time_ops.py 16384 16384 "$arg" 2>&1 | tail -8
-        echo "== current"; timeout 120 python tools/time_ops.py 16384 16384 "$arg" 2>&1 | tail -8; } > ${O}_ab.txt; cat ${O}_ab.txt ;;
+      # every vlapy_b200/lib/libvpfp_b200_<name>.so present (candidates built with -D flags) against the product library
+      { echo "== product library"; timeout 120 python tools/time_ops.py 16384 16384 "$arg" 2>&1 | tail -8
+        for so in vlapy_b200/lib/libvpfp_b200_*.so; do
+          [ -f "$so" ] || continue
+          echo "== $so"; VPFP_B200_LIB=$PWD/$so timeout 120 python tools/time_ops.py 16384 16384 "$arg" 2>&1 | tail -8
+          if [ -n "$AB_TESTS" ]; then echo "-- parity tests on $so"; VPFP_B200_LIB=$PWD/$so timeout 300 python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "$AB_TESTS" 2>&1 | tail -2; fi
+        done; } > ${O}_ab.txt; cat ${O}_ab.txt ;;
     launches)
       timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file ${O}_launches.csv \
         python bench.py --steps 2 --warmup 1 --no-e2e --no-cpu > ${O}_launches.log 2>&1

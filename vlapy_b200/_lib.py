@@ -11,7 +11,7 @@ ROOT = os.path.dirname(PKG)
 # VPFP_B200_LIB: another build of the same CUDA library (A/B timing of two revisions in one GPU session)
 SO = os.environ.get("VPFP_B200_LIB") or os.path.join(PKG, "lib", "libvpfp_b200.so")
 SRC = os.path.join(PKG, "csrc", "vpfp_cuda.cu")
-HEADERS = [os.path.join(PKG, "csrc", n) for n in ("vpfp_common.h", "advect.h", "rowops.h", "butterflies.h", "rowfft.cuh", "tridiag.h",
+HEADERS = [os.path.join(PKG, "csrc", n) for n in ("vpfp_common.h", "advect.h", "rowops.h", "butterflies.h", "rowfft.cuh", "tridiag.h", "spline.h",
                                                     "advect_fast.cuh", "fp_fast.cuh", "fp_reg.cuh")] + [
     os.path.join(ROOT, "include", "vpfp_b200.h")]
 
@@ -50,6 +50,8 @@ _SIGS = {
     "vpfp_vdfdx_exp": ([_P, _L, _P, _L, _P, _P, _D, _I, _I, _I, _I, _P], _I),
     "vpfp_vdfdx_exp_density": ([_P, _L, _P, _L, _P, _P, _D, _I, _I, _I, _I, _P, _D, _I, _P], _I),
     "vpfp_edfdv_cd2": ([_P, _L, _P, _L, _P, _D, _D, _I, _I, _P], _I),
+    "vpfp_vdfdx_sl": ([_P, _L, _P, _L, _P, _P, _D, _D, _I, _I, _P], _I),
+    "vpfp_edfdv_sl": ([_P, _L, _P, _L, _P, _P, _D, _D, _I, _I, _P], _I),
     "vpfp_moments": ([_P, _L, _P, _D, _P, _L, _I, _I, _I, _I, _P], _I),
     "vpfp_poisson": ([_P, _P, _P, _P, _I, _I, _P], _I),
     "vpfp_fp_step": ([_P, _L, _P, _L, _P, _D, _D, _D, _I, _P, _L, _I, _I, _P], _I),

@@ -92,11 +92,49 @@ def get_edfdv_center_differenced(dv):
     return step_edfdv_center_difference
 
 
+def _axis_spacing(ax):
+    """the spacing the reference pads with (vlapy/core/vlasov.py:35-37): ax[2] - ax[1]"""
+    ax = np.asarray(ax, dtype=np.float64)
+    if ax.ndim != 1 or ax.size < 4:
+        raise NotImplementedError("<sl> needs a one-dimensional axis of at least four points")
+    return float(ax[2] - ax[1])
+
+
+def get_vdfdx_sl(x, v):
+    """vlapy/core/vlasov.py:42-80 -- backward semi-Lagrangian v df/dx: cubic spline along x through f padded with
+    one periodic ghost row on either side, evaluated at x - v dt (csrc/spline.h)."""
+    x_d, v_d = const(x), const(v)
+    dx = _axis_spacing(x)
+
+    def update_spatial_adv_sl(f, dt):
+        f_d, host = to_dev(f)
+        return back(ops.vdfdx_sl(f_d.contiguous(), x_d, v_d, dt, dx), host)
+
+    return update_spatial_adv_sl
+
+
+def get_edfdv_sl(x, v):
+    """vlapy/core/vlasov.py:168-210 -- backward semi-Lagrangian e df/dv: cubic spline along v, evaluated at
+    v - e dt (the reference's cubic interp1d of e is evaluated at its own nodes, i.e. it returns e)."""
+    v_d = const(v)
+    dv = _axis_spacing(v)
+    _axis_spacing(x)
+
+    def update_velocity_adv_sl(f, e, dt):
+        f_d, host = to_dev(f)
+        e_d, _ = to_dev(e)
+        return back(ops.edfdv_sl(f_d.contiguous(), e_d.contiguous(), v_d, dt, dv), host)
+
+    return update_velocity_adv_sl
+
+
 def get_vdfdx(stuff_for_time_loop, vdfdx_implementation="exponential"):
     """vlapy/core/vlasov.py:213-235."""
     if vdfdx_implementation == "exponential":
         vdfdx = get_vdfdx_exponential(kx=stuff_for_time_loop["kx"], v=stuff_for_time_loop["v"],
                                       dv=stuff_for_time_loop.get("dv"))
+    elif vdfdx_implementation == "sl":
+        vdfdx = get_vdfdx_sl(x=stuff_for_time_loop["x"], v=stuff_for_time_loop["v"])
     else:
         raise NotImplementedError(
             "v df/dx: <" + vdfdx_implementation + "> has not yet been implemented on the b200 backend")
@@ -109,6 +147,8 @@ def get_edfdv(stuff_for_time_loop, edfdv_implementation="exponential"):
         edfdv = get_edfdv_exponential(kv=stuff_for_time_loop["kv"])
     elif edfdv_implementation == "cd2":
         edfdv = get_edfdv_center_differenced(dv=stuff_for_time_loop["dv"])
+    elif edfdv_implementation == "sl":
+        edfdv = get_edfdv_sl(v=stuff_for_time_loop["v"], x=stuff_for_time_loop["x"])
     else:
         raise NotImplementedError(
             "e df/dv: <" + edfdv_implementation + "> has not yet been implemented on the b200 backend")

@@ -33,10 +33,6 @@
 #pragma once
 #include "fp_fast.cuh"
 
-#ifndef FPREG_BULK
-#define FPREG_BULK 1   // next row through cp.async.bulk + mbarrier (TMA unit) instead of per-thread cp.async (LSU)
-#endif
-
 namespace fpreg {
 
 using fpfast::Args;
@@ -61,54 +57,6 @@ __device__ __forceinline__ void cp_async_wait_all() {
   asm volatile("cp.async.wait_group 0;\n" ::: "memory");
 #endif
 }
-// ---- Blackwell/Hopper bulk asynchronous copy (the 1-D form of TMA: cp.async.bulk, SASS UBLKCP) with an mbarrier
-// that counts the arriving bytes (SASS SYNCS).  One instruction moves a whole 256-byte chunk global -> shared
-// through the TMA unit instead of 16 LDGSTS through the load/store unit (host emulation: plain copy, no barrier).
-__device__ __forceinline__ void mbar_init(unsigned long long* bar, int count) {
-#if defined(__CUDA_ARCH__)
-  const unsigned a = (unsigned)__cvta_generic_to_shared(bar);
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(a), "r"(count) : "memory");
-  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-#else
-  (void)bar; (void)count;
-#endif
-}
-__device__ __forceinline__ void mbar_arrive_expect_tx(unsigned long long* bar, unsigned bytes) {
-#if defined(__CUDA_ARCH__)
-  const unsigned a = (unsigned)__cvta_generic_to_shared(bar);
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(a), "r"(bytes) : "memory");
-#else
-  (void)bar; (void)bytes;
-#endif
-}
-__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
-#if defined(__CUDA_ARCH__)
-  const unsigned a = (unsigned)__cvta_generic_to_shared(bar);
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "WAIT_LOOP:\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-      "@p bra WAIT_DONE;\n"
-      "bra WAIT_LOOP;\n"
-      "WAIT_DONE:\n"
-      "}\n" ::"r"(a), "r"(parity) : "memory");
-#else
-  (void)bar; (void)parity;
-#endif
-}
-__device__ __forceinline__ void bulk_g2s(void* smem, const void* gmem, unsigned bytes, unsigned long long* bar) {
-#if defined(__CUDA_ARCH__)
-  const unsigned d = (unsigned)__cvta_generic_to_shared(smem);
-  const unsigned b = (unsigned)__cvta_generic_to_shared(bar);
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-               ::"r"(d), "l"(gmem), "r"(bytes), "r"(b) : "memory");
-#else
-  (void)bar;
-  memcpy(smem, gmem, bytes);
-#endif
-}
-
 __device__ __forceinline__ double2 ld2(const double* p) {     // 16-byte aligned pair
 #if defined(__CUDA_ARCH__)
   return *reinterpret_cast<const double2*>(p);
@@ -164,7 +112,7 @@ struct Geo {
   static constexpr int PITCH = M + 2;                    // doubles per chunk in the staging buffer
   static constexpr int G1 = MI / 3, G2 = (2 * MI) / 3;   // back-substitution groups [0,G1) [G1,G2) [G2,MI)
   static constexpr int PCAP = imax(imax(G1, G2 - G1), MI - G2) + 1;   // N_{lo-1} .. N_{hi-1} of a group
-  static constexpr size_t SMEM = sizeof(double) * (size_t)(T * PITCH + 64 + 8 * T + PCAP * T + 1024 + 2);
+  static constexpr size_t SMEM = sizeof(double) * (size_t)(T * PITCH + 64 + 8 * T + PCAP * T + 1024);
 };
 
 // ln x = e ln2 + ln c_i + log1p(r) with a 64-entry table (c_i = 1 + (i + 1/2)/64, |r| < 2^-7) and a
@@ -276,15 +224,9 @@ __global__ void __launch_bounds__(T, (M >= 64 ? 256 : 512) / T) fp_reg_kernel(co
   double* X = red + 64;                                  // 8 * T scratch (separator system / moments)
   volatile double* PV = X + 8 * T;                       // PCAP * T parked pivots (private to a thread)
   double2* LT = reinterpret_cast<double2*>(X + 8 * T + PCAP * T);   // 64 x 8 entries of the log table
-  unsigned long long* const MB = reinterpret_cast<unsigned long long*>(LT + 512);   // mbarrier of the row in flight
   const int t = threadIdx.x;
   const int lane = t & 31, warp = t >> 5;
   for (int i = t; i < 512; i += T) LT[i] = a.logtab64[i >> 3];      // 8 replicas, see log_split
-#if FPREG_BULK
-  if (t == 0) mbar_init(MB, 1);
-  __syncthreads();
-  unsigned mb_phase = 0;
-#endif
   const double2* const LTl = LT + (t & 7);                          // this lane's replica
   const int s = t * M;
   const double vs0 = fma((double)s, a.vstep, a.v0);      // velocity of the chunk's first cell
@@ -295,31 +237,17 @@ __global__ void __launch_bounds__(T, (M >= 64 ? 256 : 512) / T) fp_reg_kernel(co
   // compile-time strides (T is a multiple of U)
   static_assert(T % (M / 2) == 0, "staging layout");
   double* const stage_t = stage + (t / U) * PITCH + 2 * (t % U);
-#if FPREG_BULK
-  // the next row as T bulk copies of one 256-byte chunk each (the staging layout pads every chunk to 272 bytes):
-  // thread t moves ITS chunk with one instruction; thread 0 tells the barrier how many bytes the row has
-  auto prefetch = [&](long r) {
-    if (t == 0) mbar_arrive_expect_tx(MB, (unsigned)(T * M * sizeof(double)));
-    bulk_g2s(stage + t * PITCH, a.fin + r * a.ld_in + (long)t * M, (unsigned)(M * sizeof(double)), MB);
-  };
-#else
   auto prefetch = [&](long r) {
     const double* src = a.fin + r * a.ld_in + 2 * t;
 #pragma unroll
     for (int k = 0; k < U; ++k) cp_async16(stage_t + k * (T / U) * PITCH, src + k * 2 * T);
     cp_async_commit();
   };
-#endif
 
   long r = blockIdx.x;
   if (r < a.rows) prefetch(r);
   for (; r < a.rows; r += gridDim.x) {
-#if FPREG_BULK
-    mbar_wait(MB, mb_phase);
-    mb_phase ^= 1u;
-#else
     cp_async_wait_all();
-#endif
     __syncthreads();
     // ---------------- first moment straight from the staged row (unit weights, np.trapz ends fixed below)
     const double* const sp = stage + t * PITCH;           // this thread's chunk in the staging buffer
@@ -569,10 +497,6 @@ __global__ void __launch_bounds__(T, (M >= 64 ? 256 : 512) / T) fp_reg_kernel(co
       __syncthreads();                                    // every thread is done with the staged row
       const long rn = r + gridDim.x;
       const bool has_next = rn < a.rows;
-#if FPREG_BULK
-      if (has_next) prefetch(rn);                         // one bulk copy per thread: nothing to spread
-#define PF_ONE()
-#else
       const double* nsrc = a.fin + (has_next ? rn : r) * a.ld_in + 2 * t;
       const bool spread = has_next;
       int pf = 0;                                         // compile-time after unrolling: cp.async issued so far
@@ -581,7 +505,6 @@ __global__ void __launch_bounds__(T, (M >= 64 ? 256 : 512) / T) fp_reg_kernel(co
     if (spread) cp_async16(stage_t + pf * (T / U) * PITCH, nsrc + pf * 2 * T);                     \
     ++pf;                                                                                          \
   }
-#endif
 #pragma unroll
       for (int i = G2; i <= L; ++i) {                     // prepare the top group from its parked determinants
         PF_ONE()
@@ -628,9 +551,7 @@ __global__ void __launch_bounds__(T, (M >= 64 ? 256 : 512) / T) fp_reg_kernel(co
       }
       static_assert(MI - 1 >= U, "one cp.async per prepared cell covers the row");
 #undef PF_ONE
-#if !FPREG_BULK
       cp_async_commit();
-#endif
 #pragma unroll
       for (int i = G1 - 1; i >= 0; --i) {
         x = fma(-PV[i * T + t], x, c[i]);

@@ -22,6 +22,7 @@
 #include "rowfft.cuh"
 #include "rowops.h"
 #include "tridiag.h"
+#include "spline.h"
 
 // ------------------------------------------------------------------------------------------
 // error plumbing
@@ -104,11 +105,12 @@ static int launch_prog(const Prog& prog, long nblocks, int threads, long smem, i
 // ------------------------------------------------------------------------------------------
 struct DeviceCache {
   std::map<int, cplx*> tw;
-  void* scratch[4] = {nullptr, nullptr, nullptr, nullptr};   // grow-only, one per purpose
-  size_t scratch_bytes[4] = {0, 0, 0, 0};
+  void* scratch[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};   // grow-only, one per purpose
+  size_t scratch_bytes[5] = {0, 0, 0, 0, 0};
+  std::map<int, double*> spline_tab;   // per n: elimination factors of the (1,4,1) system, then n ones, then n fours
   std::vector<void*> retired;   // outgrown scratch blocks: kept until vpfp_shutdown (a captured CUDA graph may hold them)
 };
-enum { SCR_XMODES = 0, SCR_PHANTOM = 1, SCR_DENSITY = 2, SCR_TRIDIAG = 3 };
+enum { SCR_XMODES = 0, SCR_PHANTOM = 1, SCR_DENSITY = 2, SCR_TRIDIAG = 3, SCR_SPLINE = 4 };
 static std::map<int, DeviceCache> g_cache;
 static std::mutex g_cache_mu;
 
@@ -162,6 +164,26 @@ static int get_scratch(int slot, size_t bytes, void** out) {
     ++g_scratch_generation;
   }
   *out = c.scratch[slot];
+  return VPFP_OK;
+}
+
+// tables of the spline operators (spline.h), cached per device and length n: [0, n) the elimination factors
+// c'_k = 1 / (4 - c'_{k-1}) of the constant (1, 4, 1) system, [n, 2n) ones, [2n, 3n) fours (broadcast diagonals)
+static int get_spline_tab(int n, const double** out) {
+  int dev = 0;
+  CUDA_TRY(cudaGetDevice(&dev));
+  std::lock_guard<std::mutex> lk(g_cache_mu);
+  DeviceCache& c = g_cache[dev];
+  auto it = c.spline_tab.find(n);
+  if (it != c.spline_tab.end()) { *out = it->second; return VPFP_OK; }
+  std::vector<double> h(3 * (size_t)n);
+  double cp = 0.0;
+  for (int k = 0; k < n; ++k) { cp = 1.0 / (4.0 - cp); h[k] = cp; h[n + k] = 1.0; h[2 * (size_t)n + k] = 4.0; }
+  double* d = nullptr;
+  CUDA_TRY(cudaMalloc(&d, sizeof(double) * h.size()));
+  CUDA_TRY(cudaMemcpy(d, h.data(), sizeof(double) * h.size(), cudaMemcpyHostToDevice));
+  c.spline_tab[n] = d;
+  *out = d;
   return VPFP_OK;
 }
 
@@ -575,8 +597,9 @@ int vpfp_shutdown(void) {
     for (auto& t : kv.second.tw) cudaFree(t.second);
     for (int n : {128, 64})
       if (g_logtab.count({kv.first, n})) { cudaFree(g_logtab[{kv.first, n}]); g_logtab.erase({kv.first, n}); }
-    for (int i = 0; i < 4; ++i)
+    for (int i = 0; i < 5; ++i)
       if (kv.second.scratch[i]) cudaFree(kv.second.scratch[i]);
+    for (auto& t : kv.second.spline_tab) cudaFree(t.second);
     for (void* r : kv.second.retired) cudaFree(r);
   }
   g_cache.clear();
@@ -781,6 +804,19 @@ int vpfp_moments(const double* f, long ld, const double* v, double dv, double* o
   MomentsProg p;
   p.f = f; p.ld = ld; p.v = v; p.dv = dv; p.out = out; p.out_ld = out_ld;
   p.nmom = nmom; p.rows = rows; p.ncols = ncols; p.edge_flags = edge_flags;
+  if (ncols <= 2048 && rows >= 1024) {
+    // many short rows: one warp per row (rowops.h moments_warp_kernel)
+    const unsigned grid = (unsigned)((rows + 7) / 8);
+    cudaStream_t st = (cudaStream_t)stream;
+    {
+      ProfScope ps("moments", st);
+      if (nmom == 1) moments_warp_kernel<1><<<grid, 256, 0, st>>>(p);
+      else if (nmom <= 6) moments_warp_kernel<6><<<grid, 256, 0, st>>>(p);
+      else moments_warp_kernel<8><<<grid, 256, 0, st>>>(p);
+    }
+    CUDA_TRY(cudaGetLastError());
+    return VPFP_OK;
+  }
   int threads = 256;
   while (threads > 32 && threads * 2 > ncols) threads >>= 1;
   return launch_prog(p, rows, threads, p.smem_bytes(threads), p.nphases(threads), (cudaStream_t)stream, "moments");
@@ -875,8 +911,8 @@ int vpfp_fp_diagonals(const double* f, long ld, const double* v, double nu, doub
 
 int vpfp_tridiag_solve(const double* a, long lda, const double* b, long ldb, const double* c, long ldc,
                        const double* d, long ldd, double* x, long ldx, int rows, int nv, void* stream) {
-  if (!a || !b || !c || !d || !x || rows <= 0 || nv <= 0 || lda < nv - 1 || ldb < nv || ldc < nv - 1 || ldd < nv ||
-      ldx < nv)
+  if (!a || !b || !c || !d || !x || rows <= 0 || nv <= 0 || (lda != 0 && lda < nv - 1) || (ldb != 0 && ldb < nv) ||
+      (ldc != 0 && ldc < nv - 1) || ldd < nv || ldx < nv)
     return fail(VPFP_ERR_ARG, "vpfp_tridiag_solve: bad argument");
   if (nv < 8 || nv > 16384)
     return fail(VPFP_ERR_UNSUPPORTED, "batched tridiagonal solver needs 8 <= nv <= 16384 on the b200 backend");
@@ -891,6 +927,59 @@ int vpfp_tridiag_solve(const double* a, long lda, const double* b, long ldb, con
   int threads = ((p.P + 31) / 32) * 32;
   if (threads > 1024) threads = 1024;
   return launch_prog(p, rows, threads, p.smem_bytes(threads), p.nphases(), (cudaStream_t)stream, "tridiag_solve");
+}
+
+// ---- semi-Lagrangian operators (spline.h)
+int vpfp_vdfdx_sl(const double* f_in, long ld_in, double* f_out, long ld_out, const double* x, const double* v,
+                  double dt, double dx, int nx, int nv, void* stream) {
+  if (!f_in || !f_out || !x || !v || nx < 4 || nv < 1 || ld_in < nv || ld_out < nv || !(dx > 0.0))
+    return fail(VPFP_ERR_ARG, "vpfp_vdfdx_sl: bad argument (nx >= 4)");
+  cudaStream_t st = (cudaStream_t)stream;
+  void* scr = nullptr;
+  int rc = get_scratch(SCR_SPLINE, sizeof(double) * (size_t)(nx + 2) * nv, &scr);
+  if (rc) return rc;
+  const double* tab = nullptr;
+  rc = get_spline_tab(nx, &tab);
+  if (rc) return rc;
+  SplineColSweepProg sw;
+  sw.f = f_in; sw.ld = ld_in; sw.M = (double*)scr; sw.ldm = nv; sw.cp = tab; sw.h = dx; sw.nx = nx; sw.nv = nv;
+  rc = launch_prog(sw, (nv + 63) / 64, 64, 0, 1, st, "vdfdx.sl");
+  if (rc) return rc;
+  SplineEvalProg<1> ev;
+  ev.f = f_in; ev.ld = ld_in; ev.M = (const double*)scr; ev.ldm = nv; ev.out = f_out; ev.ld_out = ld_out;
+  ev.ax = x; ev.c = v; ev.dt = dt; ev.nx = nx; ev.nv = nv; ev.cblocks = (nv + 255) / 256;
+  return launch_prog(ev, (long)nx * ev.cblocks, 256, 0, 1, st, "vdfdx.sl");
+}
+
+int vpfp_tridiag_solve(const double* a, long lda, const double* b, long ldb, const double* c, long ldc,
+                       const double* d, long ldd, double* x, long ldx, int rows, int nv, void* stream);
+
+int vpfp_edfdv_sl(const double* f_in, long ld_in, double* f_out, long ld_out, const double* e, const double* v,
+                  double dt, double dv, int nx, int nv, void* stream) {
+  if (!f_in || !f_out || !e || !v || nx < 1 || nv < 4 || ld_in < nv || ld_out < nv || !(dv > 0.0))
+    return fail(VPFP_ERR_ARG, "vpfp_edfdv_sl: bad argument (nv >= 4)");
+  if (nv - 2 < 8 || nv - 2 > 16384)
+    return fail(VPFP_ERR_UNSUPPORTED, "e df/dv: <sl> needs 10 <= nv <= 16386 on the b200 backend");
+  cudaStream_t st = (cudaStream_t)stream;
+  void* scr = nullptr;
+  int rc = get_scratch(SCR_SPLINE, sizeof(double) * (size_t)nx * (nv + 2), &scr);
+  if (rc) return rc;
+  const double* tab = nullptr;
+  rc = get_spline_tab(nv, &tab);
+  if (rc) return rc;
+  double* M = (double*)scr;
+  const long ldm = nv + 2;
+  SplineRowRhsProg rh;
+  rh.f = f_in; rh.ld = ld_in; rh.M = M; rh.ldm = ldm; rh.h = dv; rh.nx = nx; rh.nv = nv; rh.cblocks = (nv + 255) / 256;
+  rc = launch_prog(rh, (long)nx * rh.cblocks, 256, 0, 1, st, "edfdv.sl");
+  if (rc) return rc;
+  // (1, 4, 1) systems of all rows in place: unknowns M_2 .. M_{nv-1}; the diagonals are broadcast (pitch 0)
+  rc = vpfp_tridiag_solve(tab + nv, 0, tab + 2 * (long)nv, 0, tab + nv, 0, M + 2, ldm, M + 2, ldm, nx, nv - 2, stream);
+  if (rc) return rc;
+  SplineEvalProg<0> ev;
+  ev.f = f_in; ev.ld = ld_in; ev.M = M; ev.ldm = ldm; ev.out = f_out; ev.ld_out = ld_out;
+  ev.ax = v; ev.c = e; ev.dt = dt; ev.nx = nx; ev.nv = nv; ev.cblocks = (nv + 255) / 256;
+  return launch_prog(ev, (long)nx * ev.cblocks, 256, 0, 1, st, "edfdv.sl");
 }
 
 int vpfp_xmodes_partial(const double* f, long ld, double* out, int nmodes, int batch, int nx, int ncols,

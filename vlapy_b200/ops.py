@@ -184,6 +184,36 @@ def edfdv_cd2(f, e, dt, dv, out=None):
     return out
 
 
+def vdfdx_sl(f, x, v, dt, dx, out=None):
+    """vlapy/core/vlasov.py:42-80 on device: semi-Lagrangian x advection of f (nx, nv); x, v device axes."""
+    _, ld = _chk_f(f)
+    if f.dim() != 2:
+        raise ValueError("the semi-Lagrangian operators take one (nx, nv) grid")
+    nx, nv = f.shape
+    if out is None:
+        out = torch.empty(f.shape, dtype=f.dtype, device=f.device)
+    _, ldo = _chk_f(out, "out")
+    _vec(x, nx, "x"); _vec(v, nv, "v")
+    _lib.check(_lib.lib().vpfp_vdfdx_sl(f.data_ptr(), ld, out.data_ptr(), ldo, x.data_ptr(), v.data_ptr(), float(dt),
+                                        float(dx), nx, nv, _stream()))
+    return out
+
+
+def edfdv_sl(f, e, v, dt, dv, out=None):
+    """vlapy/core/vlasov.py:168-210 on device: semi-Lagrangian v advection of f (nx, nv); e (nx), v (nv)."""
+    _, ld = _chk_f(f)
+    if f.dim() != 2:
+        raise ValueError("the semi-Lagrangian operators take one (nx, nv) grid")
+    nx, nv = f.shape
+    if out is None:
+        out = torch.empty(f.shape, dtype=f.dtype, device=f.device)
+    _, ldo = _chk_f(out, "out")
+    _vec(e, nx, "e"); _vec(v, nv, "v")
+    _lib.check(_lib.lib().vpfp_edfdv_sl(f.data_ptr(), ld, out.data_ptr(), ldo, e.data_ptr(), v.data_ptr(), float(dt),
+                                        float(dv), nx, nv, _stream()))
+    return out
+
+
 def moments(f, v, dv, nmom=8, out=None, edge_flags=3):
     """Rows of v-moments (nmom, rows): n, j, T, q, fv4, vN, int f^2, int f ln f."""
     rows, ld = _chk_f(f)
