@@ -49,9 +49,11 @@ def test_unknown_flavours_raise_like_the_reference():
     with pytest.raises(NotImplementedError):
         vlasov_poisson.get_time_integrator("rk4", None, None, None, {"dt": 0.1, "driver_function": None})
     with pytest.raises(NotImplementedError):
-        vlasov.get_vdfdx({"kx": cfg["kx"], "v": cfg["v"], "x": cfg["x"]}, "sl")
+        vlasov.get_vdfdx({"kx": cfg["kx"], "v": cfg["v"], "x": cfg["x"]}, "weno")
     with pytest.raises(NotImplementedError):
-        vlasov.get_edfdv({"kv": cfg["kv"], "dv": cfg["dv"]}, "sl")
+        vlasov.get_edfdv({"kv": cfg["kv"], "dv": cfg["dv"]}, "upwind")
+    with pytest.raises(NotImplementedError):          # <sl> needs at least four points along the advected axis
+        vlasov._axis_spacing(np.arange(3.0))
     with pytest.raises(NotImplementedError):
         step.get_collision_step({}, {"nu": -1.0})
     with pytest.raises(NotImplementedError):
