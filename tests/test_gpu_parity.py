@@ -540,7 +540,8 @@ def test_landau_damping_semi_lagrangian(dev, vdfdx, edfdv):
     assert abs(rate - float(g["nu_ld"])) < 1.5e-4
     assert abs(rate - float(g["rate_" + key])) < 1e-7
     assert np.max(np.abs(outs[-1]["e"] - g["e_final_" + key])) < 1e-12
-    assert rel_err(outs[-1]["f"][::2, ::8], g["f_final_sub_" + key]) < 1e-10
+    # 1600 spline operators at ~1e-13 each (the line-by-line form against FITPACK's tensor-product solve)
+    assert rel_err(outs[-1]["f"][::2, ::8], g["f_final_sub_" + key]) < 1e-9
 
 
 def test_small_collisional_run_through_inner_loop(dev):
