@@ -12,7 +12,7 @@ CSRC = os.path.join(os.path.dirname(os.path.dirname(HERE)), "vlapy_b200", "csrc"
 
 
 def build(force=False):
-    deps = [SRC] + [os.path.join(CSRC, n) for n in ("advect.h", "rowops.h", "tridiag.h", "spline.h", "vpfp_common.h", "butterflies.h", "rowfft.cuh")]
+    deps = [SRC] + [os.path.join(CSRC, n) for n in ("advect.h", "rowops.h", "tridiag.h", "spline.h", "midfft.cuh", "advect_fast.cuh", "vpfp_common.h", "butterflies.h", "rowfft.cuh")]
     if force or not os.path.exists(SO) or any(os.path.getmtime(d) > os.path.getmtime(SO) for d in deps):
         subprocess.check_call(["g++", "-O2", "-ffp-contract=off", "-std=c++17", "-shared", "-fPIC",
                                "-o", SO, SRC])
@@ -160,6 +160,25 @@ def edfdv_sl(f, e, v, dt):
     f = np.ascontiguousarray(f); out = np.empty_like(f); nx, nv = f.shape
     rc = lib().emul_edfdv_sl(_p(f), _p(out), _p(np.ascontiguousarray(e)), _p(np.ascontiguousarray(v)), c_double(dt),
                              c_double(v[2] - v[1]), c_int(nx), c_int(nv))
+    assert rc == 0
+    return out
+
+
+def midfft_rows(f, e, kv, dt):
+    """single-pass mid-size e df/dv (midfft.cuh), nv in {256, 512, 1024, 2048}"""
+    f = np.ascontiguousarray(f); out = np.empty_like(f); rows, nv = f.shape
+    rc = lib().emul_midfft(c_int(1), _p(f), c_long(nv), _p(out), c_long(nv), _p(np.ascontiguousarray(kv)),
+                           _p(np.ascontiguousarray(e)), c_double(dt), c_int(1), c_int(rows), c_int(nv))
+    assert rc == 0
+    return out
+
+
+def midfft_cols(f, kx, v, dt, batch=1):
+    """single-pass mid-size v df/dx (midfft.cuh), nx in {256, 512, 1024, 2048}; f (batch, nx, ncols)"""
+    f = np.ascontiguousarray(f); out = np.empty_like(f)
+    nx, ncols = f.shape[-2], f.shape[-1]
+    rc = lib().emul_midfft(c_int(0), _p(f), c_long(ncols), _p(out), c_long(ncols), _p(np.ascontiguousarray(kx)),
+                           _p(np.ascontiguousarray(v)), c_double(dt), c_int(batch), c_int(nx), c_int(ncols))
     assert rc == 0
     return out
 

@@ -279,6 +279,53 @@ extern "C" int emul_butterfly(double* xy, int radix, int dir) {
   return 0;
 }
 
+// ---- mid-size single-pass kernels (vlapy_b200/csrc/midfft.cuh): per-thread registers persist across phases
+#include "../../vlapy_b200/csrc/midfft.cuh"
+template <class P>
+static void run_midfft(const P& prog) {
+  std::vector<typename P::Regs> regs((size_t)P::NT);
+  std::vector<unsigned char> smem((size_t)P::SMEM_BYTES + 64);
+  unsigned char* base = smem.data();
+  base += (16 - ((uintptr_t)base & 15)) & 15;
+  const char* oe = getenv("VPFP_EMUL_ORDER");
+  const int order = oe ? atoi(oe) : 0;
+  for (int tid = 0; tid < P::NT; ++tid) prog.init(tid, base);
+  for (long tile = 0; tile < prog.ntiles(); ++tile)
+    for (int ph = 0; ph < P::NPH; ++ph)
+      for (int i = 0; i < P::NT; ++i) {
+        int tid = i;
+        if (order == 1) tid = P::NT - 1 - i;
+        else if (order == 2) tid = (i & 1) ? P::NT / 2 + i / 2 : i / 2;
+        prog.phase(ph, tile, tid, regs[tid], base);
+      }
+}
+
+extern "C" int emul_midfft(int mode, const double* f_in, long ld_in, double* f_out, long ld_out, const double* kvec,
+                           const double* cvec, double dt, int nsim, int nrows_or_nx, int ncols) {
+  midfft::Args a;
+  memset(&a, 0, sizeof(a));
+  int N;
+  if (mode == ADV_COLS) { N = nrows_or_nx; a.nsim = nsim; a.nrows = N; a.nseq = ncols / 2; }
+  else { N = ncols; a.nsim = 1; a.nrows = nrows_or_nx; a.nseq = (nrows_or_nx + 1) / 2; }
+  std::vector<cplx> tw = make_tw(N);
+  a.fin = f_in; a.ld_in = ld_in; a.fout = f_out; a.ld_out = ld_out; a.kvec = kvec; a.cvec = cvec; a.dt = dt;
+  a.tw = tw.data();
+  if (mode == ADV_COLS) {
+    if (N == 256) { midfft::Prog<256, 8, 4, ADV_COLS, 8> p; p.a = a; run_midfft(p); }
+    else if (N == 512) { midfft::Prog<512, 8, 8, ADV_COLS, 8> p; p.a = a; run_midfft(p); }
+    else if (N == 1024) { midfft::Prog<1024, 16, 8, ADV_COLS, 4> p; p.a = a; run_midfft(p); }
+    else if (N == 2048) { midfft::Prog<2048, 16, 16, ADV_COLS, 4> p; p.a = a; run_midfft(p); }
+    else return 1;
+  } else {
+    if (N == 256) { midfft::Prog<256, 8, 4, ADV_ROWS, 8> p; p.a = a; run_midfft(p); }
+    else if (N == 512) { midfft::Prog<512, 8, 8, ADV_ROWS, 8> p; p.a = a; run_midfft(p); }
+    else if (N == 1024) { midfft::Prog<1024, 16, 8, ADV_ROWS, 4> p; p.a = a; run_midfft(p); }
+    else if (N == 2048) { midfft::Prog<2048, 16, 16, ADV_ROWS, 2> p; p.a = a; run_midfft(p); }
+    else return 1;
+  }
+  return 0;
+}
+
 // ---- single-pass row kernel (vlapy_b200/csrc/rowfft.cuh): per-thread registers persist across phases
 #include "../../vlapy_b200/csrc/rowfft.cuh"
 template <class P>

@@ -293,3 +293,34 @@ def test_semi_lagrangian_programs_vs_reference():
         for dt in (0.2, -1.3):
             assert rel_err(E.vdfdx_sl(f, x, v, dt), O.vdfdx_sl(f, dt, x, v)) < TOL
             assert rel_err(E.edfdv_sl(f, e, v, dt), O.edfdv_sl(f, e, dt, x, v)) < TOL
+
+
+@pytest.mark.parametrize("n", [256, 512, 1024, 2048])
+def test_midfft_programs(n, monkeypatch):
+    """midfft.cuh (single-pass mid-size transforms, 16 values per thread, L = R1 x R2 x 8) against the oracle: e df/dv
+    with odd and even row counts, v df/dx with ragged column tiles and per-simulation wavenumbers, both signs of dt,
+    in three thread orders (a race inside a phase would make the result order dependent)"""
+    rng = np.random.default_rng(n)
+    dv, v, kv = O.velocity_grid(6.4, n)
+    f = rng.standard_normal((5, n))
+    f[1] = np.exp(-v ** 2 / 2) * (1 + 1e-3 * rng.standard_normal(n))
+    e = np.array([0.05, -0.7, 1.3, 0.0, 2.5])
+    outs = []
+    for order in ("0", "1", "2"):
+        monkeypatch.setenv("VPFP_EMUL_ORDER", order)
+        for dt in (0.37, -0.066):
+            out = E.midfft_rows(f, e, kv, dt)
+            assert rel_err(out, O.edfdv_exponential(f, e, dt, kv)) < TOL
+            outs.append(out)
+    assert np.array_equal(outs[0], outs[2]) and np.array_equal(outs[0], outs[4])
+    monkeypatch.setenv("VPFP_EMUL_ORDER", "0")
+    assert rel_err(E.midfft_rows(f[:4], e[:4], kv, 0.2), O.edfdv_exponential(f[:4], e[:4], 0.2, kv)) < TOL
+    ncols = 26
+    vv = np.linspace(-6.4, 6.4, ncols)
+    k0s = (0.3, 0.41)
+    kx = np.stack([O.spatial_grid(0.0, 2 * np.pi / k, n)[2] for k in k0s])
+    g = rng.standard_normal((2, n, ncols))
+    for dt in (0.16, -0.05):
+        out = E.midfft_cols(g, kx, vv, dt, batch=2)
+        for s in range(2):
+            assert rel_err(out[s], O.vdfdx_exponential(g[s], dt, kx[s], vv)) < TOL

@@ -544,6 +544,44 @@ def test_landau_damping_semi_lagrangian(dev, vdfdx, edfdv):
     assert rel_err(outs[-1]["f"][::2, ::8], g["f_final_sub_" + key]) < 1e-9
 
 
+@pytest.mark.parametrize("n", [256, 512, 1024, 2048])
+def test_mid_size_single_pass_kernels(dev, n):
+    """midfft.cuh through the C ABI (uniform grids, VPFP_PHASE_TABLE): e df/dv at nv = n (odd row count, a row pitch
+    larger than the row, many tiles) and v df/dx at nx = n (ragged column tile, per-simulation wavenumbers) against the
+    oracle, and against the generic kernels the same call used before (VPFP_FORCE_GENERIC)"""
+    from vlapy_b200 import ops
+    rng = np.random.default_rng(n + 3)
+    dv, v, kv = O.velocity_grid(6.4, n)
+    rows = 301
+    f = np.exp(-v ** 2 / 2)[None, :] * (1 + 0.1 * rng.standard_normal((rows, n)))
+    f[::7] = rng.standard_normal((len(f[::7]), n))
+    e = 0.3 * rng.standard_normal(rows)
+    big = torch.zeros((rows, n + 8), dtype=torch.float64, device=dev)
+    big[:, :n] = torch.from_numpy(f).to(dev)
+    fd, ed, kd = big[:, :n], torch.from_numpy(e).to(dev), torch.from_numpy(kv).to(dev)
+    for dt in (0.125, -0.033):
+        ref = O.edfdv_exponential(f, e, dt, kv)
+        out = ops.edfdv_exp(fd, ed, kd, dt, flags=ops.PHASE_TABLE).cpu().numpy()
+        gen = ops.edfdv_exp(fd, ed, kd, dt, flags=ops.PHASE_TABLE | ops.FORCE_GENERIC).cpu().numpy()
+        assert rel_err(out, ref) < TOL
+        assert rel_err(out, gen) < TOL
+        assert not np.array_equal(out, gen)               # two different kernels really ran
+    ncols = 54
+    vv = np.linspace(-6.4, 6.4, ncols)
+    k0s = (0.3, 0.35, 0.41)
+    kx = np.stack([O.spatial_grid(0.0, 2 * np.pi / k, n)[2] for k in k0s])
+    g = rng.standard_normal((3, n, ncols))
+    gd, kxd, vd = torch.from_numpy(g).to(dev), torch.from_numpy(kx).to(dev), torch.from_numpy(vv).to(dev)
+    nd = torch.zeros((3, n), dtype=torch.float64, device=dev)
+    for dt in (0.16, -0.05):
+        out = ops.vdfdx_exp(gd, kxd, vd, dt, flags=ops.PHASE_TABLE, density_out=nd, dv=0.25).cpu().numpy()
+        for s in range(3):
+            ref = O.vdfdx_exponential(g[s], dt, kx[s], vv)
+            assert rel_err(out[s], ref) < TOL
+            w = np.full(ncols, 0.25); w[0] = w[-1] = 0.125
+            assert np.max(np.abs(nd[s].cpu().numpy() - (ref * w).sum(1))) < 1e-12 * np.abs(ref).max() * ncols
+
+
 def test_small_collisional_run_through_inner_loop(dev):
     """16 x 128 collisional run through two inner loops of the reference (everything the storage
     layer receives: fields, series, stored modes, final state)."""

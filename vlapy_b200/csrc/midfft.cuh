@@ -1,0 +1,298 @@
+// midfft.cuh -- single-pass advection for MID-SIZE transforms, L in {256, 512, 1024, 2048}: the whole packed sequence
+// is transformed, phase-multiplied and transformed back by ONE kernel with 16 complex values per thread in
+// registers, so the operator costs one read and one write of f (16 B/cell).  Serves the grids of BASELINE configs
+// 1, 2 and 4 (C1 32 x 512, C2 256 x 2048, C4 1024 x (256 x 512)):
+//     ROWS  e df/dv, vlapy/core/vlasov.py:123-138, nv = L   (two adjacent rows packed as one complex sequence)
+//     COLS  v df/dx, vlapy/core/vlasov.py:94-108,  nx = L   (two adjacent v-columns packed: one 16-byte load)
+// Before, these sizes took either the generic shared-memory program of advect.h (one launch, but radix-2/4 stages
+// through shared memory: ~1 TB/s) or the three register passes of advect_fast.cuh (48 B/cell).
+//
+// Decomposition L = R1 * R2 * 8, n = n1 (L/R1) + n2 8 + n3, k = k1 + R1 k2 + R1 R2 k3:
+//   stage A: radix-R1 over n1 for fixed r = (n2, n3), twiddle W_L^(r k1)                      -> y[k1][r]
+//   stage B: radix-R2 over n2 for fixed (k1, n3), twiddle W_L^(R1 n3 k2), IN PLACE             -> z[s = k1 + R1 k2][n3]
+//   stage C: radix-8 over n3; a thread owns sub-transforms s and S - s (S = L/8), i.e. BOTH members of every pair
+//            (k, L - k): bin s + S k3 pairs with (S - s) + S (7 - k3); thread 0 owns the self-paired s = 0 and S/2.
+// The pointwise step un-mixes the two packed real channels on the pair (advect_fast.cuh pass 2):
+//   U = Z + conj Z', V = Z - conj Z', X1 = Pa U, X2 = Pb V, Y[k] = X1 + X2, Y[L-k] = conj(X1 - X2), with the phase
+//   factors P(j) = exp(-i phi j) / (2L) = T0[j & 15] T12[j >> 4] from two small tables per channel (phi = (K[1] dt) c,
+//   the reference's two roundings; uniform fftfreq grids: VPFP_PHASE_TABLE).  The Nyquist factor keeps its real part
+//   (np.real of the reference).
+// The kernel body is a phase program whose per-thread registers persist across barriers (as rowfft.cuh); tests/emul
+// runs the same source thread by thread on the host.
+#pragma once
+#include "advect.h"
+#include "butterflies.h"
+
+namespace midfft {
+
+using fast::fft8;
+using fast::fftR;
+
+struct Args {
+  int nsim, nseq, nrows;     // COLS: nseq = ncols / 2 per simulation; ROWS: nrows rows, nseq = ceil(nrows / 2)
+  const double* fin; long ld_in;
+  double* fout; long ld_out;
+  const double* kvec;        // COLS: [nsim][L]; ROWS: [L]   (only K[1] is used)
+  const double* cvec;        // COLS: v[ncols]; ROWS: e[nrows]
+  double dt;
+  const cplx* tw;            // exp(-2 pi i m / L), L entries
+};
+
+template <int L_, int R1_, int R2_, int MODE_, int CB_>
+struct Prog {
+  static constexpr int L = L_, R1 = R1_, R2 = R2_, MODE = MODE_, CB = CB_;
+  static_assert(R1 * R2 * 8 == L, "L = R1 * R2 * 8");
+  static constexpr int S = L / 8;              // stage-C sub-transforms
+  static constexpr int TPC = L / 16;           // threads per sequence
+  static constexpr int NT = CB * TPC;          // threads per CTA
+  static constexpr int LA = L / R1;            // points per k1 row
+  static constexpr int PITCH = LA + 1;         // odd pitch (in 16-byte units) of a k1 row
+  static constexpr int XELEMS = R1 * PITCH;    // exchange buffer of one sequence
+  static constexpr int NQA = 16 / R1, NQB = 16 / R2;
+  static constexpr int NT12 = L / 32 + 1;      // table over j >> 4, j = 0 .. L/2
+  static constexpr int NPH = 5;
+  static constexpr long SMEM_BYTES = (long)sizeof(cplx) * ((long)XELEMS * CB + L + 2L * CB * (16 + NT12));
+
+  struct Regs {
+    cplx x[16];
+  };
+
+  Args a;
+
+  VPFP_HD long ntiles() const {
+    const long tb = (a.nseq + CB - 1) / CB;
+    return (MODE == ADV_COLS) ? (long)a.nsim * tb : tb;
+  }
+  VPFP_HD static cplx* xbuf(unsigned char* smem) { return reinterpret_cast<cplx*>(smem); }
+  VPFP_HD static cplx* twl(unsigned char* smem) { return xbuf(smem) + (long)XELEMS * CB; }
+  VPFP_HD static cplx* t0(unsigned char* smem) { return twl(smem) + L; }               // [2][CB][16]
+  VPFP_HD static cplx* t12(unsigned char* smem) { return t0(smem) + 2 * CB * 16; }     // [2][CB][NT12]
+  // exchange-buffer index of slot `slot` of sequence b: lanes run along b (COLS) or along the slot (ROWS)
+  VPFP_HD static int xi(int b, int slot) { return (MODE == ADV_COLS) ? slot * CB + b : b * XELEMS + slot; }
+  VPFP_HD static void roles(int tid, int* b, int* u) {
+    if (MODE == ADV_COLS) { *b = tid % CB; *u = tid / CB; }
+    else { *u = tid % TPC; *b = tid / TPC; }
+  }
+
+  // once per CTA: the twiddle table
+  VPFP_HD void init(int tid, unsigned char* smem) const {
+    cplx* TW = twl(smem);
+    for (int j = tid; j < L; j += NT) TW[j] = a.tw[j];
+  }
+
+  struct Tile {
+    int sim, seq0;
+  };
+  VPFP_HD Tile decode(long tile) const {
+    Tile t;
+    const long tb = (a.nseq + CB - 1) / CB;
+    t.sim = (MODE == ADV_COLS) ? (int)(tile / tb) : 0;
+    t.seq0 = (int)(tile % tb) * CB;
+    return t;
+  }
+  // advection constants of the two packed channels of sequence seq
+  VPFP_HD void consts(int seq, double* ca, double* cb) const {
+    const long ra = 2 * (long)seq, rb = ra + 1;
+    *ca = 0.0; *cb = 0.0;
+    if (seq >= a.nseq) return;
+    *ca = a.cvec[ra];
+    if (MODE == ADV_COLS || rb < a.nrows) *cb = a.cvec[rb];
+  }
+
+  VPFP_HD cplx gload(const Tile& t, int seq, int n) const {
+    if (seq >= a.nseq) return cmake(0.0, 0.0);
+    if (MODE == ADV_COLS) {
+      const double* p = a.fin + ((long)t.sim * L + n) * a.ld_in + 2L * seq;
+#if defined(__CUDA_ARCH__)
+      const double2 v2 = *reinterpret_cast<const double2*>(p);
+      return cmake(v2.x, v2.y);
+#else
+      return cmake(p[0], p[1]);
+#endif
+    }
+    const long ra = 2 * (long)seq, rb = ra + 1;
+    return cmake(a.fin[ra * a.ld_in + n], (rb < a.nrows) ? a.fin[rb * a.ld_in + n] : 0.0);
+  }
+  VPFP_HD void gstore(const Tile& t, int seq, int n, cplx v) const {
+    if (seq >= a.nseq) return;
+    if (MODE == ADV_COLS) {
+      double* p = a.fout + ((long)t.sim * L + n) * a.ld_out + 2L * seq;
+#if defined(__CUDA_ARCH__)
+      *reinterpret_cast<double2*>(p) = make_double2(v.x, v.y);
+#else
+      p[0] = v.x; p[1] = v.y;
+#endif
+      return;
+    }
+    const long ra = 2 * (long)seq, rb = ra + 1;
+    a.fout[ra * a.ld_out + n] = v.x;
+    if (rb < a.nrows) a.fout[rb * a.ld_out + n] = v.y;
+  }
+
+  // one (k, L-k) pair: Zr = Z[kbin], Zpr = Z[L-kbin] in; the phase-multiplied, re-packed pair out
+  VPFP_HD static void pair_op(cplx& Zr, cplx& Zpr, const int kbin, const bool selfpair, const cplx* T0a, const cplx* T0b,
+                              const cplx* T12a, const cplx* T12b) {
+    const bool neg = (2 * kbin > L);
+    const bool nyq = (2 * kbin == L);
+    const int j = neg ? L - kbin : kbin;                 // |signed frequency index|, 0 .. L/2
+    cplx Pa = cmul(T0a[j & 15], T12a[j >> 4]);
+    cplx Pb = cmul(T0b[j & 15], T12b[j >> 4]);
+    if (neg) { Pa = cconj(Pa); Pb = cconj(Pb); }
+    if (nyq) { Pa.y = 0.0; Pb.y = 0.0; }
+    const cplx Z = Zr, Zp = Zpr;
+    const cplx U = cadd(Z, cconj(Zp)), V = csub(Z, cconj(Zp));
+    const cplx X1 = cmul(Pa, U), X2 = cmul(Pb, V);
+    Zr = cadd(X1, X2);
+    if (!selfpair) Zpr = cconj(csub(X1, X2));
+  }
+
+  VPFP_HD void phase(int ph, long tile, int tid, Regs& r, unsigned char* smem) const {
+    cplx* X = xbuf(smem);
+    const cplx* TW = twl(smem);
+    cplx* x = r.x;
+    int b, u;
+    roles(tid, &b, &u);
+    const Tile t = decode(tile);
+    const int seq = t.seq0 + b;
+    switch (ph) {
+      case 0: {
+        // ---- phase tables of this tile: T0[j] = exp(-i phi j) / (2L), j < 16; T12[i] = exp(-i phi 16 i)
+        const double* K = a.kvec + ((MODE == ADV_COLS) ? (long)t.sim * L : 0);
+        const double kdt = mul_rn(K[1], a.dt);
+        cplx* T0 = t0(smem);
+        cplx* T12 = t12(smem);
+        constexpr int PER = 16 + NT12;
+        for (int w = tid; w < 2 * CB * PER; w += NT) {
+          const int i = w % PER, cb_ = (w / PER) % CB, ch = w / (PER * CB);
+          double ca, cbv;
+          consts(t.seq0 + cb_, &ca, &cbv);
+          const double phi = mul_rn(kdt, ch ? cbv : ca);
+          const double j = (i < 16) ? (double)i : 16.0 * (double)(i - 16);
+          double sn, cs;
+          sincos_hd(phi * j, &sn, &cs);
+          if (i < 16) T0[(ch * CB + cb_) * 16 + i] = cmake(cs * (0.5 / (double)L), -sn * (0.5 / (double)L));
+          else T12[(ch * CB + cb_) * NT12 + (i - 16)] = cmake(cs, -sn);
+        }
+        // ---- stage A: radix-R1 over n1 for r = u + TPC q
+#pragma unroll
+        for (int q = 0; q < NQA; ++q) {
+          const int rr = u + TPC * q;
+#pragma unroll
+          for (int n1 = 0; n1 < R1; ++n1) x[q * R1 + n1] = gload(t, seq, n1 * LA + rr);
+        }
+#pragma unroll
+        for (int q = 0; q < NQA; ++q) {
+          const int rr = u + TPC * q;
+          fftR<R1, -1>(x + q * R1);
+#pragma unroll
+          for (int k1 = 1; k1 < R1; ++k1) x[q * R1 + k1] = cmul(x[q * R1 + k1], TW[rr * k1]);
+#pragma unroll
+          for (int k1 = 0; k1 < R1; ++k1) X[xi(b, k1 * PITCH + rr)] = x[q * R1 + k1];
+        }
+      } break;
+      case 1: {
+        // ---- stage B, in place: radix-R2 over n2 for (k1, n3) = c = u + TPC q
+#pragma unroll
+        for (int q = 0; q < NQB; ++q) {
+          const int c = u + TPC * q, k1 = c >> 3, n3 = c & 7;
+#pragma unroll
+          for (int n2 = 0; n2 < R2; ++n2) x[q * R2 + n2] = X[xi(b, k1 * PITCH + n2 * 8 + n3)];
+          fftR<R2, -1>(x + q * R2);
+#pragma unroll
+          for (int k2 = 1; k2 < R2; ++k2) x[q * R2 + k2] = cmul(x[q * R2 + k2], TW[n3 * k2 * R1]);
+#pragma unroll
+          for (int k2 = 0; k2 < R2; ++k2) X[xi(b, k1 * PITCH + k2 * 8 + n3)] = x[q * R2 + k2];
+        }
+      } break;
+      case 2: {
+        // ---- stage C for the sub-transforms sA, sB of this thread, pointwise on the pairs, inverse stage C
+        const bool special = (u == 0);
+        const int sA = special ? 0 : u, sB = special ? S / 2 : S - u;
+        const int slotA = (sA % R1) * PITCH + (sA / R1) * 8, slotB = (sB % R1) * PITCH + (sB / R1) * 8;
+#pragma unroll
+        for (int n3 = 0; n3 < 8; ++n3) {
+          x[n3] = X[xi(b, slotA + n3)];
+          x[8 + n3] = X[xi(b, slotB + n3)];
+        }
+        fft8<-1>(x);
+        fft8<-1>(x + 8);
+        const cplx* T0a = t0(smem) + (0 * CB + b) * 16;
+        const cplx* T0b = t0(smem) + (1 * CB + b) * 16;
+        const cplx* T12a = t12(smem) + (0 * CB + b) * NT12;
+        const cplx* T12b = t12(smem) + (1 * CB + b) * NT12;
+        if (!special) {
+          // A[k3] (bin sA + S k3) pairs with B[7 - k3]
+#pragma unroll
+          for (int pr = 0; pr < 8; ++pr) pair_op(x[pr], x[15 - pr], sA + S * pr, false, T0a, T0b, T12a, T12b);
+        } else {
+          pair_op(x[0], x[0], 0, true, T0a, T0b, T12a, T12b);                       // DC
+          pair_op(x[4], x[4], S * 4, true, T0a, T0b, T12a, T12b);                   // Nyquist
+#pragma unroll
+          for (int pr = 1; pr < 4; ++pr) pair_op(x[pr], x[8 - pr], S * pr, false, T0a, T0b, T12a, T12b);
+#pragma unroll
+          for (int pr = 0; pr < 4; ++pr) pair_op(x[8 + pr], x[15 - pr], S / 2 + S * pr, false, T0a, T0b, T12a, T12b);
+        }
+        fft8<1>(x);
+        fft8<1>(x + 8);
+#pragma unroll
+        for (int n3 = 0; n3 < 8; ++n3) {
+          X[xi(b, slotA + n3)] = x[n3];
+          X[xi(b, slotB + n3)] = x[8 + n3];
+        }
+      } break;
+      case 3: {
+        // ---- inverse stage B, in place
+#pragma unroll
+        for (int q = 0; q < NQB; ++q) {
+          const int c = u + TPC * q, k1 = c >> 3, n3 = c & 7;
+#pragma unroll
+          for (int k2 = 0; k2 < R2; ++k2) {
+            cplx val = X[xi(b, k1 * PITCH + k2 * 8 + n3)];
+            if (k2 > 0) val = cmulc(val, TW[n3 * k2 * R1]);
+            x[q * R2 + k2] = val;
+          }
+          fftR<R2, 1>(x + q * R2);
+#pragma unroll
+          for (int n2 = 0; n2 < R2; ++n2) X[xi(b, k1 * PITCH + n2 * 8 + n3)] = x[q * R2 + n2];
+        }
+      } break;
+      default: {
+        // ---- inverse stage A, store
+#pragma unroll
+        for (int q = 0; q < NQA; ++q) {
+          const int rr = u + TPC * q;
+#pragma unroll
+          for (int k1 = 0; k1 < R1; ++k1) {
+            cplx val = X[xi(b, k1 * PITCH + rr)];
+            if (k1 > 0) val = cmulc(val, TW[rr * k1]);
+            x[q * R1 + k1] = val;
+          }
+          fftR<R1, 1>(x + q * R1);
+#pragma unroll
+          for (int n1 = 0; n1 < R1; ++n1) gstore(t, seq, n1 * LA + rr, x[q * R1 + n1]);
+        }
+      } break;
+    }
+  }
+};
+
+#if defined(__CUDACC__)
+template <class P>
+__global__ void __launch_bounds__(P::NT, (512 / P::NT > 0 ? 512 / P::NT : 1)) midfft_kernel(const P prog) {   // <= 128 registers
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  typename P::Regs r;
+  const int tid = (int)threadIdx.x;
+  prog.init(tid, smem_raw);
+  __syncthreads();
+  const long nt = prog.ntiles();
+  for (long tile = blockIdx.x; tile < nt; tile += gridDim.x) {
+#pragma unroll
+    for (int ph = 0; ph < P::NPH; ++ph) {
+      prog.phase(ph, tile, tid, r, smem_raw);
+      __syncthreads();
+    }
+  }
+}
+#endif
+
+}  // namespace midfft

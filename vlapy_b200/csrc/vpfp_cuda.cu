@@ -18,6 +18,7 @@
 #include "advect.h"
 #include "advect_fast.cuh"
 #include "fp_fast.cuh"
+#include "midfft.cuh"
 #include "fp_reg.cuh"
 #include "rowfft.cuh"
 #include "rowops.h"
@@ -287,6 +288,51 @@ static int run_fast_mode(fast::FastArgs fa, cudaStream_t st) {
   return run_three_passes<MODE>(fa, st);
 }
 
+// ---- mid-size single-pass kernels (midfft.cuh): N in {256, 512, 1024, 2048}, uniform wavenumber grids
+template <class P>
+static int launch_midfft(const midfft::Args& ma, cudaStream_t st, const char* label) {
+  P prog;
+  prog.a = ma;
+  int rc = opt_in_smem(midfft::midfft_kernel<P>, (size_t)P::SMEM_BYTES);
+  if (rc) return rc;
+  long grid = prog.ntiles();
+  if (grid > 148L * 16) grid = 148L * 16;
+  {
+    ProfScope ps(label, st);
+    midfft::midfft_kernel<P><<<(unsigned)grid, P::NT, P::SMEM_BYTES, st>>>(prog);
+  }
+  CUDA_TRY(cudaGetLastError());
+  return VPFP_OK;
+}
+
+static bool midfft_eligible(const AdvectProg& a, int flags) {
+  if (a.op != OP_PHASE || !(flags & VPFP_PHASE_TABLE) || (flags & (VPFP_FORCE_GENERIC | VPFP_FORCE_THREE_PASS))) return false;
+  return a.N == 256 || a.N == 512 || a.N == 1024 || a.N == 2048;
+}
+
+static int run_midfft(const AdvectProg& a, cudaStream_t st) {
+  midfft::Args ma;
+  ma.nsim = a.nsim; ma.nseq = a.nseq; ma.nrows = a.nrows;
+  ma.fin = a.fin; ma.ld_in = a.ld_in; ma.fout = a.fout; ma.ld_out = a.ld_out;
+  ma.kvec = a.kvec; ma.cvec = a.cvec; ma.dt = a.dt;
+  int rc = get_twiddles(a.N, &ma.tw);
+  if (rc) return rc;
+  if (a.mode == ADV_COLS) {
+    switch (a.N) {
+      case 256: return launch_midfft<midfft::Prog<256, 8, 4, ADV_COLS, 8>>(ma, st, "vdfdx.mid");
+      case 512: return launch_midfft<midfft::Prog<512, 8, 8, ADV_COLS, 8>>(ma, st, "vdfdx.mid");
+      case 1024: return launch_midfft<midfft::Prog<1024, 16, 8, ADV_COLS, 4>>(ma, st, "vdfdx.mid");
+      default: return launch_midfft<midfft::Prog<2048, 16, 16, ADV_COLS, 4>>(ma, st, "vdfdx.mid");
+    }
+  }
+  switch (a.N) {
+    case 256: return launch_midfft<midfft::Prog<256, 8, 4, ADV_ROWS, 8>>(ma, st, "edfdv.mid");
+    case 512: return launch_midfft<midfft::Prog<512, 8, 8, ADV_ROWS, 8>>(ma, st, "edfdv.mid");
+    case 1024: return launch_midfft<midfft::Prog<1024, 16, 8, ADV_ROWS, 4>>(ma, st, "edfdv.mid");
+    default: return launch_midfft<midfft::Prog<2048, 16, 16, ADV_ROWS, 2>>(ma, st, "edfdv.mid");
+  }
+}
+
 static bool fast_eligible(const AdvectProg& a, const AdvectPlan& pl) {
   if (a.op != OP_PHASE || pl.N1 == 1) return false;
   auto ok = [](int n) { return n == 16 || n == 32 || n == 64 || n == 128; };
@@ -314,6 +360,7 @@ static int run_advect(AdvectProg a, cudaStream_t st, int flags = VPFP_PHASE_EXAC
   const bool small = cells < (1L << 22) && a.N <= 2048;
   const AdvectPlan pl = ((flags & VPFP_FORCE_GENERIC) || small) ? make_advect_plan(a.mode, a.N, 2048, 2048)
                                                                 : make_advect_plan(a.mode, a.N, 128, 128);
+  if (!(scat && scat->mode) && midfft_eligible(a, flags)) return run_midfft(a, st);   // density: the caller's fallback
   int rc = get_twiddles(a.N, &a.tw);
   if (rc) return rc;
   if (scat && scat->mode && !(fast_eligible(a, pl) && !(flags & VPFP_FORCE_GENERIC)))
