@@ -122,10 +122,11 @@ def test_peer_scatter_matches_all_to_all_and_oracle(world, nx, nv, integrator):
         assert p.exitcode == 0
     f = {m: np.concatenate([o[1][m][0] for o in outs], axis=0) for m in ("a2a", "scatter")}
     e = {m: outs[0][1][m][1] for m in ("a2a", "scatter")}
-    # only the destination of the last pass' stores differs: bit-identical results
-    assert np.array_equal(f["a2a"], f["scatter"])
-    assert np.array_equal(e["a2a"], e["scatter"])
-    assert np.array_equal(outs[0][1]["a2a"][2], outs[0][1]["scatter"][2])
+    # the two modes differ in where the last pass stores and, for sequences of up to 2048 points, in the kernel that
+    # serves the local operator (mid-size single-pass kernel against the three passes with peer stores): rounding only
+    assert np.max(np.abs(f["a2a"] - f["scatter"])) / np.max(np.abs(f["scatter"])) < 1e-13
+    assert np.max(np.abs(e["a2a"] - e["scatter"])) / np.max(np.abs(e["scatter"])) < 1e-12
+    np.testing.assert_allclose(outs[0][1]["a2a"][2], outs[0][1]["scatter"][2], rtol=1e-11, atol=1e-15)
     from oracle import vpfp_oracle as O
     cfg = O.nlepw_config(nx=nx, nv=nv, log_nu=-2)
     e_ref, f_ref = O.run_steps(cfg, nsteps, integrator, "lb")
@@ -204,8 +205,13 @@ def test_sharded_inner_loop_api_equals_single_gpu_inner_loop():
                     for kk in a[k]:
                         ra, rb = a[k][kk], b[k][kk]
                         assert ra.shape == rb.shape and ra.dtype == rb.dtype, (k, kk)
-                        scale = max(np.max(np.abs(ra)), 1e-300)
-                        assert np.max(np.abs(ra - rb)) / scale < 1e-11, (rank, li, k, kk)
+                        # a v^p moment (field or its x-mean) is a linear functional of f with weight int |v|^p dv: two
+                        # runs that agree to 1e-12 on f (max f ~ 0.4) may differ by that much whatever the moment's size
+                        pw = {"n": 0, "j": 1, "T": 2, "q": 3, "fv4": 4, "vN": 5, "mean_n": 0, "mean_j": 1, "mean_T": 2}.get(kk)
+                        tol = 1e-11 * np.max(np.abs(ra)) + 1e-14
+                        if pw is not None:
+                            tol += 1e-12 * 0.4 * 2 * 6.4 ** (pw + 1) / (pw + 1)
+                        assert np.max(np.abs(ra - rb)) < tol, (rank, li, k, kk, float(np.max(np.abs(ra - rb))), tol)
                 elif k == "f":
                     x0, x1 = b["f_slab"]
                     assert rb_shape_ok(b[k], x1 - x0, nv)
@@ -213,7 +219,7 @@ def test_sharded_inner_loop_api_equals_single_gpu_inner_loop():
                 elif isinstance(a[k], np.ndarray):
                     assert a[k].shape == b[k].shape and a[k].dtype == b[k].dtype, k
                     tol = 1e-6 if k == "stored_f" else 1e-11
-                    assert np.max(np.abs(a[k] - b[k])) <= tol * max(np.max(np.abs(a[k])), 1e-300), (rank, li, k)
+                    assert np.max(np.abs(a[k] - b[k])) <= tol * np.max(np.abs(a[k])) + 1e-14, (rank, li, k)
     assert outs[0][1][0]["f_slab"] == (0, nx) and outs[1][1][0]["f_slab"] == (nx // 2, nx)
 
 
