@@ -290,14 +290,22 @@ static void run_midfft(const P& prog) {
   const char* oe = getenv("VPFP_EMUL_ORDER");
   const int order = oe ? atoi(oe) : 0;
   for (int tid = 0; tid < P::NT; ++tid) prog.init(tid, base);
-  for (long tile = 0; tile < prog.ntiles(); ++tile)
-    for (int ph = 0; ph < P::NPH; ++ph)
-      for (int i = 0; i < P::NT; ++i) {
-        int tid = i;
-        if (order == 1) tid = P::NT - 1 - i;
-        else if (order == 2) tid = (i & 1) ? P::NT / 2 + i / 2 : i / 2;
-        prog.phase(ph, tile, tid, regs[tid], base);
-      }
+  // two emulated CTAs (grid = 2) walk the tiles: every CTA prefetches its next tile into its own slots
+  const long grid = 2;
+  for (long cta = 0; cta < grid; ++cta) {
+    bool prefetched = false;
+    for (long tile = cta; tile < prog.ntiles(); tile += grid) {
+      const long nxt = (tile + grid < prog.ntiles()) ? tile + grid : -1;
+      for (int ph = 0; ph < P::NPH; ++ph)
+        for (int i = 0; i < P::NT; ++i) {
+          int tid = i;
+          if (order == 1) tid = P::NT - 1 - i;
+          else if (order == 2) tid = (i & 1) ? P::NT / 2 + i / 2 : i / 2;
+          prog.phase(ph, tile, nxt, prefetched, tid, regs[tid], base);
+        }
+      prefetched = true;
+    }
+  }
 }
 
 extern "C" int emul_midfft(int mode, const double* f_in, long ld_in, double* f_out, long ld_out, const double* kvec,

@@ -315,6 +315,8 @@ def test_midfft_programs(n, monkeypatch):
     assert np.array_equal(outs[0], outs[2]) and np.array_equal(outs[0], outs[4])
     monkeypatch.setenv("VPFP_EMUL_ORDER", "0")
     assert rel_err(E.midfft_rows(f[:4], e[:4], kv, 0.2), O.edfdv_exponential(f[:4], e[:4], 0.2, kv)) < TOL
+    fr, er = rng.standard_normal((37, n)), rng.standard_normal(37)      # several tiles per CTA: the prefetched path
+    assert rel_err(E.midfft_rows(fr, er, kv, -0.11), O.edfdv_exponential(fr, er, -0.11, kv)) < TOL
     ncols = 26
     vv = np.linspace(-6.4, 6.4, ncols)
     k0s = (0.3, 0.41)

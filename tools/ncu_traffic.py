@@ -5,7 +5,8 @@ import csv, json, re, sys
 
 LABELS = [(r"rowfft_kernel", "edfdv.row"), (r"rowfft2_kernel", "edfdv.row2"), (r"pass13_kernel<\d+, 0, 0", "vdfdx.pass1"), (r"pass2_kernel<\d+, 0", "vdfdx.pass2"),
           (r"pass13_kernel<\d+, 0, 1", "vdfdx.pass3"), (r"fp_reg_kernel", "fp_step"), (r"Xmodes2Prog|XmodesProg", "xmodes"),
-          (r"fp_kernel", "fp_step(shared-memory kernel)")]
+          (r"fp_kernel", "fp_step(shared-memory kernel)"),
+          (r"midfft_kernel<.*, 1, \d+>", "edfdv.mid"), (r"midfft_kernel<.*, 0, \d+>", "vdfdx.mid"), (r"moments_warp_kernel", "moments")]
 WANT = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum",
         "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active",
         "smsp__issue_active.avg.pct_of_peak_sustained_active", "sm__warps_active.avg.pct_of_peak_sustained_active",

@@ -38,6 +38,27 @@ struct Args {
   const cplx* tw;            // exp(-2 pi i m / L), L entries
 };
 
+// asynchronous copies global -> shared (host emulation: plain copies)
+VPFP_HD void cp_async(void* smem, const void* gmem, int bytes16) {
+#if defined(__CUDA_ARCH__)
+  const unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
+  if (bytes16) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(sa), "l"(gmem) : "memory");
+  else asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(sa), "l"(gmem) : "memory");
+#else
+  memcpy(smem, gmem, bytes16 ? 16 : 8);
+#endif
+}
+VPFP_HD void cp_async_commit() {
+#if defined(__CUDA_ARCH__)
+  asm volatile("cp.async.commit_group;\n" ::: "memory");
+#endif
+}
+VPFP_HD void cp_async_wait() {
+#if defined(__CUDA_ARCH__)
+  asm volatile("cp.async.wait_group 0;\n" ::: "memory");
+#endif
+}
+
 template <int L_, int R1_, int R2_, int MODE_, int CB_>
 struct Prog {
   static constexpr int L = L_, R1 = R1_, R2 = R2_, MODE = MODE_, CB = CB_;
@@ -51,7 +72,9 @@ struct Prog {
   static constexpr int NQA = 16 / R1, NQB = 16 / R2;
   static constexpr int NT12 = L / 32 + 1;      // table over j >> 4, j = 0 .. L/2
   static constexpr int NPH = 5;
-  static constexpr long SMEM_BYTES = (long)sizeof(cplx) * ((long)XELEMS * CB + L + 2L * CB * (16 + NT12));
+  static constexpr int NTWB = R2 * 8;          // stage-B twiddles
+  static constexpr bool PREFETCH = (MODE == ADV_COLS);   // ROWS would prefetch 8-byte pieces (2-way bank conflicts): direct loads
+  static constexpr long SMEM_BYTES = (long)sizeof(cplx) * ((long)XELEMS * CB + L + NTWB + 2L * CB * (16 + NT12));
 
   struct Regs {
     cplx x[16];
@@ -64,9 +87,15 @@ struct Prog {
     return (MODE == ADV_COLS) ? (long)a.nsim * tb : tb;
   }
   VPFP_HD static cplx* xbuf(unsigned char* smem) { return reinterpret_cast<cplx*>(smem); }
-  VPFP_HD static cplx* twl(unsigned char* smem) { return xbuf(smem) + (long)XELEMS * CB; }
-  VPFP_HD static cplx* t0(unsigned char* smem) { return twl(smem) + L; }               // [2][CB][16]
+  // twiddles laid out the way the lanes read them (ROWS: lanes run along r resp. n3; a single exp(-2 pi i m / L)
+  // table read at m = r k1 and m = R1 n3 k2 cost up to 8-way bank conflicts: 47 % of all shared-memory wavefronts)
+  VPFP_HD static cplx* twa(unsigned char* smem) { return xbuf(smem) + (long)XELEMS * CB; }   // [R1][L/R1]: W_L^(r k1)
+  VPFP_HD static cplx* twb(unsigned char* smem) { return twa(smem) + L; }                    // [R2][8]: W_L^(R1 n3 k2)
+  VPFP_HD static cplx* t0(unsigned char* smem) { return twb(smem) + NTWB; }            // [2][CB][16]
   VPFP_HD static cplx* t12(unsigned char* smem) { return t0(smem) + 2 * CB * 16; }     // [2][CB][NT12]
+  // phase-table index of entry i (of n) of channel ch of sequence b: the lanes of a warp run along b (COLS) or share b
+  // and differ in i (ROWS)
+  VPFP_HD static int tix(int ch, int b, int i, int n) { return (MODE == ADV_COLS) ? (ch * n + i) * CB + b : (ch * CB + b) * n + i; }
   // exchange-buffer index of slot `slot` of sequence b: lanes run along b (COLS) or along the slot (ROWS)
   VPFP_HD static int xi(int b, int slot) { return (MODE == ADV_COLS) ? slot * CB + b : b * XELEMS + slot; }
   VPFP_HD static void roles(int tid, int* b, int* u) {
@@ -74,10 +103,12 @@ struct Prog {
     else { *u = tid % TPC; *b = tid / TPC; }
   }
 
-  // once per CTA: the twiddle table
+  // once per CTA: the twiddle tables
   VPFP_HD void init(int tid, unsigned char* smem) const {
-    cplx* TW = twl(smem);
-    for (int j = tid; j < L; j += NT) TW[j] = a.tw[j];
+    cplx* TWA = twa(smem);
+    cplx* TWB = twb(smem);
+    for (int j = tid; j < L; j += NT) TWA[j] = a.tw[((j % LA) * (j / LA)) % L];
+    for (int j = tid; j < NTWB; j += NT) TWB[j] = a.tw[((j & 7) * (j >> 3) * R1) % L];
   }
 
   struct Tile {
@@ -129,14 +160,43 @@ struct Prog {
     if (rb < a.nrows) a.fout[rb * a.ld_out + n] = v.y;
   }
 
+  // The NEXT tile of the CTA travels global -> shared memory with cp.async while the current one is finished: a thread
+  // reads last (inverse stage A) and first (stage A of the next tile) the same 16 slots of the exchange buffer,
+  // (k1, r) for its own r, so it copies the raw points n = k1 (L/R1) + r exactly there and needs no barrier for them
+  // (the trick of rowfft.cuh and of pass 2 in advect_fast.cuh).
+  VPFP_HD void prefetch_own(long tile, int b, int u, unsigned char* smem) const {
+    cplx* X = xbuf(smem);
+    const Tile t = decode(tile);
+    const int seq = t.seq0 + b;
+#pragma unroll
+    for (int q = 0; q < NQA; ++q) {
+      const int rr = u + TPC * q;
+#pragma unroll
+      for (int n1 = 0; n1 < R1; ++n1) {
+        cplx* dst = X + xi(b, n1 * PITCH + rr);
+        const int n = n1 * LA + rr;
+        if (seq >= a.nseq) { *dst = cmake(0.0, 0.0); continue; }
+        if (MODE == ADV_COLS) {
+          cp_async(dst, a.fin + ((long)t.sim * L + n) * a.ld_in + 2L * seq, 1);
+        } else {
+          const long ra = 2 * (long)seq, rb = ra + 1;
+          cp_async(&dst->x, a.fin + ra * a.ld_in + n, 0);
+          if (rb < a.nrows) cp_async(&dst->y, a.fin + rb * a.ld_in + n, 0);
+          else dst->y = 0.0;
+        }
+      }
+    }
+    cp_async_commit();
+  }
+
   // one (k, L-k) pair: Zr = Z[kbin], Zpr = Z[L-kbin] in; the phase-multiplied, re-packed pair out
-  VPFP_HD static void pair_op(cplx& Zr, cplx& Zpr, const int kbin, const bool selfpair, const cplx* T0a, const cplx* T0b,
-                              const cplx* T12a, const cplx* T12b) {
+  VPFP_HD static void pair_op(cplx& Zr, cplx& Zpr, const int kbin, const bool selfpair, const int b, const cplx* T0,
+                              const cplx* T12) {
     const bool neg = (2 * kbin > L);
     const bool nyq = (2 * kbin == L);
     const int j = neg ? L - kbin : kbin;                 // |signed frequency index|, 0 .. L/2
-    cplx Pa = cmul(T0a[j & 15], T12a[j >> 4]);
-    cplx Pb = cmul(T0b[j & 15], T12b[j >> 4]);
+    cplx Pa = cmul(T0[tix(0, b, j & 15, 16)], T12[tix(0, b, j >> 4, NT12)]);
+    cplx Pb = cmul(T0[tix(1, b, j & 15, 16)], T12[tix(1, b, j >> 4, NT12)]);
     if (neg) { Pa = cconj(Pa); Pb = cconj(Pb); }
     if (nyq) { Pa.y = 0.0; Pb.y = 0.0; }
     const cplx Z = Zr, Zp = Zpr;
@@ -146,9 +206,12 @@ struct Prog {
     if (!selfpair) Zpr = cconj(csub(X1, X2));
   }
 
-  VPFP_HD void phase(int ph, long tile, int tid, Regs& r, unsigned char* smem) const {
+  // prefetched: this tile was brought into the thread's own slots by prefetch_own; nexttile: the tile this CTA handles
+  // after this one (< 0: none)
+  VPFP_HD void phase(int ph, long tile, long nexttile, bool prefetched, int tid, Regs& r, unsigned char* smem) const {
     cplx* X = xbuf(smem);
-    const cplx* TW = twl(smem);
+    const cplx* TWA = twa(smem);
+    const cplx* TWB = twb(smem);
     cplx* x = r.x;
     int b, u;
     roles(tid, &b, &u);
@@ -170,22 +233,32 @@ struct Prog {
           const double j = (i < 16) ? (double)i : 16.0 * (double)(i - 16);
           double sn, cs;
           sincos_hd(phi * j, &sn, &cs);
-          if (i < 16) T0[(ch * CB + cb_) * 16 + i] = cmake(cs * (0.5 / (double)L), -sn * (0.5 / (double)L));
-          else T12[(ch * CB + cb_) * NT12 + (i - 16)] = cmake(cs, -sn);
+          if (i < 16) T0[tix(ch, cb_, i, 16)] = cmake(cs * (0.5 / (double)L), -sn * (0.5 / (double)L));
+          else T12[tix(ch, cb_, i - 16, NT12)] = cmake(cs, -sn);
         }
         // ---- stage A: radix-R1 over n1 for r = u + TPC q
+        if (PREFETCH && prefetched) {
+          cp_async_wait();
 #pragma unroll
-        for (int q = 0; q < NQA; ++q) {
-          const int rr = u + TPC * q;
+          for (int q = 0; q < NQA; ++q) {
+            const int rr = u + TPC * q;
 #pragma unroll
-          for (int n1 = 0; n1 < R1; ++n1) x[q * R1 + n1] = gload(t, seq, n1 * LA + rr);
+            for (int n1 = 0; n1 < R1; ++n1) x[q * R1 + n1] = X[xi(b, n1 * PITCH + rr)];
+          }
+        } else {
+#pragma unroll
+          for (int q = 0; q < NQA; ++q) {
+            const int rr = u + TPC * q;
+#pragma unroll
+            for (int n1 = 0; n1 < R1; ++n1) x[q * R1 + n1] = gload(t, seq, n1 * LA + rr);
+          }
         }
 #pragma unroll
         for (int q = 0; q < NQA; ++q) {
           const int rr = u + TPC * q;
           fftR<R1, -1>(x + q * R1);
 #pragma unroll
-          for (int k1 = 1; k1 < R1; ++k1) x[q * R1 + k1] = cmul(x[q * R1 + k1], TW[rr * k1]);
+          for (int k1 = 1; k1 < R1; ++k1) x[q * R1 + k1] = cmul(x[q * R1 + k1], TWA[k1 * LA + rr]);
 #pragma unroll
           for (int k1 = 0; k1 < R1; ++k1) X[xi(b, k1 * PITCH + rr)] = x[q * R1 + k1];
         }
@@ -199,7 +272,7 @@ struct Prog {
           for (int n2 = 0; n2 < R2; ++n2) x[q * R2 + n2] = X[xi(b, k1 * PITCH + n2 * 8 + n3)];
           fftR<R2, -1>(x + q * R2);
 #pragma unroll
-          for (int k2 = 1; k2 < R2; ++k2) x[q * R2 + k2] = cmul(x[q * R2 + k2], TW[n3 * k2 * R1]);
+          for (int k2 = 1; k2 < R2; ++k2) x[q * R2 + k2] = cmul(x[q * R2 + k2], TWB[k2 * 8 + n3]);
 #pragma unroll
           for (int k2 = 0; k2 < R2; ++k2) X[xi(b, k1 * PITCH + k2 * 8 + n3)] = x[q * R2 + k2];
         }
@@ -216,21 +289,19 @@ struct Prog {
         }
         fft8<-1>(x);
         fft8<-1>(x + 8);
-        const cplx* T0a = t0(smem) + (0 * CB + b) * 16;
-        const cplx* T0b = t0(smem) + (1 * CB + b) * 16;
-        const cplx* T12a = t12(smem) + (0 * CB + b) * NT12;
-        const cplx* T12b = t12(smem) + (1 * CB + b) * NT12;
+        const cplx* T0 = t0(smem);
+        const cplx* T12 = t12(smem);
         if (!special) {
           // A[k3] (bin sA + S k3) pairs with B[7 - k3]
 #pragma unroll
-          for (int pr = 0; pr < 8; ++pr) pair_op(x[pr], x[15 - pr], sA + S * pr, false, T0a, T0b, T12a, T12b);
+          for (int pr = 0; pr < 8; ++pr) pair_op(x[pr], x[15 - pr], sA + S * pr, false, b, T0, T12);
         } else {
-          pair_op(x[0], x[0], 0, true, T0a, T0b, T12a, T12b);                       // DC
-          pair_op(x[4], x[4], S * 4, true, T0a, T0b, T12a, T12b);                   // Nyquist
+          pair_op(x[0], x[0], 0, true, b, T0, T12);                       // DC
+          pair_op(x[4], x[4], S * 4, true, b, T0, T12);                   // Nyquist
 #pragma unroll
-          for (int pr = 1; pr < 4; ++pr) pair_op(x[pr], x[8 - pr], S * pr, false, T0a, T0b, T12a, T12b);
+          for (int pr = 1; pr < 4; ++pr) pair_op(x[pr], x[8 - pr], S * pr, false, b, T0, T12);
 #pragma unroll
-          for (int pr = 0; pr < 4; ++pr) pair_op(x[8 + pr], x[15 - pr], S / 2 + S * pr, false, T0a, T0b, T12a, T12b);
+          for (int pr = 0; pr < 4; ++pr) pair_op(x[8 + pr], x[15 - pr], S / 2 + S * pr, false, b, T0, T12);
         }
         fft8<1>(x);
         fft8<1>(x + 8);
@@ -248,7 +319,7 @@ struct Prog {
 #pragma unroll
           for (int k2 = 0; k2 < R2; ++k2) {
             cplx val = X[xi(b, k1 * PITCH + k2 * 8 + n3)];
-            if (k2 > 0) val = cmulc(val, TW[n3 * k2 * R1]);
+            if (k2 > 0) val = cmulc(val, TWB[k2 * 8 + n3]);
             x[q * R2 + k2] = val;
           }
           fftR<R2, 1>(x + q * R2);
@@ -257,16 +328,19 @@ struct Prog {
         }
       } break;
       default: {
-        // ---- inverse stage A, store
+        // ---- inverse stage A, store; the thread's slots are free once they are in registers: next tile into them
 #pragma unroll
         for (int q = 0; q < NQA; ++q) {
           const int rr = u + TPC * q;
 #pragma unroll
-          for (int k1 = 0; k1 < R1; ++k1) {
-            cplx val = X[xi(b, k1 * PITCH + rr)];
-            if (k1 > 0) val = cmulc(val, TW[rr * k1]);
-            x[q * R1 + k1] = val;
-          }
+          for (int k1 = 0; k1 < R1; ++k1) x[q * R1 + k1] = X[xi(b, k1 * PITCH + rr)];
+        }
+        if (PREFETCH && nexttile >= 0) prefetch_own(nexttile, b, u, smem);
+#pragma unroll
+        for (int q = 0; q < NQA; ++q) {
+          const int rr = u + TPC * q;
+#pragma unroll
+          for (int k1 = 1; k1 < R1; ++k1) x[q * R1 + k1] = cmulc(x[q * R1 + k1], TWA[k1 * LA + rr]);
           fftR<R1, 1>(x + q * R1);
 #pragma unroll
           for (int n1 = 0; n1 < R1; ++n1) gstore(t, seq, n1 * LA + rr, x[q * R1 + n1]);
@@ -285,12 +359,15 @@ __global__ void __launch_bounds__(P::NT, (512 / P::NT > 0 ? 512 / P::NT : 1)) mi
   prog.init(tid, smem_raw);
   __syncthreads();
   const long nt = prog.ntiles();
+  bool prefetched = false;
   for (long tile = blockIdx.x; tile < nt; tile += gridDim.x) {
+    const long nxt = (tile + gridDim.x < nt) ? tile + gridDim.x : -1;
 #pragma unroll
     for (int ph = 0; ph < P::NPH; ++ph) {
-      prog.phase(ph, tile, tid, r, smem_raw);
+      prog.phase(ph, tile, nxt, prefetched, tid, r, smem_raw);
       __syncthreads();
     }
+    prefetched = true;
   }
 }
 #endif

@@ -178,7 +178,9 @@ struct Prog {
     r.wA = a.twN[sA];
     r.wB = a.twN[sB];
     cplx* TW2 = tw2(smem);
-    for (int j = tid; j < L2; j += T) TW2[j] = a.twN[(long)j * (N / L2)];
+    // stage-2 twiddles W_L2^(m3 k2) laid out [k2][m3]: the lanes of a quarter-warp read consecutive m3 of one k2
+    // (a single table indexed m3 * k2 cost up to 8-way bank conflicts for even k2: ~10 % of the kernel's wavefronts)
+    for (int j = tid; j < L2; j += T) TW2[j] = a.twN[(long)((j & 15) * (j >> 4)) * (N / L2)];
   }
 
   // sin / cos of pi*t without a slow path (exact reduction mod 2)
@@ -386,7 +388,7 @@ struct Prog {
           for (int m2 = 0; m2 < R2; ++m2) x[q * R2 + m2] = X[k1 * L2 + m2 * 16 + m3];
           fftR<R2, -1>(x + q * R2);
 #pragma unroll
-          for (int k2 = 1; k2 < R2; ++k2) x[q * R2 + k2] = cmul(x[q * R2 + k2], TW2[m3 * k2]);
+          for (int k2 = 1; k2 < R2; ++k2) x[q * R2 + k2] = cmul(x[q * R2 + k2], TW2[k2 * 16 + m3]);
         }
       } break;
       case 2: {
@@ -422,7 +424,7 @@ struct Prog {
 #pragma unroll
           for (int k2 = 0; k2 < R2; ++k2) {
             cplx val = X[(k1 + R1 * k2) * 17 + m3];
-            if (k2 > 0) val = cmulc(val, TW2[m3 * k2]);
+            if (k2 > 0) val = cmulc(val, TW2[k2 * 16 + m3]);
             x[q * R2 + k2] = val;
           }
           fftR<R2, 1>(x + q * R2);

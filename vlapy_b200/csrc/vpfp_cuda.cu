@@ -295,8 +295,26 @@ static int launch_midfft(const midfft::Args& ma, cudaStream_t st, const char* la
   prog.a = ma;
   int rc = opt_in_smem(midfft::midfft_kernel<P>, (size_t)P::SMEM_BYTES);
   if (rc) return rc;
+  // persistent: SMs x resident CTAs, every CTA walks tiles blockIdx.x, + grid, ... and prefetches its next one
+  int dev = 0;
+  CUDA_TRY(cudaGetDevice(&dev));
+  static std::mutex mu;
+  static std::map<int, int> resident;      // per device (and per instantiation P)
+  int per_dev;
+  {
+    std::lock_guard<std::mutex> lk(mu);
+    if (!resident.count(dev)) {
+      int nsm = 0, occ = 0;
+      CUDA_TRY(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev));
+      CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, midfft::midfft_kernel<P>, P::NT, P::SMEM_BYTES));
+      if (occ < 1) return fail(VPFP_ERR_CUDA, "midfft kernel does not fit an SM");
+      resident[dev] = nsm * occ;
+    }
+    per_dev = resident[dev];
+  }
   long grid = prog.ntiles();
-  if (grid > 148L * 16) grid = 148L * 16;
+  const long cap = P::PREFETCH ? per_dev : 16L * per_dev;    // without prefetch: many CTAs hide each other's loads
+  if (grid > cap) grid = cap;
   {
     ProfScope ps(label, st);
     midfft::midfft_kernel<P><<<(unsigned)grid, P::NT, P::SMEM_BYTES, st>>>(prog);
@@ -326,8 +344,11 @@ static int run_midfft(const AdvectProg& a, cudaStream_t st) {
     }
   }
   switch (a.N) {
+#ifndef MIDFFT_RCB
+#define MIDFFT_RCB 4      // row pairs per CTA at nv = 512 (measured: 8 -> 1.070 ms, 4 -> 1.005 ms, 2 -> 1.016 ms at C4)
+#endif
     case 256: return launch_midfft<midfft::Prog<256, 8, 4, ADV_ROWS, 8>>(ma, st, "edfdv.mid");
-    case 512: return launch_midfft<midfft::Prog<512, 8, 8, ADV_ROWS, 8>>(ma, st, "edfdv.mid");
+    case 512: return launch_midfft<midfft::Prog<512, 8, 8, ADV_ROWS, MIDFFT_RCB>>(ma, st, "edfdv.mid");
     case 1024: return launch_midfft<midfft::Prog<1024, 16, 8, ADV_ROWS, 4>>(ma, st, "edfdv.mid");
     default: return launch_midfft<midfft::Prog<2048, 16, 16, ADV_ROWS, 2>>(ma, st, "edfdv.mid");
   }
