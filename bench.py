@@ -712,6 +712,12 @@ def gpu_arm(args):
                          "traffic_kind": "static: dram__bytes_read+write per launch from the committed ncu --set full "
                                          "capture (%s), not measured in this run" % traffic_src,
                          "peak_source": peak_src,
+                         "fp64": {"pipe_busy_pct_ncu": (traffic.get(dom_label, {}).get("fp64_pipe_pct") if full_size else None),
+                                  "peak_tflops_measured": 34.2,
+                                  "note": "second ceiling of this kernel: share of the fp64 FMA pipe's issue slots it uses (static, "
+                                          "same ncu capture as traffic) and the DFMA rate measured on this pool's B200s "
+                                          "(profiles/fp64_peak_r02.txt); a kernel at 100 % of that pipe would sit at ~0.77 of the HBM "
+                                          "roofline (DESIGN.md section 4)"},
                          "algorithmic_bytes_per_launch": 16.0 * cells,
                          "step": {"bytes_per_cell_update": step_bytes / (nx * nv),
                                   "achieved": step_bytes / (ms / K * 1e-3) / 1e9 / world,

@@ -36,6 +36,9 @@ def main():
         dur = float(r[ix["gpu__time_duration.sum"]].replace(",", ""))
         dur_ms = dur * {"ns": 1e-6, "us": 1e-3, "ms": 1.0, "s": 1e3}.get(units[ix["gpu__time_duration.sum"]], 1.0)
         res[label] = {"kernel": name, "dram_bytes": rd + wr, "dram_read": rd, "dram_write": wr, "ncu_ms": dur_ms}
+        fk = "sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active"
+        if fk in ix and r[ix[fk]]:
+            res[label]["fp64_pipe_pct"] = float(r[ix[fk]].replace(",", ""))
         lines.append("== %s   (%s)" % (name, label))
         for w in WANT:
             if w in ix:

@@ -1071,6 +1071,8 @@ int vpfp_xmodes_partial(const double* f, long ld, double* out, int nmodes, int b
   int xch = nx / 128;
   if (xch < 1) xch = 1;
   if (xch > env_xch) xch = env_xch;
+  // (measured and rejected at 4096 x 4096: 128 row chunks instead of 32 -- the first stage gains 8 us, the reduction
+  // of four times as many partials loses 22 us)
   p.xchunks = xch;
   void* scratch = nullptr;
   size_t bytes = (size_t)batch * xch * nmodes * ncols * 2 * sizeof(double);
