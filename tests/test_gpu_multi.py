@@ -225,3 +225,27 @@ def test_sharded_inner_loop_api_equals_single_gpu_inner_loop():
 
 def rb_shape_ok(f, rows, nv):
     return f.shape == (rows, nv) and f.dtype == np.float64
+
+
+def test_kernels_with_large_shared_memory_on_a_second_device():
+    """the opt-in for more than 48 KB of dynamic shared memory is a per-device function attribute; the
+    library remembers it per (kernel, device).  Run the kernels that need it on cuda:0 and then on cuda:1 from ONE
+    process (ensembles sharded over devices do that)."""
+    if not torch.cuda.is_available() or torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    from oracle import vpfp_oracle as O
+    from vlapy_b200 import ops
+    nv = 4096
+    dv, v, kv = O.velocity_grid(6.4, nv)
+    f = O.shifted_maxwellian(6, v, 1.0, 0.3)
+    ref = O.collision_step(f, v, 3e-6, 0.25, dv, "lb")
+    e = np.linspace(-0.3, 0.3, 6)
+    ref_e = O.edfdv_exponential(f, e, 0.1, kv)
+    for d in (0, 1, 0):
+        with torch.cuda.device(d):
+            dev = torch.device("cuda", d)
+            fd, vd = torch.from_numpy(f).to(dev), torch.from_numpy(v).to(dev)
+            out = ops.fp_step(fd, vd, 3e-6, 0.25, dv, "lb", vgrid=ops.linspace_params(v))
+            assert np.max(np.abs(out.cpu().numpy() - ref)) / np.max(np.abs(ref)) < 1e-12
+            oe = ops.edfdv_exp(fd, torch.from_numpy(e).to(dev), torch.from_numpy(kv).to(dev), 0.1, flags=ops.PHASE_TABLE)
+            assert np.max(np.abs(oe.cpu().numpy() - ref_e)) / np.max(np.abs(ref_e)) < 1e-12

@@ -691,6 +691,42 @@ def test_single_pass_row_kernel(dev, nv, rows):
         assert rel_err(one.cpu().numpy(), three.cpu().numpy()) < TOL
 
 
+def test_cuda_graph_survives_growth_of_the_library_scratch(dev):
+    """a captured step keeps the pointers of the library's reduction scratch (x-mode partials, density
+    partials).  A larger problem in the same process makes that scratch grow; outgrown blocks are retired, not freed,
+    so replaying the earlier graph stays correct -- and the inner loop re-captures when the generation changed."""
+    from vlapy_b200 import ops, outer_loop
+    cfg = O.nlepw_config(nx=32, nv=256, k0=0.35, log_nu=-2)
+    params = make_params(cfg, "leapfrog", "lb")
+    params["backend"]["cuda_graph"] = True
+    stuff = make_stuff(cfg, RULES)
+    gs = outer_loop._GraphStep(params, stuff, 32, 256, (2, 256), True, dev)
+    e0, f0 = torch.from_numpy(cfg["e0"]).to(dev), torch.from_numpy(cfg["f0"]).to(dev)
+    gs.e.copy_(e0); gs.f.copy_(f0)
+    gs.capture()
+
+    def replay():
+        gs.e.copy_(e0); gs.f.copy_(f0)
+        gs.inp.zero_()
+        gs.graph.replay()
+        torch.cuda.synchronize()
+        return gs.f.clone(), gs.stage.clone()
+    f_a, st_a = replay()
+    gen = ops.scratch_generation()
+    big = torch.rand((2048, 4096), dtype=torch.float64, device=dev)          # x-modes + fused density at a larger size
+    ops.xmodes(big, 2)
+    kx = torch.from_numpy(O.spatial_grid(0.0, 18.0, 2048)[2]).to(dev)
+    vv = torch.linspace(-6.4, 6.4, 4096, dtype=torch.float64, device=dev)
+    ops.vdfdx_exp(big, kx, vv, 0.1, flags=ops.PHASE_TABLE, density_out=torch.empty(2048, dtype=torch.float64, device=dev), dv=0.1)
+    torch.cuda.synchronize()
+    assert ops.scratch_generation() > gen
+    assert gs.scratch_generation != ops.scratch_generation()                 # the inner loop would capture again
+    f_b, st_b = replay()
+    assert torch.equal(f_a, f_b) and torch.equal(st_a, st_b)
+    e_ref, f_ref = O.run_steps(cfg, 1, "leapfrog", "lb")
+    assert rel_err(f_b.cpu().numpy(), f_ref) < TOL
+
+
 @pytest.mark.parametrize("graph", [True, False])
 def test_run_loops_with_two_pinned_sets_equals_sequential_calls(dev, graph):
     """outer_loop.run_loops (storage hand-off overlapped with the next inner loop, backend.pinned_sets = 2): what
