@@ -339,7 +339,7 @@ struct P2Layout {
 // EX: per-bin sincos of the reference's own rounding (VPFP_PHASE_EXACT) instead of the geometric tables -- a
 // template parameter, so that the table kernel does not carry the registers and code of the sincos path.
 template <int L, int MODE, int CB, int PFM, bool EX>
-__global__ void __launch_bounds__(CB * 2 * Geo<L>::TPC, PFM == 1 ? 2 : 4) pass2_kernel(const FastArgs a, const int t1_chunk) {
+__global__ void __launch_bounds__(CB * 2 * Geo<L>::TPC, (PFM == 1 || CB * 2 * Geo<L>::TPC > 128) ? 2 : 4) pass2_kernel(const FastArgs a, const int t1_chunk) {
   constexpr bool PF = (PFM == 1);
   constexpr bool AL = (PFM == 2);
   using G = Geo<L>;

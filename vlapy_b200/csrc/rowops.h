@@ -490,6 +490,10 @@ struct Xmodes2Prog {
     const int x0 = (int)((long)nx * xc / xchunks), x1 = (int)((long)nx * (xc + 1) / xchunks);
     const double* col = f + ((long)b * nx) * ld + j;
     const double ang = -2.0 * 3.14159265358979323846 / (double)nx_total;
+#ifndef XMODES_UNROLL
+#define XMODES_UNROLL 2    // groups of eight rows in flight (measured at 16384^2 with the 128-thread launch: 1 -> 0.377,
+                           // 2 -> 0.370, 4 -> 0.427 ms; under prog_kernel's 1024-thread bound -- 64 registers -- it was 0.41-0.43)
+#endif
     double cr[8], ci[8];
 #pragma unroll
     for (int q = 0; q < 8; ++q) sincos_hd(ang * (double)q, &ci[q], &cr[q]);
@@ -498,6 +502,8 @@ struct Xmodes2Prog {
     sincos_hd(ang * (double)(x0 + x_offset), &wi, &wr);
     double s0a = 0.0, s0b = 0.0, sra = 0.0, sia = 0.0, srb = 0.0, sib = 0.0;
     int x = x0;
+    constexpr int XU = XMODES_UNROLL;
+#pragma unroll XU
     for (; x + 8 <= x1; x += 8) {
       double va[8], vb[8];
 #pragma unroll

@@ -75,6 +75,13 @@ __global__ void __launch_bounds__(1024) prog_kernel(const Prog prog, const int n
   }
 }
 
+// the same driver for one-phase programs launched with 128 threads: without the 1024-thread bound of prog_kernel the
+// compiler may use up to 255 registers (x-mode sums: more rows in flight)
+template <class Prog>
+__global__ void __launch_bounds__(128) prog128_kernel(const Prog prog) {
+  prog.phase(0, (long)blockIdx.x, (int)threadIdx.x, 128, nullptr);
+}
+
 template <class Prog>
 static int launch_prog(const Prog& prog, long nblocks, int threads, long smem, int nph,
                        cudaStream_t st, const char* label = "generic") {
@@ -232,7 +239,10 @@ static int launch_pass13(const fast::FastArgs& fa, cudaStream_t st) {
 template <int L, int MODE, bool EX>
 static int launch_pass2_pf(const fast::FastArgs& fa, cudaStream_t st) {
   constexpr int PFM = 2;
-  constexpr int CB = (L == 128) ? 8 : (L == 64 ? 16 : 32);
+#ifndef PASS2_CB128
+#define PASS2_CB128 8     // packed column pairs per CTA at L = 128 (measured: 16 = 256-byte rows, 256 threads, 2 CTAs/SM: no gain)
+#endif
+  constexpr int CB = (L == 128) ? PASS2_CB128 : (L == 64 ? 16 : 32);
   constexpr int threads = CB * 2 * fast::Geo<L>::TPC;
   const size_t smem = fast::pass2_smem<L, CB>(MODE, PFM);
   int rc = opt_in_smem(fast::pass2_kernel<L, MODE, CB, PFM, EX>, smem);
@@ -1084,7 +1094,12 @@ int vpfp_xmodes_partial(const double* f, long ld, double* out, int nmodes, int b
     p2.f = f; p2.ld = ld; p2.partial = p.partial; p2.batch = batch; p2.nx = nx; p2.ncols = ncols;
     p2.xchunks = xch; p2.cblocks = (ncols / 2 + threads - 1) / threads;
     p2.x_offset = x_offset; p2.nx_total = nx_total;
-    rc = launch_prog(p2, (long)batch * xch * p2.cblocks, threads, 0, 1, (cudaStream_t)stream, "xmodes");
+    {
+      ProfScope ps("xmodes", (cudaStream_t)stream);
+      prog128_kernel<Xmodes2Prog><<<(unsigned)((long)batch * xch * p2.cblocks), 128, 0, (cudaStream_t)stream>>>(p2);
+    }
+    CUDA_TRY(cudaGetLastError());
+    rc = VPFP_OK;
   } else {
     rc = launch_prog(p, (long)batch * xch * p.cblocks, threads, 0, 1, (cudaStream_t)stream, "xmodes");
   }
