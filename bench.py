@@ -137,10 +137,11 @@ def ensemble_arm(args):
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
+    sampler = ClockSampler(local_rank); sampler.start()
     for i in range(W):
         state = step_fn(state, dt * i)
     barrier()
-    sampler = ClockSampler(local_rank); sampler.start()
+    sampler.mark()
     ops.launch_count(reset=True)
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
@@ -215,15 +216,17 @@ def initial_state(cfg, pinned=False):
 
 
 class ClockSampler(threading.Thread):
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe):
-    one streaming nvidia-smi process sampling every 50 ms."""
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe): one streaming
+    nvidia-smi process sampling every 50 ms.  It is started BEFORE the warm-up steps (its start-up -- NVML
+    initialisation, up to a second on a fresh box -- perturbs the GPU and must not overlap the timed region, and the
+    GPU must not idle between warm-up and timed steps); ``mark()`` opens the window whose samples are reported."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
         super().__init__(daemon=True)
-        self.index, self.rows, self.proc = index, [], None
+        self.index, self.rows, self.proc, self.t0 = index, [], None, None
 
     def start(self):
         try:
@@ -233,7 +236,10 @@ class ClockSampler(threading.Thread):
         except Exception:
             self.proc = None
         super().start()
-        time.sleep(0.15)          # let the first sample land before the timed region starts
+
+    def mark(self):
+        """the timed region starts now"""
+        self.t0 = time.monotonic()
 
     def run(self):
         if self.proc is None:
@@ -241,17 +247,24 @@ class ClockSampler(threading.Thread):
         for line in self.proc.stdout:
             cells = [c.strip() for c in line.strip().split(",")]
             if len(cells) >= 7:
-                self.rows.append(cells)
+                self.rows.append(cells + [time.monotonic()])
 
     def summary(self):
+        t1 = time.monotonic()
         if self.proc is not None:
             time.sleep(0.06)
+            wait_until = time.monotonic() + 2.0        # very short runs: nvidia-smi may not have printed its first sample yet
+            while not self.rows and time.monotonic() < wait_until and self.proc.poll() is None:
+                time.sleep(0.05)
             self.proc.terminate()
             try:
                 self.proc.wait(timeout=3)
             except Exception:
                 self.proc.kill()
         self.join(timeout=3)
+        if self.t0 is not None:          # samples that arrived during the timed region (+ one period of slack)
+            inside = [r for r in self.rows if self.t0 <= r[-1] <= t1 + 0.06]
+            self.rows = inside if inside else self.rows[-2:]
         if not self.rows:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
 
@@ -482,11 +495,12 @@ def sharded_arm(args, cfg, params, rules, dev, barrier):
     total = W + K
     drv = [backend.driver(cfg["dt"] * i) for i in range(total)]
     store = vd.make_store(topo, backend, total)
+    sampler = ClockSampler(dev.index)
+    sampler.start()
     for i in range(W):
         state = step_fn(state, cfg["dt"] * i, drv[i], store)
     barrier()
-    sampler = ClockSampler(dev.index)
-    sampler.start()
+    sampler.mark()
     ops.launch_count(reset=True)
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
@@ -611,19 +625,27 @@ def gpu_arm(args):
             def run_step(i):
                 nonlocal work
                 work, _ = one_step(work, i)
+        sampler = ClockSampler(local_rank)
+        sampler.start()
         for i in range(W):
             run_step(i)
         barrier()
-        sampler = ClockSampler(local_rank)
-        sampler.start()
+        sampler.mark()
         ops.launch_count(reset=True)
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        step_ev = [torch.cuda.Event(enable_timing=True) for _ in range(K + 1)] if os.environ.get("VPFP_BENCH_STEPTIMES") else None
         ev0.record()
         for i in range(W, W + K):
+            if step_ev:
+                step_ev[i - W].record()
             run_step(i)
         ev1.record()
+        if step_ev:
+            step_ev[K].record()
         barrier()
         ms = ev0.elapsed_time(ev1)
+        if step_ev:      # diagnostic only: per-step device times to stderr
+            sys.stderr.write("step ms: " + " ".join("%.3f" % step_ev[j].elapsed_time(step_ev[j + 1]) for j in range(K)) + "\n")
         launches = ops.launch_count()
         clocks = sampler.summary()
         # ---- per-kernel durations (second pass over the same steps, events around every launch)

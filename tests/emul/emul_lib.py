@@ -108,6 +108,17 @@ def poisson(n, ook, driver, max_single=8192):
     return e
 
 
+def poisson_rowfft(n, ook, driver):
+    """single-launch Poisson solve (rowfft.cuh in Poisson mode), nx in {4096, 8192, 16384}"""
+    n = np.ascontiguousarray(np.atleast_2d(n)); batch, nx = n.shape
+    ook = np.ascontiguousarray(np.broadcast_to(ook, n.shape))
+    drv = None if driver is None else np.ascontiguousarray(np.broadcast_to(driver, n.shape))
+    e = np.empty_like(n)
+    rc = lib().emul_poisson_rowfft(_p(n), _p(ook), _p(drv), _p(e), c_int(batch), c_int(nx))
+    assert rc == 0
+    return e
+
+
 def edfdv_cd2(f, e, dt, dv):
     f = np.ascontiguousarray(f); out = np.empty_like(f); rows, nv = f.shape
     lib().emul_edfdv_cd2(_p(f), c_long(nv), _p(out), c_long(nv), _p(np.ascontiguousarray(e)), c_double(dt),

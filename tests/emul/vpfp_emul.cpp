@@ -368,6 +368,19 @@ static void run_rowfft(const P& prog) {
     }
 }
 
+extern "C" int emul_poisson_rowfft(const double* n, const double* ook, const double* driver, double* e, int batch, int nx) {
+  std::vector<cplx> tw = make_tw(nx);
+  rowfft::Args a;
+  memset(&a, 0, sizeof(a));
+  a.fin = n; a.ld_in = nx; a.fout = e; a.ld_out = nx; a.kvec = ook; a.cvec = nullptr; a.dt = 0.0;
+  a.nrows = batch; a.twN = tw.data(); a.addv = driver;
+  if (nx == 16384) { rowfft::Prog<32, 16, false, true> p; p.a = a; run_rowfft(p); }
+  else if (nx == 8192) { rowfft::Prog<16, 16, false, true> p; p.a = a; run_rowfft(p); }
+  else if (nx == 4096) { rowfft::Prog<8, 16, false, true> p; p.a = a; run_rowfft(p); }
+  else return 1;
+  return 0;
+}
+
 extern "C" int emul_edfdv_rowfft(const double* f_in, long ld_in, double* f_out, long ld_out, const double* e,
                                  const double* kv, double dt, int rows, int nv) {
   std::vector<cplx> tw = make_tw(nv);

@@ -326,3 +326,16 @@ def test_midfft_programs(n, monkeypatch):
         out = E.midfft_cols(g, kx, vv, dt, batch=2)
         for s in range(2):
             assert rel_err(out[s], O.vdfdx_exponential(g[s], dt, kx[s], vv)) < TOL
+
+
+@pytest.mark.parametrize("nx", [4096, 8192, 16384])
+def test_poisson_single_launch_program(nx):
+    """rowfft.cuh in Poisson mode (one CTA per density row: load 1 - n, multiplier i one_over_kx, add the driver)
+    against the oracle's vlapy/core/field.py:39-88, with and without a driver row, three rows"""
+    rng = np.random.default_rng(nx)
+    dx, x, kx, ook = O.spatial_grid(0.0, 2 * np.pi / 0.35, nx)
+    n = 1.0 + 0.1 * rng.standard_normal((3, nx))
+    drv = 0.02 * np.sin(0.35 * x)
+    ref = np.stack([O.solve_for_field(n[i], ook) for i in range(3)])
+    assert np.max(np.abs(E.poisson_rowfft(n, ook, None) - ref)) < TOL * np.abs(ref).max()
+    assert np.max(np.abs(E.poisson_rowfft(n, ook, drv) - (ref + drv))) < TOL * np.abs(ref).max()

@@ -54,6 +54,7 @@ struct Args {
   int peer_mode, nparts, my_rank, lpart;   // part = 1 << lpart
   double* peer[8];
   int l2_prefetch;      // rows ahead that thread 0 asks L2 to fetch (0: off)
+  const double* addv;   // POISSON: driver rows [nrows][N] added to the result (nullable)
 };
 
 // 16-byte asynchronous copy global -> shared (host emulation: plain copy)
@@ -129,7 +130,12 @@ VPFP_HD void pair_op(cplx& Z, cplx& Zp, const cplx Wk, const cplx Pk, const cplx
 
 // PEER_: the result is scattered to peer GPUs (Args::peer_mode) -- a template parameter, so that the
 // single-GPU kernel does not carry the registers and code of the scatter path.
-template <int R1_, int R2_, bool PEER_ = false>
+// POISSON_: the same transform pair as the spectral Poisson solve of vlapy/core/field.py:39-63 on a row of densities,
+//   E = Re ifft( i one_over_kx fft(1 - n) ) + driver:  the row is loaded as 1 - n, the multiplier of bin k is
+//   i ook[k] (kvec = one_over_kx; real and antisymmetric, so the result is real; bins 0 and N/2 contribute nothing),
+//   the driver row is added on the store.  One CTA, one launch, for nx in {4096, 8192, 16384} (the generic path took
+//   three dependent launches of ~20 us).
+template <int R1_, int R2_, bool PEER_ = false, bool POISSON_ = false>
 struct Prog {
   static constexpr int R1 = R1_, R2 = R2_, V = 32;
   static constexpr int S = R1 * R2;        // stage-3 sub-transforms
@@ -210,6 +216,7 @@ struct Prog {
   }
   // phase slope of a row over pi: (K[1] dt e[row]) / pi, the reference's two roundings of (k dt) e
   VPFP_HD double phi_over_pi(long row) const {
+    if (POISSON_) return 0.0;
     return mul_rn(mul_rn(a.kvec[1], a.dt), a.cvec[row]) * 0.31830988618379067154;
   }
   // first row of a CTA: copy and phase tables.  For the following rows the last phase of the previous row
@@ -226,6 +233,7 @@ struct Prog {
   // w / NWARP of warp w % NWARP (every warp pays for one sincos).  Written one phase before the row starts
   // (prefetch_row), read in its fourth phase.
   VPFP_HD void row_tables(int tid, const double phi_pi, unsigned char* smem) const {
+    if (POISSON_) return;
     constexpr int NWARP = (T >= 32) ? T / 32 : 1;
     cplx* G = tabs(smem);
     const int w = (tid & 31) * NWARP + (tid >> 5);
@@ -280,7 +288,7 @@ struct Prog {
   // MS = false: the caller knows that this thread is not thread 0 (ROWFFT_SPECIAL_BRANCH: a warp-uniform branch
   // around the select-based special case of thread 0, so that warps 1.. do not carry its selects).
   template <bool MS>
-  VPFP_HD void pointwise_phase(int tid, Regs& r, unsigned char* smem) const {
+  VPFP_HD void pointwise_phase(int tid, long row, Regs& r, unsigned char* smem) const {
     cplx* X = xbuf(smem);
     cplx* G = tabs(smem);
     cplx* LO = G + 16;
@@ -297,8 +305,9 @@ struct Prog {
         }
         fft16<-1>(x);
         fft16<-1>(x + 16);
-        const cplx bA = cmul(LO[sA & 31], HI[sA >> 5]);
-        const cplx bB = cmul(LO[sB & 31], HI[sB >> 5]);
+        const cplx bA = POISSON_ ? cmake(0.0, 0.0) : cmul(LO[sA & 31], HI[sA >> 5]);
+        const cplx bB = POISSON_ ? cmake(0.0, 0.0) : cmul(LO[sB & 31], HI[sB >> 5]);
+        const double* ook = a.kvec + (POISSON_ ? row * (long)N : 0);
         // Pair slots j = 0..15 hold (x[j], x[31-j]).  Ordinary threads: bin sA + S j with its partner
         // sB + S (15-j).  Thread 0 owns the two self-paired sub-transforms s = 0 and s = S/2; its
         // registers are permuted (selects, no divergent copy of the pair code) so that the same slots
@@ -331,8 +340,19 @@ struct Prog {
                              : cmake(special ? cos32(jw) : cos32(j), special ? -sin32(jw) : -sin32(j));
           if (j == 0 && special) w32 = cmake(0.0, -1.0);                             // W_N^(M/2) = -i
           const cplx Wk = cmul((j < 8) ? r.wA : wHi, w32);
-          const cplx Pk = cmul((j < 8) ? bA : pHi, G[gk]);
-          const cplx Pm = cmul((j < 8) ? qLo : bB, G[gm]);
+          cplx Pk, Pm;
+          if (POISSON_) {
+            // multipliers i ook[k] / (4M) of bin k and of its partner M - k (both in the lower half of the spectrum)
+            const int sK = (j < 8) ? sA : (special ? sB : sA), sM = (j < 8) ? (special ? sA : sB) : sB;
+            // (np.real of the reference keeps the Hermitian part of the multiplier: (ook[k] - ook[N-k]) / 2, which is
+            // ook[k] itself for the antisymmetric one_over_kx of vlapy/initializers.py:85-87)
+            const int kk = sK + S * gk, km = sM + S * gm;
+            Pk = cmake(0.0, (ook[kk] - ook[N - kk]) * (0.125 / (double)M));
+            Pm = cmake(0.0, (ook[km] - ook[N - km]) * (0.125 / (double)M));
+          } else {
+            Pk = cmul((j < 8) ? bA : pHi, G[gk]);
+            Pm = cmul((j < 8) ? qLo : bB, G[gm]);
+          }
           pair_op(x[j], x[31 - j], Wk, Pk, Pm);
         }
         if (special) {
@@ -340,7 +360,7 @@ struct Prog {
           {  // bin 0: Y[0] = X[0], Y[M] = Re(P_M) X[M]
             const double sc = 0.5 / (double)M;
             const double y0 = (dc.x + dc.y) * sc, ym = (dc.x - dc.y) * (*cosM(smem)) * sc;
-            y[0] = cmake(y0 + ym, y0 - ym);
+            y[0] = POISSON_ ? cmake(0.0, 0.0) : cmake(y0 + ym, y0 - ym);   // Poisson: ook[0] = 0, Nyquist imaginary
           }
           y[8] = x[0];
 #pragma unroll
@@ -373,6 +393,10 @@ struct Prog {
           const int rr = tid + T * q;
 #pragma unroll
           for (int m1 = 0; m1 < R1; ++m1) x[q * R1 + m1] = X[m1 * L2 + rr];
+          if (POISSON_) {                                   // net charge 1 - n (vlapy/core/field.py:61-63)
+#pragma unroll
+            for (int m1 = 0; m1 < R1; ++m1) x[q * R1 + m1] = cmake(1.0 - x[q * R1 + m1].x, 1.0 - x[q * R1 + m1].y);
+          }
           fftR<R1, -1>(x + q * R1);
           twiddle1<false>(x + q * R1, r.w1[q], r.w4[q]);
 #pragma unroll
@@ -401,10 +425,10 @@ struct Prog {
       } break;
       case 3: {
 #if ROWFFT_SPECIAL_BRANCH
-        if (tid < 32) pointwise_phase<true>(tid, r, smem);
-        else pointwise_phase<false>(tid, r, smem);
+        if (tid < 32) pointwise_phase<true>(tid, row, r, smem);
+        else pointwise_phase<false>(tid, row, r, smem);
 #else
-        pointwise_phase<true>(tid, r, smem);
+        pointwise_phase<true>(tid, row, r, smem);
 #endif
       } break;
       case 4: {
@@ -453,6 +477,11 @@ struct Prog {
           const int rr = tid + T * q;
           twiddle1<true>(x + q * R1, r.w1[q], r.w4[q]);
           fftR<R1, 1>(x + q * R1);
+          if (POISSON_ && a.addv != nullptr) {               // total field = self-consistent field + driver (field.py:66-88)
+            const cplx* drv = reinterpret_cast<const cplx*>(a.addv + row * (long)N) + rr;
+#pragma unroll
+            for (int m1 = 0; m1 < R1; ++m1) x[q * R1 + m1] = cadd(x[q * R1 + m1], drv[m1 * L2]);
+          }
           if (!PEER_) {
             // one base address, compile-time offsets: a store must not wait for the address registers
             // of the previous one (they are held until the load/store unit has taken the store)

@@ -603,7 +603,7 @@ static bool rowfft_eligible(const double* f_in, long ld_in, const double* f_out,
 }
 
 template <class P>
-static int launch_rowfft(const rowfft::Args& ra, cudaStream_t st) {
+static int launch_rowfft(const rowfft::Args& ra, cudaStream_t st, const char* label = "edfdv.row") {
   P prog;
   prog.a = ra;
   int dev = 0;
@@ -625,7 +625,7 @@ static int launch_rowfft(const rowfft::Args& ra, cudaStream_t st) {
   int grid = grid_for[dev];
   if (grid > ra.nrows) grid = ra.nrows;
   {
-    ProfScope ps("edfdv.row", st);
+    ProfScope ps(label, st);
     rowfft::rowfft_kernel<P><<<grid, P::T, P::SMEM_BYTES, st>>>(prog);
   }
   CUDA_TRY(cudaGetLastError());
@@ -908,6 +908,21 @@ int vpfp_poisson(const double* n, const double* one_over_kx, const double* drive
     PoissonDftProg p;
     p.n = n; p.ook = one_over_kx; p.driver = driver; p.e = e; p.N = nx;
     return launch_prog(p, batch, 256, p.smem_bytes(), 3, (cudaStream_t)stream, "poisson");
+  }
+  if ((nx == 4096 || nx == 8192 || nx == 16384) && !(((uintptr_t)n | (uintptr_t)e | (uintptr_t)(driver ? driver : n)) & 15)) {
+    // one CTA per density row, one launch (rowfft.cuh in Poisson mode); the generic path below takes three launches
+    rowfft::Args ra;
+    memset(&ra, 0, sizeof(ra));
+    ra.fin = n; ra.ld_in = nx; ra.fout = e; ra.ld_out = nx; ra.kvec = one_over_kx; ra.cvec = nullptr; ra.dt = 0.0;
+    ra.nrows = batch; ra.addv = driver;
+    int rc = get_twiddles(nx, &ra.twN);
+    if (rc) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    switch (nx) {
+      case 16384: return launch_rowfft<rowfft::Prog<32, 16, false, true>>(ra, st, "poisson");
+      case 8192: return launch_rowfft<rowfft::Prog<16, 16, false, true>>(ra, st, "poisson");
+      default: return launch_rowfft<rowfft::Prog<8, 16, false, true>>(ra, st, "poisson");
+    }
   }
   AdvectProg a;
   memset(&a, 0, sizeof(a));
