@@ -75,42 +75,6 @@ struct MomentsProg {
   }
 };
 
-#if defined(__CUDACC__)
-// Short rows (ncols <= 2048: ensembles of small grids, C1/C2/C4): ONE WARP per row instead of one CTA with a
-// shared-memory tree -- every lane takes 16-byte pieces of the row, the eight sums are folded with shuffles in a
-// fixed order (deterministic).  262144 rows of 512 cells (C4) took 3.7 ms with the CTA-per-row program
-// (292 GB/s): the barriers of its tree dominate rows this short.
-template <int NMOM>
-__global__ void __launch_bounds__(256) moments_warp_kernel(const MomentsProg p) {
-  const int lane = threadIdx.x & 31;
-  const long row = (long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (row >= p.rows) return;
-  const double* src = p.f + row * p.ld;
-  double acc[8];
-#pragma unroll
-  for (int k = 0; k < 8; ++k) acc[k] = 0.0;
-  const bool vec = ((p.ld & 1) == 0) && ((p.ncols & 1) == 0) && (((reinterpret_cast<uintptr_t>(p.f) | reinterpret_cast<uintptr_t>(p.v)) & 15) == 0);
-  if (vec) {
-    for (int j = 2 * lane; j < p.ncols; j += 64) {
-      const double2 f2 = *reinterpret_cast<const double2*>(src + j);
-      const double2 v2 = *reinterpret_cast<const double2*>(p.v + j);
-      MomentsProg::accumulate(acc, trapz_w(j, p.ncols, p.dv, p.edge_flags), f2.x, v2.x, NMOM);
-      MomentsProg::accumulate(acc, trapz_w(j + 1, p.ncols, p.dv, p.edge_flags), f2.y, v2.y, NMOM);
-    }
-  } else {
-    for (int j = lane; j < p.ncols; j += 32)
-      MomentsProg::accumulate(acc, trapz_w(j, p.ncols, p.dv, p.edge_flags), src[j], p.v[j], NMOM);
-  }
-#pragma unroll
-  for (int k = 0; k < NMOM; ++k) {
-    double y = acc[k];
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) y += __shfl_xor_sync(0xffffffffu, y, o);
-    if (lane == 0 && k < p.nmom) p.out[(long)k * p.out_ld + row] = y;
-  }
-}
-#endif
-
 // ---------------------------------------------------------------------------------------------
 // Implicit Fokker-Planck step for one row (vlapy/core/collisions.py:44-81, 104-158, 232-263 through
 // vlapy/core/step.py:102-108).  The diagonals are functions of two row scalars (T = v0t_sq, vbar):
