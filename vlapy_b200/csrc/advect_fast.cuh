@@ -324,24 +324,17 @@ struct P2Layout {
     return (b * 2 + g) * (R1 * 9) + m * 9 + r;   // 9: odd pitch, conflict free for lanes along r or m
   }
   static constexpr int S_ELEMS = (MODE == ADV_COLS) ? 2 * L * CB : CB * 2 * R1 * 9;
-  // staging buffer index of (group g, position l, sequence b)
-  __device__ static __forceinline__ int tidx(int g, int l, int b) {
-    if (MODE == ADV_COLS) return (g * L + l) * CB + b;
-    return (b * 2 + g) * L + l;
-  }
-  static constexpr int T_ELEMS = 2 * L * CB;
 };
 
-// PFM: 0 direct loads (4 CTAs/SM hide the latency), 1 next tile staged with cp.async in a second
-// buffer (2 CTAs/SM), 2 next tile prefetched with cp.async INTO THE EXCHANGE BUFFER: a thread reads
-// last (inverse step A') and first (step A of the next tile) the same 16 slots of S, so it prefetches
-// exactly those, needs no barrier for them and the kernel keeps the shared-memory footprint of PFM 0.
+// The next tile is prefetched with cp.async INTO THE EXCHANGE BUFFER: a thread reads last (inverse step A') and first
+// (step A of the next tile) the same 16 slots of S, so it prefetches exactly those and needs no barrier for them
+// and no second buffer.  (Round 1 also measured direct loads at 4 CTAs/SM and a staged second buffer at 2 CTAs/SM:
+// both slower; PFM stays in the signature as the tag of the surviving variant.)
 // EX: per-bin sincos of the reference's own rounding (VPFP_PHASE_EXACT) instead of the geometric tables -- a
 // template parameter, so that the table kernel does not carry the registers and code of the sincos path.
 template <int L, int MODE, int CB, int PFM, bool EX>
 __global__ void __launch_bounds__(CB * 2 * Geo<L>::TPC, (PFM == 1 || CB * 2 * Geo<L>::TPC > 128) ? 2 : 4) pass2_kernel(const FastArgs a, const int t1_chunk) {
-  constexpr bool PF = (PFM == 1);
-  constexpr bool AL = (PFM == 2);
+  static_assert(PFM == 2, "only the own-slot prefetch variant is built");
   using G = Geo<L>;
   using LY = P2Layout<L, MODE, CB>;
   constexpr int R1 = G::R1, TPC = G::TPC, NA = G::NA;
@@ -350,13 +343,12 @@ __global__ void __launch_bounds__(CB * 2 * Geo<L>::TPC, (PFM == 1 || CB * 2 * Ge
   extern __shared__ __align__(16) unsigned char smem_raw[];
   constexpr int NPT = 8 + HALF / 8 + 1;               // Lo[0..7] = G^j, Hi[0..HALF/8] = G^(8j)
   cplx* S = reinterpret_cast<cplx*>(smem_raw);        // exchange
-  cplx* STG = S + LY::S_ELEMS;                        // staging (prefetched tile), PF only
-  cplx* PT = STG + (PF ? LY::T_ELEMS : 0);            // [2 chan][CB][NPT]
+  cplx* PT = S + LY::S_ELEMS;                         // [2 chan][CB][NPT]
   cplx* BASE0 = PT + 2 * CB * NPT;                    // [2 tiles (parity)][2 groups][2 chan][CB]
   cplx* TWL = BASE0 + 8 * CB;                         // [L]     exp(-2 pi i m / L)
   cplx* TWT = TWL + L;                                // [2][L]  four-step twiddles W_N^(n2 k1) of the staged tile
-  cplx* TWC = TWT + 2 * L;                            // [2][L]  PF: twiddles of the tile being transformed; AL: second buffer
-  double* PHI = reinterpret_cast<double*>(TWC + ((PF || AL) ? 2 * L : 0));    // [2 chan][CB]
+  cplx* TWC = TWT + 2 * L;                            // [2][L]  second buffer of the four-step twiddles
+  double* PHI = reinterpret_cast<double*>(TWC + 2 * L);                       // [2 chan][CB]
 
   // thread roles: b = packed sequence, u = 0..R1-1 (step A: group u / TPC, r-slot u % TPC)
   int b, u;
@@ -385,40 +377,7 @@ __global__ void __launch_bounds__(CB * 2 * Geo<L>::TPC, (PFM == 1 || CB * 2 * Ge
   }
   const double* K = a.kvec + (MODE == ADV_COLS ? (long)sim * N : 0);
 
-  // asynchronous load of the tile of group pair t1 into STG
-  auto prefetch = [&](int t1) {
-    const int k1g0 = (t1 == 0) ? 0 : t1, k1g1 = (t1 == 0) ? (int)(N1 / 2) : (int)(N1 - t1);
-    if (MODE == ADV_COLS) {
-      for (int w = threadIdx.x; w < 2 * L * CB; w += NT) {
-        const int bb = w % CB, l = (w / CB) % L, gg = w / (CB * L);
-        const int sq = seq0 + bb;
-        cplx* dst = STG + LY::tidx(gg, l, bb);
-        if (sq < seq_end)
-          cp_async16(dst, a.fout + ((long)sim * N + (long)(gg ? k1g1 : k1g0) * L + l) * a.ld_out + 2 * (long)sq);
-        else *dst = cmake(0.0, 0.0);
-      }
-    } else {
-      for (int w = threadIdx.x; w < 2 * L * CB; w += NT) {
-        const int l = w % L, bb = (w / L) % CB, gg = w / (L * CB);
-        const int sq = seq0 + bb;
-        cplx* dst = STG + LY::tidx(gg, l, bb);
-        const long n = (long)(gg ? k1g1 : k1g0) * L + l;
-        if (sq < seq_end) {
-          const long ra = 2 * (long)sq, rb = ra + 1;
-          cp_async8(&dst->x, a.fout + ra * a.ld_out + n);
-          if (rb < a.nrows) cp_async8(&dst->y, a.fout + rb * a.ld_out + n);
-          else dst->y = a.phantom ? a.phantom[n] : 0.0;
-        } else *dst = cmake(0.0, 0.0);
-      }
-    }
-    for (int w = threadIdx.x; w < 2 * L; w += NT) {
-      const int n2 = w % L, gg = w / L;
-      cp_async16(TWT + w, a.twN + (long)n2 * (gg ? k1g1 : k1g0));
-    }
-    cp_async_commit();
-  };
-
-  // PFM 2: this thread's 16 elements of the tile of group pair t1 -> its own slots of S, and its share
+  // this thread's 16 elements of the tile of group pair t1 -> its own slots of S, and its share
   // of the tile's four-step twiddles -> twbuf
   // COLS: column base of this thread's packed sequence (element of row n at col0 + n * ld_out)
   double* const col0 = a.fout + (long)sim * N * a.ld_out + 2 * (long)seq;
@@ -456,8 +415,7 @@ __global__ void __launch_bounds__(CB * 2 * Geo<L>::TPC, (PFM == 1 || CB * 2 * Ge
   // parameter, so that no per-thread loop bounds stay live across the tile (they were spilled, and their reloads
   // queued behind the cp.async / LDS bursts: 12 % of the kernel in the ncu source view)
   const int t1_begin = chunk * t1_chunk;
-  if (PF) prefetch(t1_begin);
-  if (AL) prefetch_own(t1_begin, TWT);
+  prefetch_own(t1_begin, TWT);
 
   if (!EX) {
     // phi = (K[1] dt) c ; G = exp(-i N1 phi); PT[j] = G^j = H[j>>3] * Lo[j&7]
@@ -504,22 +462,7 @@ __global__ void __launch_bounds__(CB * 2 * Geo<L>::TPC, (PFM == 1 || CB * 2 * Ge
     cplx x[16];
     const int g = u / TPC, ta = u % TPC;
     const cplx* TWI;                                   // twiddles for the inverse at the end of this tile
-    if (PF) {
-      cp_async_wait_all();
-      __syncthreads();                                 // tile t1 is in STG
-      // ---------------- step A: staged tile -> registers, four-step twiddle, radix-R1
-#pragma unroll
-      for (int q = 0; q < NA; ++q)
-#pragma unroll
-        for (int j = 0; j < R1; ++j) {
-          const int n2 = (ta + TPC * q) + 8 * j;
-          x[q * R1 + j] = cmul(STG[LY::tidx(g, n2, b)], TWT[g * L + n2]);
-        }
-      for (int w = threadIdx.x; w < 2 * L; w += NT) TWC[w] = TWT[w];   // keep for the inverse (TWT gets the next tile's)
-      TWI = TWC;
-      __syncthreads();                                 // STG consumed, S free (previous tile's readers done)
-      if (has_next) prefetch(t1 + 1);
-    } else if (AL) {
+    {
       // own slots of S and this tile's twiddle buffer were filled by prefetch_own one tile earlier
       cplx* TWcur = (it & 1) ? TWC : TWT;
       TWI = TWcur;
@@ -531,29 +474,6 @@ __global__ void __launch_bounds__(CB * 2 * Geo<L>::TPC, (PFM == 1 || CB * 2 * Ge
         for (int j = 0; j < R1; ++j) {
           const int r = ta + TPC * q;
           x[q * R1 + j] = cmul(S[LY::sidx(g, j, r, b)], TWcur[g * L + r + 8 * j]);
-        }
-    } else {
-      // direct loads (4 CTAs per SM hide the latency); twiddles of this tile into shared memory
-#pragma unroll
-      for (int q = 0; q < NA; ++q)
-#pragma unroll
-        for (int j = 0; j < R1; ++j)
-          if (MODE == ADV_COLS)
-            x[q * R1 + j] = valid ? ldg_plain(col0 + ((long)K1G(g) * L + ta) * a.ld_out + (long)(TPC * q + 8 * j) * a.ld_out)
-                                  : cmake(0.0, 0.0);
-          else
-            x[q * R1 + j] = valid ? gload<MODE>(a, a.fout, a.ld_out, sim, seq, (long)K1G(g) * L + (ta + TPC * q) + 8 * j, false)
-                                  : cmake(0.0, 0.0);
-      __syncthreads();                                 // previous tile done with S, TWT, BASE
-      for (int w = threadIdx.x; w < 2 * L; w += NT) TWT[w] = ldg_c(a.twN + (long)(w % L) * K1G(w / L));
-      TWI = TWT;
-      __syncthreads();
-#pragma unroll
-      for (int q = 0; q < NA; ++q)
-#pragma unroll
-        for (int j = 0; j < R1; ++j) {
-          const int n2 = (ta + TPC * q) + 8 * j;
-          x[q * R1 + j] = cmul(x[q * R1 + j], TWT[g * L + n2]);
         }
     }
 #pragma unroll
@@ -663,7 +583,7 @@ __global__ void __launch_bounds__(CB * 2 * Geo<L>::TPC, (PFM == 1 || CB * 2 * Ge
 #pragma unroll
       for (int m = 0; m < R1; ++m) x[q * R1 + m] = S[LY::sidx(g, m, r, b)];
     }
-    if (AL && has_next) prefetch_own(t1 + 1, ((it + 1) & 1) ? TWC : TWT);
+    if (has_next) prefetch_own(t1 + 1, ((it + 1) & 1) ? TWC : TWT);
 #pragma unroll
     for (int q = 0; q < NA; ++q) {
       const int r = ta + TPC * q;
@@ -684,8 +604,9 @@ __global__ void __launch_bounds__(CB * 2 * Geo<L>::TPC, (PFM == 1 || CB * 2 * Ge
 
 template <int L, int CB>
 constexpr size_t pass2_smem(int mode, int pfm) {
-  return sizeof(cplx) * (size_t)(((mode == ADV_ROWS) ? CB * 2 * (L / 8) * 9 : 2 * L * CB) + (pfm == 1 ? 2 * L * CB : 0) +
-                                 2 * CB * (8 + L / 16 + 1) + 8 * CB + 3 * L + (pfm ? 2 * L : 0)) +
+  (void)pfm;
+  return sizeof(cplx) * (size_t)(((mode == ADV_ROWS) ? CB * 2 * (L / 8) * 9 : 2 * L * CB) +
+                                 2 * CB * (8 + L / 16 + 1) + 8 * CB + 3 * L + 2 * L) +
          sizeof(double) * 2 * CB;
 }
 

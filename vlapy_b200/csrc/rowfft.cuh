@@ -53,7 +53,6 @@ struct Args {
   // element (row, n) goes to the v-shard of rank q = n / part at [my_rank*nrows + row][n % part]
   int peer_mode, nparts, my_rank, lpart;   // part = 1 << lpart
   double* peer[8];
-  int l2_prefetch;      // rows ahead that thread 0 asks L2 to fetch (0: off)
   const double* addv;   // POISSON: driver rows [nrows][N] added to the result (nullable)
 };
 
@@ -511,11 +510,6 @@ __global__ void __launch_bounds__(P::T, 1) rowfft_kernel(const P prog) {
   for (long row = blockIdx.x; row < prog.a.nrows; row += gridDim.x) {
     long nxt = row + gridDim.x;
     if (nxt >= prog.a.nrows) nxt = -1;
-    const long pfrow = row + (long)prog.a.l2_prefetch * gridDim.x;
-    if (tid == 0 && prog.a.l2_prefetch > 0 && pfrow < prog.a.nrows) {      // L2 prefetch a few rows ahead
-      const double* p = prog.a.fin + pfrow * prog.a.ld_in;
-      asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"((unsigned)(P::N * 8)) : "memory");
-    }
 #pragma unroll
     for (int ph = 0; ph < P::NPH; ++ph) {
       prog.phase(ph, row, nxt, tid, r, smem_raw);

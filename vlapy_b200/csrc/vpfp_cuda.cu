@@ -696,7 +696,6 @@ static int run_rowfft(const double* f_in, long ld_in, double* f_out, long ld_out
   memset(&ra, 0, sizeof(ra));
   ra.fin = f_in; ra.ld_in = ld_in; ra.fout = f_out; ra.ld_out = ld_out; ra.kvec = kv; ra.cvec = e; ra.dt = dt;
   ra.nrows = rows;
-  ra.l2_prefetch = 0;
   int rc = get_twiddles(nv, &ra.twN);
   if (rc) return rc;
   if (scat && scat->mode) {
