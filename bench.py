@@ -137,6 +137,36 @@ def ensemble_arm(args):
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
+    # ---- parity: the first and last member of this rank's shard, PARITY_STEPS steps in the batch, against the same
+    # simulation run ALONE through the single-grid path of the library (vlapy_b200.core.step.get_timestep)
+    from vlapy_b200.core import step as core_step
+    stp = {"e": torch.zeros((B, nx), dtype=torch.float64, device=dev), "f": f_host.to(dev)}
+    for i in range(PARITY_STEPS):
+        stp = step_fn(stp, dt * i)
+    perr = torch.zeros(2, dtype=torch.float64, device=dev)
+    rules = {"time": "first-last", "space": ["k0", "k1"]}
+    p1 = dict(params, backend={"core": "b200"})
+    for j in sorted({0, B - 1}):
+        stuff_j = dict(kx=kxs[j], x=xs[j], one_over_kx=ooks[j], v=v, kv=kv, nv=nv, nx=nx, dv=dv, dt=dt, nu=0.0,
+                       rules_to_store_f=rules, pulse_dictionary=pulses[j], driver_function=None)
+        one = core_step.get_timestep(all_params=p1, stuff_for_time_loop=stuff_j)
+        times = dt * np.arange(PARITY_STEPS)
+        arr = ops.pulses_to_array(pulses[j])
+        xj = torch.from_numpy(xs[j]).to(dev)
+        drv_rows = torch.stack([ops.driver(xj, float(t), arr) for t in times])
+        work = make_work({"nx": nx, "nv": nv}, torch.zeros(nx, dtype=torch.float64, device=dev), f_host[j].to(dev),
+                         PARITY_STEPS, dev, drv_rows, times)
+        for i in range(PARITY_STEPS):
+            work, _ = one(work, i)
+        perr[0] = torch.maximum(perr[0], (stp["f"][j] - work["f"]).abs().max() / work["f"].abs().max())
+        perr[1] = torch.maximum(perr[1], (stp["e"][j] - work["e"]).abs().max())     # absolute: E ~ 1e-10 after three steps
+    if world > 1:
+        dist.all_reduce(perr, op=dist.ReduceOp.MAX)
+    parity = {"vs": "first and last member of every rank's shard run alone through the single-grid path of this library",
+              "steps": PARITY_STEPS, "max_rel_err_f_vs_single": float(perr[0]), "max_abs_err_e_vs_single": float(perr[1]),
+              "checks_member0": {"sum_f": float(stp["f"][0].sum()), "e_max": float(stp["e"][0].abs().max()),
+                                 "mean_n": float(stp["series"][0, 0])}}
+    del stp, work
     sampler = ClockSampler(local_rank); sampler.start()
     for i in range(W):
         state = step_fn(state, dt * i)
@@ -182,7 +212,7 @@ def ensemble_arm(args):
                              "traffic": None, "peak_source": peak_src},
                 "e2e": {"value": cells * K / sec, "unit": "cell-updates/s",
                         "h2d_bytes_per_step": C4_BATCH * nx * nv * 8 / K, "d2h_bytes_per_step": C4_BATCH * nx * nv * 8 / K},
-                "mean_n_last_step": mean_n}
+                "parity": parity, "mean_n_last_step": mean_n}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
