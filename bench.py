@@ -422,10 +422,11 @@ def make_work(cfg, e_dev, f_dev, total, dev, drv_rows, times):
     import torch
     from vlapy_b200.core import step
     nx, nv = cfg["nx"], cfg["nv"]
+    block = torch.zeros((len(step.FIELD_KEYS), total, nx), dtype=torch.float64, device=dev)      # as outer_loop._device_storage
     return {
         "time_batch": times, "driver_array_batch": drv_rows, "e": e_dev, "f": f_dev,
         "stored_f": torch.zeros((total, 2, nv), dtype=torch.complex128, device=dev),
-        "fields": {k: torch.zeros((total, nx), dtype=torch.float64, device=dev) for k in step.FIELD_KEYS},
+        "fields": dict({k: block[j] for j, k in enumerate(step.FIELD_KEYS)}, _block=block),
         "series": {"_rows": torch.zeros((total, 7), dtype=torch.float64, device=dev)},
         "_moment_scratch": torch.zeros((8, nx), dtype=torch.float64, device=dev),
     }

@@ -109,10 +109,17 @@ def get_fields_update(dv, v):
     def update_fields(temp_storage_fields, e, de, f, i, moments=None):
         if moments is None:
             moments = ops.moments(f, v_d, dv, nmom=8)
-        temp_storage_fields["e"][i] = e
-        temp_storage_fields["driver"][i] = de
-        for k, name in enumerate(("n", "j", "T", "q", "fv4", "vN")):
-            temp_storage_fields[name][i] = moments[k]
+        block = temp_storage_fields.get("_block")
+        if block is not None:
+            # the eight fields are rows of ONE device buffer (len(FIELD_KEYS), nt, nx): three copies instead of eight
+            block[0, i] = e
+            block[1, i] = de
+            block[2:8, i] = moments[:6]
+        else:
+            temp_storage_fields["e"][i] = e
+            temp_storage_fields["driver"][i] = de
+            for k, name in enumerate(("n", "j", "T", "q", "fv4", "vN")):
+                temp_storage_fields[name][i] = moments[k]
         temp_storage_fields["_moments"] = moments
         return temp_storage_fields
 

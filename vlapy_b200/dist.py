@@ -198,6 +198,14 @@ class DeviceBackend:
         m = self.ops.xmodes(fx, nmodes, x_offset=self.topo.x0, nx_total=self.topo.nx)[0]
         return torch.view_as_real(m).contiguous()
 
+    def xmodes_partial_into(self, fx, out):
+        """the same, written into ``out`` (1, nmodes, nv, 2) -- a row of the per-loop buffer -- without a copy"""
+        self.ops.xmodes(fx, out.shape[1], out=out, x_offset=self.topo.x0, nx_total=self.topo.nx)
+
+    def series_means(self, mom, e_loc, de_loc, out):
+        """the seven series entries of vlapy/core/step.py:202-224 as means over this rank's x cells: one kernel"""
+        self.ops.series(mom, e_loc, de_loc, out=out)
+
     def zeros(self, shape):
         return torch.zeros(shape, dtype=torch.float64, device=self.x.device)
 
@@ -272,7 +280,8 @@ def get_sharded_timestep(all_params, stuff_for_time_loop, topo, backend=None):
 
     def timestep(state, t, de=None, store=None):
         e, f = vp_step(e=state["e"], f=state["f"], t=t)
-        mom = store["moments"] if store is not None else None
+        # the eight row moments of this step go straight into their row of the per-loop buffer (no copy)
+        mom = store["moments_all"][store["i"]] if store is not None else None
         if collide:
             f = ops_["fp_step"](f, moments_out=mom)
         else:
@@ -285,17 +294,23 @@ def get_sharded_timestep(all_params, stuff_for_time_loop, topo, backend=None):
         if store is not None:
             i = store["i"]
             sl = slice(topo.x0, topo.x0 + topo.nxl)
-            store["fields_e"][i] = e[sl]
+            el = e[sl]
+            store["fields_e"][i] = el
             if de is not None:
                 store["fields_driver"][i] = de[sl]
-            store["fields_mom"][i] = mom[:6]
-            # series: local sums over this rank's x cells (means are finished after an all-reduce)
-            el = e[sl]
-            store["series_sum"][i, 0:3] = mom[0:3].sum(dim=1)
-            store["series_sum"][i, 3] = (el * el).sum()
-            store["series_sum"][i, 4] = (de[sl] * de[sl]).sum() if de is not None else 0.0
-            store["series_sum"][i, 5:7] = mom[6:8].sum(dim=1)
-            store["modes_partial"][i] = backend.xmodes_partial(f.t, store["modes_partial"].shape[1])
+            # series: means over this rank's x cells (finished by an all-reduce at the storage cadence)
+            if hasattr(backend, "series_means"):
+                backend.series_means(mom, el, de[sl] if de is not None else None, store["series_mean"][i])
+            else:
+                row = store["series_mean"][i]
+                row[0:3] = mom[0:3].mean(dim=1)
+                row[3] = (el * el).mean()
+                row[4] = (de[sl] * de[sl]).mean() if de is not None else 0.0
+                row[5:7] = mom[6:8].mean(dim=1)
+            if hasattr(backend, "xmodes_partial_into"):
+                backend.xmodes_partial_into(f.t, store["modes_partial"][i:i + 1])
+            else:
+                store["modes_partial"][i] = backend.xmodes_partial(f.t, store["modes_partial"].shape[1])
             store["i"] = i + 1
         return {"e": e, "f": f}
 
@@ -304,20 +319,24 @@ def get_sharded_timestep(all_params, stuff_for_time_loop, topo, backend=None):
 
 
 def make_store(topo, backend, nsteps, nmodes=2):
+    """per-loop buffers of one rank: row i of every buffer belongs to step i of the loop.  ``moments_all`` receives the
+    eight row moments of the kernels directly; ``fields_mom`` is its view of the six stored v-moments."""
+    moments_all = backend.zeros((nsteps, 8, topo.nxl))
     return {
         "i": 0,
-        "moments": backend.zeros((8, topo.nxl)),
+        "moments_all": moments_all,
+        "fields_mom": moments_all[:, :6],
         "fields_e": backend.zeros((nsteps, topo.nxl)),
         "fields_driver": backend.zeros((nsteps, topo.nxl)),
-        "fields_mom": backend.zeros((nsteps, 6, topo.nxl)),
-        "series_sum": backend.zeros((nsteps, 7)),
+        "series_mean": backend.zeros((nsteps, 7)),
         "modes_partial": backend.zeros((nsteps, nmodes, topo.nv, 2)),
     }
 
 
 def finish_store(topo, store):
-    """storage cadence: turn local sums into global means / modes (two small all-reduces)"""
-    series = topo.all_reduce_sum(store["series_sum"].clone()) / topo.nx
+    """storage cadence: turn the slab means into global means (equal slabs: the mean of the means) and the slab
+    partials of the x-modes into the modes (two small all-reduces)"""
+    series = topo.all_reduce_sum(store["series_mean"].clone()) / topo.world
     modes = topo.all_reduce_sum(store["modes_partial"].clone())
     return series, torch.view_as_complex(modes.contiguous())
 

@@ -230,7 +230,7 @@ def get_inner_loop_stepper(all_params, stuff_for_time_loop, steps_in_loop):
                 "driver_array_batch": drv,
                 "e": d["e"], "f": d["f"],
                 "stored_f": d["stored_f"],
-                "fields": {k: d["fields"][j] for j, k in enumerate(step.FIELD_KEYS)},
+                "fields": dict({k: d["fields"][j] for j, k in enumerate(step.FIELD_KEYS)}, _block=d["fields"]),
                 "series": {"_rows": d["series_rows"]},
                 "_moment_scratch": d["moments"],
             }
