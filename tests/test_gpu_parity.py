@@ -663,6 +663,35 @@ def test_ensemble_matches_independent_oracle_runs(dev, integ, nu_log):
     assert ensemble.shard(1024, 3, 8) == (384, 512) and ensemble.shard(10, 3, 4) == (9, 10)
 
 
+def test_ensemble_at_c4_member_size_vs_oracle(dev):
+    """BASELINE config 4 at its real member size: a batch of 256 x 512 Landau-damping simulations with their own
+    box lengths (k0 from the sweep's ends and middle), 12 collisionless leapfrog steps through the batched kernels
+    (mid-size single-pass advection, warp-per-row moments) against the oracle run of every member"""
+    from vlapy_b200 import ensemble
+    k0s = [0.25, 0.3, 0.35, 0.45]
+    cfgs = [O.make_config(256, 512, k0, tmax=80, nt=500, a0=1e-3, t_R=20) for k0 in k0s]
+    stuff = dict(kx=np.stack([c["kx"] for c in cfgs]), one_over_kx=np.stack([c["one_over_kx"] for c in cfgs]),
+                 x=np.stack([c["x"] for c in cfgs]), v=cfgs[0]["v"], kv=cfgs[0]["kv"], dv=cfgs[0]["dv"],
+                 dt=cfgs[0]["dt"], nu=0.0, pulses=[c["pulses"] for c in cfgs])
+    params = make_params(cfgs[0], "leapfrog", "lb")
+    params["nu"] = 0.0
+    step_fn = ensemble.get_ensemble_timestep(params, stuff)
+    state = {"e": torch.from_numpy(np.stack([c["e0"] for c in cfgs])).to(dev),
+             "f": torch.from_numpy(np.stack([c["f0"] for c in cfgs])).to(dev)}
+    nsteps = 12
+    for i in range(nsteps):
+        state = step_fn(state, cfgs[0]["dt"] * i)
+    f, e = state["f"].cpu().numpy(), state["e"].cpu().numpy()
+    mom, ser = state["moments"].cpu().numpy(), state["series"].cpu().numpy()
+    for b, c in enumerate(cfgs):
+        c = dict(c, nu=0.0)
+        e_ref, f_ref, hist = O.run_steps(c, nsteps, "leapfrog", "lb", collect=True)
+        assert rel_err(f[b], f_ref) < TOL
+        assert np.max(np.abs(e[b] - e_ref)) < 1e-13
+        assert rel_err(mom[:3, b], hist["mom"][-1][:3]) < TOL
+        np.testing.assert_allclose(ser[b, :7], hist["series"][-1][:7], rtol=1e-9, atol=1e-13)
+
+
 def test_smoke_entry(dev):
     import __graft_entry__ as ge
     assert ge.smoke()
