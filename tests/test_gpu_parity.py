@@ -720,6 +720,27 @@ def test_single_pass_row_kernel(dev, nv, rows):
         assert rel_err(one.cpu().numpy(), three.cpu().numpy()) < TOL
 
 
+def test_resume_from_a_stored_state(dev):
+    """a FRESH inner loop restarted from the host copy of the state after loop 1 (what the
+    storage layer wrote as full_distribution) reproduces loop 2 of an uninterrupted run"""
+    from vlapy_b200 import outer_loop
+    cfg = O.nlepw_config(nx=32, nv=256, k0=0.35, log_nu=-2)
+    params = make_params(cfg, "leapfrog", "lb")
+    nt = 10
+    straight = run_inner_loops(cfg, params, nt, 2)
+    sim, inner = outer_loop.get_sim_config_and_inner_loop_step(params, make_stuff(cfg, RULES), nt, RULES)
+    sim = outer_loop.resume_from(sim, straight[0]["f"], straight[0]["e"],
+                                 mean_cum_de2_previous=straight[0]["series"]["mean_cum_de2"][-1])
+    t = cfg["dt"] * np.arange(nt, 2 * nt)
+    drv = np.stack([cfg["driver_function"](ti) for ti in t])
+    sim = inner(time_array=t, driver_array=drv, temp_storage=sim)
+    assert np.array_equal(sim["f"], straight[1]["f"]) and np.array_equal(sim["e"], straight[1]["e"])
+    for k in ("mean_n", "mean_T", "mean_e2", "mean_cum_de2"):
+        np.testing.assert_allclose(sim["series"][k], straight[1]["series"][k], rtol=1e-14, atol=0)
+    with pytest.raises(ValueError):
+        outer_loop.resume_from(sim, straight[0]["f"][0], straight[0]["e"])
+
+
 def test_cuda_graph_survives_growth_of_the_library_scratch(dev):
     """a captured step keeps the pointers of the library's reduction scratch (x-mode partials, density
     partials).  A larger problem in the same process makes that scratch grow; outgrown blocks are retired, not freed,

@@ -266,6 +266,23 @@ def get_inner_loop_stepper(all_params, stuff_for_time_loop, steps_in_loop):
 
 
 
+def resume_from(temp_storage, f, e, mean_cum_de2_previous=0.0):
+    """Restart hook (the reference leaves it as a TODO at vlapy/manager.py:118-119): continue a
+    simulation from a stored state, e.g. ``f`` = the last ``full_distribution`` record that vlapy/storage.py:211-231
+    wrote (shape (nx, nv), or this rank's x-slab under the sharded inner loop) and ``e`` = the matching field row.
+    The device-resident copies are dropped, so the next ``inner_loop`` call uploads these arrays; the cumulative
+    driver energy of vlapy/outer_loop.py:218-245 restarts from ``mean_cum_de2_previous``.  The caller starts the
+    manager's loop at the step index of the record, so that ``time_array`` / ``driver_array`` continue from there."""
+    f = np.array(f, dtype=np.float64, order="C")
+    e = np.array(e, dtype=np.float64, order="C")
+    if f.ndim != 2 or e.ndim != 1 or e.shape[0] < f.shape[0]:
+        raise ValueError("resume_from: f must be (nx, nv) or an x-slab of it, e the full field (nx)")
+    temp_storage.pop("_dev", None)
+    temp_storage["f"], temp_storage["e"] = f, e
+    temp_storage["mean_cum_de2_previous"] = float(mean_cum_de2_previous)
+    return temp_storage
+
+
 def sharded_world(all_params):
     """Number of ranks the inner loop is sharded over: the size of the default process group when
     torch.distributed is initialised (torchrun, one process per GPU) and ``backend.sharded`` is not False."""
