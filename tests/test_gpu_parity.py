@@ -720,6 +720,38 @@ def test_single_pass_row_kernel(dev, nv, rows):
         assert rel_err(one.cpu().numpy(), three.cpu().numpy()) < TOL
 
 
+def test_scattering_vdfdx_with_emulated_ranks(dev):
+    """the scattering v df/dx of the multi-GPU path (last pass stores into the peers' x-shards) with four ranks emulated
+    in one process: every "peer" buffer is local.  Result and summed partial densities against the one-grid operator
+    (same kernels per column) and the oracle."""
+    from vlapy_b200 import ops
+    nx, nv, P = 2048, 8192, 4
+    nxl, nvl = nx // P, nv // P
+    cfg = O.nlepw_config(nx=nx, nv=nv, k0=0.35, log_nu=-2)
+    rng = np.random.default_rng(5)
+    f = cfg["f0"] * (1.0 + 0.1 * np.sin(0.35 * cfg["x"]))[:, None] + 1e-3 * rng.standard_normal((nx, nv))
+    fd = torch.from_numpy(f).to(dev)
+    kx, v = torch.from_numpy(cfg["kx"]).to(dev), torch.from_numpy(cfg["v"]).to(dev)
+    dt, dv = 0.25, float(cfg["dv"])
+    n_one = torch.empty(nx, dtype=torch.float64, device=dev)
+    one = ops.vdfdx_exp(fd, kx, v, dt, flags=1, density_out=n_one, dv=dv)
+    shards = [torch.zeros((nxl, nv), dtype=torch.float64, device=dev) for _ in range(P)]
+    ptrs = [t.data_ptr() for t in shards]
+    scratch = torch.empty((nx, nvl), dtype=torch.float64, device=dev)
+    n_sum = torch.zeros(nx, dtype=torch.float64, device=dev)
+    for r in range(P):
+        fv = fd[:, r * nvl:(r + 1) * nvl].contiguous()
+        n_r = torch.empty(nx, dtype=torch.float64, device=dev)
+        edge = (1 if r == 0 else 0) | (2 if r == P - 1 else 0)
+        ops.vdfdx_exp_scatter(fv, kx, v[r * nvl:(r + 1) * nvl].contiguous(), dt, scratch, ptrs, r, flags=1,
+                              density_out=n_r, dv=dv, edge_flags=edge)
+        n_sum += n_r
+    got = torch.cat(shards, dim=0)
+    assert rel_err(got.cpu().numpy(), one.cpu().numpy()) < 1e-14      # same kernels, the phase tables start per shard
+    assert rel_err(n_sum.cpu().numpy(), n_one.cpu().numpy()) < 1e-14
+    assert rel_err(got.cpu().numpy(), O.vdfdx_exponential(f, dt, cfg["kx"], cfg["v"])) < TOL
+
+
 def test_resume_from_a_stored_state(dev):
     """a FRESH inner loop restarted from the host copy of the state after loop 1 (what the
     storage layer wrote as full_distribution) reproduces loop 2 of an uninterrupted run"""
