@@ -41,6 +41,7 @@ def main():
         "edfdv_exp(table)": (lambda: ops.edfdv_exp(f, e, kv, 0.125, out=out, flags=1), gb),
         "edfdv_exp(table,3pass)": (lambda: ops.edfdv_exp(f, e, kv, 0.125, out=out, flags=5), gb),
         "vdfdx_exp(table)": (lambda: ops.vdfdx_exp(f, kx, v, 0.25, out=out, flags=1), gb),
+        "vdfdx_exp(table)+density": (lambda: ops.vdfdx_exp(f, kx, v, 0.25, out=out, flags=1, density_out=n, dv=cfg["dv"]), gb),
         "edfdv_exp(exact)": (lambda: ops.edfdv_exp(f, e, kv, 0.125, out=out, flags=0), gb),
         "vdfdx_exp(exact)": (lambda: ops.vdfdx_exp(f, kx, v, 0.25, out=out, flags=0), gb),
         "fp_fast+mom": (lambda: ops.fp_step(f, v, cfg["nu"], cfg["dt"], cfg["dv"], "lb", out=out, moments_out=mom, vgrid=vg), gb),

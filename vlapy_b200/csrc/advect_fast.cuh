@@ -275,7 +275,9 @@ __global__ void __launch_bounds__(CB* Geo<L>::TPC) pass13_kernel(const FastArgs 
         double d = 0.0;
 #pragma unroll 8
         for (int bb = 0; bb < CB; ++bb) d += D[l * DP + bb];
-        a.dens_partial[((long)bt * a.nsim + sim) * a.N + (long)l * N2 + n2] = d;
+        // cell x = l N2 + n2 is parked at n2 L + l: the CTA writes 1 KB in one piece (x order: 128 lone 8-byte writes,
+        // 1 KB apart); dens_reduce_kernel puts the sums back in x order
+        a.dens_partial[((long)bt * a.nsim + sim) * a.N + (long)n2 * L + l] = d;
       }
     }
   }
@@ -286,14 +288,21 @@ __global__ void __launch_bounds__(CB* Geo<L>::TPC) pass13_kernel(const FastArgs 
 // [g gs, (g+1) gs) in order and leaves the result IN PLACE in the group's first tile row (read and written by the same
 // thread); the second launch (stride = gs) adds the group sums in order.  Deterministic.  (Measured and rejected: eight
 // interleaved accumulators per thread, 90 us against 59 us for 512 x 16384 partials.)
-__global__ void dens_reduce_kernel(double* __restrict__ partial, int ntiles, int stride, long n, double* __restrict__ out) {
+// The partial rows hold cell x = l N2 + n2 of a simulation at n2 L + l (pass 3 writes them that way); the final stage
+// stores in x order.
+__global__ void dens_reduce_kernel(double* __restrict__ partial, int ntiles, int stride, long n, double* __restrict__ out,
+                                   int L, int N2) {
   const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const int t0 = blockIdx.y * ntiles * stride;
   double s = 0.0;
   for (int t = 0; t < ntiles; ++t) s += partial[(long)(t0 + t * stride) * n + i];
-  if (out) out[i] = s;
-  else partial[(long)t0 * n + i] = s;
+  if (out) {
+    const long N = (long)L * N2, p = i % N;
+    out[i - p + (p % L) * N2 + p / L] = s;
+  } else {
+    partial[(long)t0 * n + i] = s;
+  }
 }
 
 // ------------------------------------------------------------------------------------------

@@ -446,10 +446,10 @@ static int run_advect(AdvectProg a, cudaStream_t st, int flags = VPFP_PHASE_EXAC
         ProfScope ps("vdfdx.density_reduce", st, groups > 1 ? 2 : 1);
         const unsigned gx = (unsigned)((n + 255) / 256);
         if (groups > 1) {
-          fast::dens_reduce_kernel<<<dim3(gx, groups), 256, 0, st>>>(fa.dens_partial, dens_tiles / groups, 1, n, nullptr);
-          fast::dens_reduce_kernel<<<gx, 256, 0, st>>>(fa.dens_partial, groups, dens_tiles / groups, n, dens->out);
+          fast::dens_reduce_kernel<<<dim3(gx, groups), 256, 0, st>>>(fa.dens_partial, dens_tiles / groups, 1, n, nullptr, fa.N1, fa.N2);
+          fast::dens_reduce_kernel<<<gx, 256, 0, st>>>(fa.dens_partial, groups, dens_tiles / groups, n, dens->out, fa.N1, fa.N2);
         } else {
-          fast::dens_reduce_kernel<<<gx, 256, 0, st>>>(fa.dens_partial, dens_tiles, 1, n, dens->out);
+          fast::dens_reduce_kernel<<<gx, 256, 0, st>>>(fa.dens_partial, dens_tiles, 1, n, dens->out, fa.N1, fa.N2);
         }
       }
       CUDA_TRY(cudaGetLastError());
