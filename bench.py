@@ -213,6 +213,13 @@ def ensemble_arm(args):
                 "e2e": {"value": cells * K / sec, "unit": "cell-updates/s",
                         "h2d_bytes_per_step": C4_BATCH * nx * nv * 8 / K, "d2h_bytes_per_step": C4_BATCH * nx * nv * 8 / K},
                 "parity": parity, "mean_n_last_step": mean_n}
+        if world == 1 and not args.no_cpu:
+            # one member of the ensemble (the members are independent) through the oracle port on one host core
+            v1, _ = run_cpu_steps("c4", nx, nv, 20, 2, workers=1)
+            line["cpu_baseline"] = {"value": v1, "unit": "cell-updates/s", "cores": 1, "kind": "port",
+                                    "sample": "oracle port (numpy/scipy, scipy.fft workers=1 as the reference runs it) on ONE "
+                                              "%dx%d member of the ensemble, 20 steps after 2 warm-up; host has %d cores"
+                                              % (nx, nv, os.cpu_count() or 1)}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

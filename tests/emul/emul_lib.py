@@ -194,6 +194,18 @@ def midfft_cols(f, kx, v, dt, batch=1):
     return out
 
 
+def midfft_cols_density(f, kx, v, dt, dv, edge_flags=3, batch=1):
+    """the same with the charge density fused into the store phase; returns (f_out, n (batch, nx))"""
+    f = np.ascontiguousarray(f); out = np.empty_like(f)
+    nx, ncols = f.shape[-2], f.shape[-1]
+    n = np.empty((batch, nx))
+    rc = lib().emul_midfft_cols_density(_p(f), c_long(ncols), _p(out), c_long(ncols), _p(np.ascontiguousarray(kx)),
+                                        _p(np.ascontiguousarray(v)), c_double(dt), c_int(batch), c_int(nx), c_int(ncols),
+                                        c_double(dv), c_int(edge_flags), _p(n))
+    assert rc == 0
+    return out, n
+
+
 def xmodes(f, nmodes=2):
     f = np.ascontiguousarray(f); nx, ncols = f.shape
     out = np.zeros((nmodes, ncols, 2))

@@ -334,6 +334,35 @@ extern "C" int emul_midfft(int mode, const double* f_in, long ld_in, double* f_o
   return 0;
 }
 
+// v df/dx with the charge density fused into the store phase (Prog<..., DENS = true>); the sum over the column tiles
+// (fast::dens_reduce_kernel on the device) is done here on the host, in tile order
+extern "C" int emul_midfft_cols_density(const double* f_in, long ld_in, double* f_out, long ld_out, const double* kvec,
+                                        const double* cvec, double dt, int nsim, int nx, int ncols, double dv,
+                                        int edge_flags, double* n_out) {
+  midfft::Args a;
+  memset(&a, 0, sizeof(a));
+  const int N = nx;
+  a.nsim = nsim; a.nrows = N; a.nseq = ncols / 2;
+  std::vector<cplx> tw = make_tw(N);
+  a.fin = f_in; a.ld_in = ld_in; a.fout = f_out; a.ld_out = ld_out; a.kvec = kvec; a.cvec = cvec; a.dt = dt;
+  a.tw = tw.data();
+  const int CB = (N == 1024) ? 4 : 8;
+  const int tiles = (a.nseq + CB - 1) / CB;
+  std::vector<double> partial((size_t)tiles * nsim * N, -1.0);
+  a.dens_partial = partial.data(); a.dv = dv; a.edge_flags = edge_flags;
+  if (N == 256) { midfft::Prog<256, 8, 4, ADV_COLS, 8, true> p; p.a = a; run_midfft(p); }
+  else if (N == 512) { midfft::Prog<512, 8, 8, ADV_COLS, 8, true> p; p.a = a; run_midfft(p); }
+  else if (N == 1024) { midfft::Prog<1024, 16, 8, ADV_COLS, 4, true> p; p.a = a; run_midfft(p); }
+  else return 1;
+  const long n = (long)nsim * N;
+  for (long i = 0; i < n; ++i) {
+    double s2 = 0.0;
+    for (int t = 0; t < tiles; ++t) s2 += partial[(size_t)t * n + i];
+    n_out[i] = s2;
+  }
+  return 0;
+}
+
 // ---- single-pass row kernel (vlapy_b200/csrc/rowfft.cuh): per-thread registers persist across phases
 #include "../../vlapy_b200/csrc/rowfft.cuh"
 template <class P>

@@ -326,6 +326,19 @@ def test_midfft_programs(n, monkeypatch):
         out = E.midfft_cols(g, kx, vv, dt, batch=2)
         for s in range(2):
             assert rel_err(out[s], O.vdfdx_exponential(g[s], dt, kx[s], vv)) < TOL
+    if n <= 1024:
+        # charge density fused into the store phase: same f, n = trapz_v of it (whole grid and the slices of a v-shard)
+        for edge in (3, 1, 2, 0):
+            out2, dens = E.midfft_cols_density(g, kx, vv, 0.16, 0.05, edge_flags=edge, batch=2)
+            w = np.full(ncols, 0.05)
+            if edge & 1:
+                w[0] *= 0.5
+            if edge & 2:
+                w[-1] *= 0.5
+            for s in range(2):
+                ref = O.vdfdx_exponential(g[s], 0.16, kx[s], vv)
+                assert rel_err(out2[s], ref) < TOL
+                assert rel_err(dens[s], (ref * w).sum(axis=1)) < TOL
 
 
 @pytest.mark.parametrize("nx", [4096, 8192, 16384])

@@ -36,6 +36,10 @@ struct Args {
   const double* cvec;        // COLS: v[ncols]; ROWS: e[nrows]
   double dt;
   const cplx* tw;            // exp(-2 pi i m / L), L entries
+  // fused charge density (COLS, Prog<..., DENS = true>): dens_partial[(column tile * nsim + sim) * L + x] = weighted sum
+  // (trapezoid, vlapy/core/field.py:27-36) over the 2 CB columns of the tile; summed over the tiles by
+  // fast::dens_reduce_kernel.  edge_flags: bit 0 / 1 = the first / last column is an end of the global v axis.
+  double* dens_partial; double dv; int edge_flags;
 };
 
 // asynchronous copies global -> shared (host emulation: plain copies)
@@ -59,9 +63,11 @@ VPFP_HD void cp_async_wait() {
 #endif
 }
 
-template <int L_, int R1_, int R2_, int MODE_, int CB_>
+template <int L_, int R1_, int R2_, int MODE_, int CB_, bool DENS_ = false>
 struct Prog {
   static constexpr int L = L_, R1 = R1_, R2 = R2_, MODE = MODE_, CB = CB_;
+  static constexpr bool DENS = DENS_;
+  static_assert(!DENS_ || MODE_ == ADV_COLS, "the fused density belongs to v df/dx");
   static_assert(R1 * R2 * 8 == L, "L = R1 * R2 * 8");
   static constexpr int S = L / 8;              // stage-C sub-transforms
   static constexpr int TPC = L / 16;           // threads per sequence
@@ -71,10 +77,13 @@ struct Prog {
   static constexpr int XELEMS = R1 * PITCH;    // exchange buffer of one sequence
   static constexpr int NQA = 16 / R1, NQB = 16 / R2;
   static constexpr int NT12 = L / 32 + 1;      // table over j >> 4, j = 0 .. L/2
-  static constexpr int NPH = 5;
+  static constexpr int NPH = DENS ? 8 : 5;
+  static constexpr int DP = CB * TPC + 1;      // pitch of the density exchange buffer D[8][DP] (doubles): two rounds of 8
+                                               // output slots, so that the buffer does not cost a resident CTA
   static constexpr int NTWB = R2 * 8;          // stage-B twiddles
   static constexpr bool PREFETCH = (MODE == ADV_COLS);   // ROWS would prefetch 8-byte pieces (2-way bank conflicts): direct loads
-  static constexpr long SMEM_BYTES = (long)sizeof(cplx) * ((long)XELEMS * CB + L + NTWB + 2L * CB * (16 + NT12));
+  static constexpr long SMEM_BYTES = (long)sizeof(cplx) * ((long)XELEMS * CB + L + NTWB + 2L * CB * (16 + NT12)) +
+                                     (DENS ? (long)sizeof(double) * 8 * DP : 0);
 
   struct Regs {
     cplx x[16];
@@ -93,6 +102,7 @@ struct Prog {
   VPFP_HD static cplx* twb(unsigned char* smem) { return twa(smem) + L; }                    // [R2][8]: W_L^(R1 n3 k2)
   VPFP_HD static cplx* t0(unsigned char* smem) { return twb(smem) + NTWB; }            // [2][CB][16]
   VPFP_HD static cplx* t12(unsigned char* smem) { return t0(smem) + 2 * CB * 16; }     // [2][CB][NT12]
+  VPFP_HD static double* dbuf(unsigned char* smem) { return reinterpret_cast<double*>(t12(smem) + 2 * CB * NT12); }
   // phase-table index of entry i (of n) of channel ch of sequence b: the lanes of a warp run along b (COLS) or share b
   // and differ in i (ROWS)
   VPFP_HD static int tix(int ch, int b, int i, int n) { return (MODE == ADV_COLS) ? (ch * n + i) * CB + b : (ch * CB + b) * n + i; }
@@ -204,6 +214,17 @@ struct Prog {
     const cplx X1 = cmul(Pa, U), X2 = cmul(Pb, V);
     Zr = cadd(X1, X2);
     if (!selfpair) Zpr = cconj(csub(X1, X2));
+  }
+
+  // fused density: the weighted sum of the two columns of this thread for its output slots j0 .. j0 + 7 -> D[j - j0][tid]
+  VPFP_HD void dens_park(int j0, int seq, int tid, const cplx* x, unsigned char* smem) const {
+    double* D = dbuf(smem);
+    const int ncols = 2 * a.nseq;
+    const bool valid = seq < a.nseq;
+    const double wa = valid ? ((2 * seq == 0 && (a.edge_flags & 1)) ? 0.5 * a.dv : a.dv) : 0.0;
+    const double wb = valid ? ((2 * seq + 1 == ncols - 1 && (a.edge_flags & 2)) ? 0.5 * a.dv : a.dv) : 0.0;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) D[j * DP + tid] = wa * x[j0 + j].x + wb * x[j0 + j].y;
   }
 
   // prefetched: this tile was brought into the thread's own slots by prefetch_own; nexttile: the tile this CTA handles
@@ -327,6 +348,27 @@ struct Prog {
           for (int n2 = 0; n2 < R2; ++n2) X[xi(b, k1 * PITCH + n2 * 8 + n3)] = x[q * R2 + n2];
         }
       } break;
+      case 5:
+      case 7: {
+        // ---- fused density: thread (b, u) adds, in a fixed order, the CB column pairs of the slots j = b, b + CB, ...
+        // of this round (slots 0..7 in phase 5, 8..15 in phase 7)
+        if (!DENS) break;
+        const double* D = dbuf(smem);
+        const long tb = (a.nseq + CB - 1) / CB;
+        double* dst = a.dens_partial + ((tile % tb) * a.nsim + t.sim) * (long)L;
+        const int round = (ph == 7);
+#pragma unroll
+        for (int jg = 0; jg < 8 / CB; ++jg) {
+          const int jl = b + CB * jg, j = jl + 8 * round, q = j / R1, n1 = j % R1;
+          double sum = 0.0;
+#pragma unroll
+          for (int bb = 0; bb < CB; ++bb) sum += D[jl * DP + u * CB + bb];
+          dst[n1 * LA + u + TPC * q] = sum;
+        }
+      } break;
+      case 6: {
+        if (DENS) dens_park(8, seq, tid, x, smem);
+      } break;
       default: {
         // ---- inverse stage A, store; the thread's slots are free once they are in registers: next tile into them
 #pragma unroll
@@ -345,6 +387,7 @@ struct Prog {
 #pragma unroll
           for (int n1 = 0; n1 < R1; ++n1) gstore(t, seq, n1 * LA + rr, x[q * R1 + n1]);
         }
+        if (DENS) dens_park(0, seq, tid, x, smem);
       } break;
     }
   }

@@ -338,13 +338,33 @@ static bool midfft_eligible(const AdvectProg& a, int flags) {
   return a.N == 256 || a.N == 512 || a.N == 1024 || a.N == 2048;
 }
 
-static int run_midfft(const AdvectProg& a, cudaStream_t st) {
+struct DensityReq;
+static int midfft_density(midfft::Args& ma, const AdvectProg& a, const DensityReq* dens, int CB, cudaStream_t st, bool finish);
+
+static int run_midfft(const AdvectProg& a, cudaStream_t st, const DensityReq* dens = nullptr, bool* dens_done = nullptr) {
   midfft::Args ma;
   ma.nsim = a.nsim; ma.nseq = a.nseq; ma.nrows = a.nrows;
   ma.fin = a.fin; ma.ld_in = a.ld_in; ma.fout = a.fout; ma.ld_out = a.ld_out;
   ma.kvec = a.kvec; ma.cvec = a.cvec; ma.dt = a.dt;
+  ma.dens_partial = nullptr; ma.dv = 0.0; ma.edge_flags = 3;
   int rc = get_twiddles(a.N, &ma.tw);
   if (rc) return rc;
+  if (a.mode == ADV_COLS && dens && a.N <= 1024) {
+    // charge density fused into the store phase (one partial row per column tile) + a small reduce kernel
+    const int CB = (a.N == 1024) ? 4 : 8;
+    rc = midfft_density(ma, a, dens, CB, st, false);
+    if (rc) return rc;
+    switch (a.N) {
+      case 256: rc = launch_midfft<midfft::Prog<256, 8, 4, ADV_COLS, 8, true>>(ma, st, "vdfdx.mid"); break;
+      case 512: rc = launch_midfft<midfft::Prog<512, 8, 8, ADV_COLS, 8, true>>(ma, st, "vdfdx.mid"); break;
+      default: rc = launch_midfft<midfft::Prog<1024, 16, 8, ADV_COLS, 4, true>>(ma, st, "vdfdx.mid"); break;
+    }
+    if (rc) return rc;
+    rc = midfft_density(ma, a, dens, CB, st, true);
+    if (rc) return rc;
+    if (dens_done) *dens_done = true;
+    return VPFP_OK;
+  }
   if (a.mode == ADV_COLS) {
     switch (a.N) {
       case 256: return launch_midfft<midfft::Prog<256, 8, 4, ADV_COLS, 8>>(ma, st, "vdfdx.mid");
@@ -376,6 +396,25 @@ struct DensityReq {   // fused charge density request (vdfdx only)
   int edge_flags = 3;
 };
 
+// before the launch (finish = false): scratch for the partial rows; after it: the sum over the column tiles
+static int midfft_density(midfft::Args& ma, const AdvectProg& a, const DensityReq* dens, int CB, cudaStream_t st, bool finish) {
+  const int tiles = (a.nseq + CB - 1) / CB;
+  const long n = (long)a.nsim * a.N;
+  if (!finish) {
+    void* scr = nullptr;
+    int rc = get_scratch(SCR_DENSITY, sizeof(double) * (size_t)tiles * n, &scr);
+    if (rc) return rc;
+    ma.dens_partial = (double*)scr; ma.dv = dens->dv; ma.edge_flags = dens->edge_flags;
+    return VPFP_OK;
+  }
+  {
+    ProfScope ps("vdfdx.density_reduce", st);
+    fast::dens_reduce_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(ma.dens_partial, tiles, 1, n, dens->out, 1, a.N);
+  }
+  CUDA_TRY(cudaGetLastError());
+  return VPFP_OK;
+}
+
 struct ScatterReq {   // last pass stores into peer shards (multi-GPU), see advect_fast.cuh FastArgs
   int mode = 0, nparts = 1, my_rank = 0;
   double* peer[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
@@ -391,7 +430,8 @@ static int run_advect(AdvectProg a, cudaStream_t st, int flags = VPFP_PHASE_EXAC
   const bool small = cells < (1L << 22) && a.N <= 2048;
   const AdvectPlan pl = ((flags & VPFP_FORCE_GENERIC) || small) ? make_advect_plan(a.mode, a.N, 2048, 2048)
                                                                 : make_advect_plan(a.mode, a.N, 128, 128);
-  if (!(scat && scat->mode) && midfft_eligible(a, flags)) return run_midfft(a, st);   // density: the caller's fallback
+  if (!(scat && scat->mode) && midfft_eligible(a, flags))     // density at N = 2048: the caller's fallback
+    return run_midfft(a, st, (dens && dens->out) ? dens : nullptr, dens_done);
   int rc = get_twiddles(a.N, &a.tw);
   if (rc) return rc;
   if (scat && scat->mode && !(fast_eligible(a, pl) && !(flags & VPFP_FORCE_GENERIC)))
