@@ -164,6 +164,28 @@ def test_vdfdx_fused_density(dev, nx, ncols, edge):
     assert rel_err(n.cpu().numpy(), (ref * w).sum(axis=1)) < TOL
 
 
+@pytest.mark.parametrize("nx,ncols", [(4096, 40), (512, 48), (256, 2048)])
+def test_vdfdx_fused_density_of_an_ensemble(dev, nx, ncols):
+    """the same for a batch of simulations with their own wavenumbers: three passes (nx = 4096: the partial sums are
+    parked in a permuted order per simulation) and the mid-size single-pass kernel (density in the store phase)"""
+    from vlapy_b200 import ops
+    rng = np.random.default_rng(nx + ncols)
+    B = 3
+    f = rng.standard_normal((B, nx, ncols)) + 1.0
+    vv = np.linspace(-3.0, 3.0, ncols)
+    kx = np.stack([O.spatial_grid(0.0, 15.0 + 2.0 * b, nx)[2] for b in range(B)])
+    n = torch.empty((B, nx), dtype=torch.float64, device=dev)
+    out = ops.vdfdx_exp(torch.from_numpy(f).to(dev), torch.from_numpy(kx).to(dev), torch.from_numpy(vv).to(dev), 0.3,
+                        flags=1, density_out=n, dv=0.05)
+    w = np.full(ncols, 0.05)
+    w[0] *= 0.5
+    w[-1] *= 0.5
+    for b in range(B):
+        ref = O.vdfdx_exponential(f[b], 0.3, kx[b], vv)
+        assert rel_err(out[b].cpu().numpy(), ref) < TOL
+        assert rel_err(n[b].cpu().numpy(), (ref * w).sum(axis=1)) < TOL
+
+
 def test_vdfdx_ensemble_with_per_simulation_kx(dev):
     from vlapy_b200.core import vlasov
     rng = np.random.default_rng(11)
