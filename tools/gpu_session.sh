@@ -55,7 +55,7 @@ for st in "$@"; do
       timeout 600 ncu --set full --clock-control none --import-source on -k regex:"$arg" -c 4 -f -o ${O}_full \
         python tools/prof_one.py 16384 16384 all 1 > ${O}_full.log 2>&1; tail -2 ${O}_full.log ;;
     sanitizer)
-      SEL="test_fp_sizes_vs_oracle and 4096 or test_single_pass_row_kernel and 257 or test_vdfdx_fused_density and 4096 or test_tridiag or test_mid_size_single_pass_kernels and 512 or test_semi_lagrangian_operators or test_moments_many_short_rows and 512"
+      SEL="test_fp_sizes_vs_oracle and 4096 or test_single_pass_row_kernel and 257 or test_vdfdx_fused_density and 4096 or test_vdfdx_fused_density_of_an_ensemble or test_tridiag or test_mid_size_single_pass_kernels and 512 or test_semi_lagrangian_operators or test_moments_many_short_rows and 512"
       ( timeout 900 compute-sanitizer --tool racecheck --racecheck-report all --print-limit 20 python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "$SEL" 2>&1 | tail -40 ) > ${O}_racecheck.txt
       ( timeout 900 compute-sanitizer --tool memcheck --print-limit 20 python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "$SEL" 2>&1 | tail -25 ) > ${O}_memcheck.txt
       tail -n 4 ${O}_racecheck.txt; tail -n 4 ${O}_memcheck.txt ;;

@@ -20,7 +20,7 @@ for _ in range(reps):
     if which in ("all", "edfdv"):
         ops.edfdv_exp(f, e, kv, 0.5 * cfg["dt"], out=out, flags=1)
     if which in ("all", "vdfdx"):
-        ops.vdfdx_exp(f, kx, v, cfg["dt"], out=out, flags=1)
+        ops.vdfdx_exp(f, kx, v, cfg["dt"], out=out, flags=1, density_out=mom[0], dv=cfg["dv"])   # with the fused density, as in a step
     if which in ("all", "fp", "fpx"):
         ops.fp_step(f, v, cfg["nu"], cfg["dt"], cfg["dv"], "lb", out=out, moments_out=mom, vgrid=vg)
     if which in ("all", "xmodes", "fpx"):
