@@ -15,6 +15,7 @@
 #   full:<regex>     ncu --set full --import-source on of the kernels matching <regex> (tools/prof_one.py)
 #   sanitizer        compute-sanitizer racecheck + memcheck on the kernels with barrier-free prefetch / peer stores
 #   fp64peak         tools/fp64_peak (DFMA chain microbenchmark)
+#   wirebench        tools/wirebench.cu (2 GPUs: NVLink-bound kernel beside a local copy)
 #   smoke            __graft_entry__.smoke()
 TAG=${1:-s}; shift
 cd "$(dirname "$0")/.."
@@ -59,6 +60,9 @@ for st in "$@"; do
       ( timeout 900 compute-sanitizer --tool racecheck --racecheck-report all --print-limit 20 python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "$SEL" 2>&1 | tail -40 ) > ${O}_racecheck.txt
       ( timeout 900 compute-sanitizer --tool memcheck --print-limit 20 python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "$SEL" 2>&1 | tail -25 ) > ${O}_memcheck.txt
       tail -n 4 ${O}_racecheck.txt; tail -n 4 ${O}_memcheck.txt ;;
+    wirebench)
+      # needs 2 GPUs: a wire-bound peer-store kernel beside a local HBM copy, sharing SMs or confined to a few
+      nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o tools/wirebench.bin tools/wirebench.cu && timeout 120 ./tools/wirebench.bin > ${O}_wirebench.txt 2>&1; cat ${O}_wirebench.txt ;;
     fp64peak)
       timeout 120 python tools/fp64_peak.py > ${O}_fp64_peak.txt 2>&1; cat ${O}_fp64_peak.txt ;;
     smoke)
