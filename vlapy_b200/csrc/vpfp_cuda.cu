@@ -408,8 +408,17 @@ static int midfft_density(midfft::Args& ma, const AdvectProg& a, const DensityRe
     return VPFP_OK;
   }
   {
-    ProfScope ps("vdfdx.density_reduce", st);
-    fast::dens_reduce_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(ma.dens_partial, tiles, 1, n, dens->out, 1, a.N);
+    // many tiles, few cells (C2: 128 tiles, 256 cells): the serial sum of one thread per cell is a chain of dependent
+    // loads (12.7 us); eight groups in a first launch, their sums in a second (as for the three passes)
+    const int groups = (tiles >= 64 && tiles % 8 == 0) ? 8 : 1;
+    ProfScope ps("vdfdx.density_reduce", st, groups > 1 ? 2 : 1);
+    const unsigned gx = (unsigned)((n + 255) / 256);
+    if (groups > 1) {
+      fast::dens_reduce_kernel<<<dim3(gx, groups), 256, 0, st>>>(ma.dens_partial, tiles / groups, 1, n, nullptr, 1, a.N);
+      fast::dens_reduce_kernel<<<gx, 256, 0, st>>>(ma.dens_partial, groups, tiles / groups, n, dens->out, 1, a.N);
+    } else {
+      fast::dens_reduce_kernel<<<gx, 256, 0, st>>>(ma.dens_partial, tiles, 1, n, dens->out, 1, a.N);
+    }
   }
   CUDA_TRY(cudaGetLastError());
   return VPFP_OK;
@@ -979,8 +988,8 @@ int vpfp_moments(const double* f, long ld, const double* v, double dv, double* o
   MomentsProg p;
   p.f = f; p.ld = ld; p.v = v; p.dv = dv; p.out = out; p.out_ld = out_ld;
   p.nmom = nmom; p.rows = rows; p.ncols = ncols; p.edge_flags = edge_flags;
-  if (ncols <= 2048 && rows >= 1024) {
-    // many short rows: one warp per row (rowops.h moments_warp_kernel)
+  if ((ncols <= 2048 && rows >= 1024) || ncols <= 512) {
+    // many short rows, or very short rows (C1: 32 x 512): one warp per row (moments_warp_kernel)
     const unsigned grid = (unsigned)((rows + 7) / 8);
     cudaStream_t st = (cudaStream_t)stream;
     const double2* lt = nullptr;
@@ -1192,10 +1201,17 @@ int vpfp_xmodes_partial(const double* f, long ld, double* out, int nmodes, int b
   XmodesProg p;
   p.f = f; p.ld = ld; p.nmodes = nmodes; p.batch = batch; p.nx = nx; p.ncols = ncols;
   p.x_offset = x_offset; p.nx_total = nx_total;
-  // measured configuration: a CTA of 128 threads reads 128 x 16 contiguous bytes of every row; at most 32 row chunks
+  // measured configuration: a CTA of 128 threads reads 128 x 16 contiguous bytes of every row; chunks of 128 rows, at
+  // most 32 row chunks.  Small grids (C1, C2: a handful of CTAs, each walking its rows one group of eight after the
+  // other -- 24 us at 256 x 2048) get shorter chunks, down to 8 rows, until there is a CTA per SM.
   const int threads = 128, env_xch = 32;
   p.cblocks = (ncols + threads - 1) / threads;
-  int xch = nx / 128;
+  int rows_per_chunk = 128;
+  {
+    const long col_ctas = (long)batch * ((ncols / 2 + threads - 1) / threads);
+    while (rows_per_chunk > 8 && col_ctas * ((nx + rows_per_chunk - 1) / rows_per_chunk) < 148) rows_per_chunk >>= 1;
+  }
+  int xch = nx / rows_per_chunk;
   if (xch < 1) xch = 1;
   if (xch > env_xch) xch = env_xch;
   // (measured and rejected at 4096 x 4096: 128 row chunks instead of 32 -- the first stage gains 8 us, the reduction
