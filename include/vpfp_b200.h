@@ -110,7 +110,8 @@ int vpfp_moments(const double *f, long ld, const double *v, double dv, double *o
 
 /* Spectral Poisson: e = driver + Re ifft( i one_over_kx fft(1 - n) ).
  * Replaces vlapy/core/field.py:39-88.  n, driver, e: (batch, nx); one_over_kx: (batch, nx).
- * driver may be NULL.  Any nx >= 2 (powers of two use the FFT path, others a direct DFT). */
+ * driver may be NULL.  Any nx >= 2: powers of two use an FFT (one launch for nx >= 256: the e df/dv kernels of that length
+ * in Poisson mode, two density rows per packed sequence up to nx = 2048), other lengths a direct DFT. */
 int vpfp_poisson(const double *n, const double *one_over_kx, const double *driver, double *e,
                  int batch, int nx, void *stream);
 

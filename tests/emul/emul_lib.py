@@ -194,6 +194,17 @@ def midfft_cols(f, kx, v, dt, batch=1):
     return out
 
 
+def midfft_poisson(n, ook, driver=None):
+    """spectral Poisson solve through midfft.cuh in Poisson mode; n, ook (batch, nx), driver (batch, nx) or None"""
+    n = np.ascontiguousarray(np.atleast_2d(n)); ook = np.ascontiguousarray(np.atleast_2d(ook))
+    batch, nx = n.shape
+    e = np.empty_like(n)
+    d = np.ascontiguousarray(np.atleast_2d(driver)) if driver is not None else None
+    rc = lib().emul_midfft_poisson(_p(n), _p(ook), _p(d) if d is not None else None, _p(e), c_int(batch), c_int(nx))
+    assert rc == 0
+    return e
+
+
 def midfft_cols_density(f, kx, v, dt, dv, edge_flags=3, batch=1):
     """the same with the charge density fused into the store phase; returns (f_out, n (batch, nx))"""
     f = np.ascontiguousarray(f); out = np.empty_like(f)

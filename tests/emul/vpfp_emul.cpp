@@ -334,6 +334,21 @@ extern "C" int emul_midfft(int mode, const double* f_in, long ld_in, double* f_o
   return 0;
 }
 
+// spectral Poisson solve through the mid-size kernel in Poisson mode (two density rows per packed sequence)
+extern "C" int emul_midfft_poisson(const double* n, const double* ook, const double* driver, double* e, int batch, int nx) {
+  midfft::Args a;
+  memset(&a, 0, sizeof(a));
+  a.nsim = 1; a.nrows = batch; a.nseq = (batch + 1) / 2;
+  std::vector<cplx> tw = make_tw(nx);
+  a.fin = n; a.ld_in = nx; a.fout = e; a.ld_out = nx; a.kvec = ook; a.addv = driver; a.tw = tw.data();
+  if (nx == 256) { midfft::Prog<256, 8, 4, ADV_ROWS, 8, false, true> p; p.a = a; run_midfft(p); }
+  else if (nx == 512) { midfft::Prog<512, 8, 8, ADV_ROWS, 4, false, true> p; p.a = a; run_midfft(p); }
+  else if (nx == 1024) { midfft::Prog<1024, 16, 8, ADV_ROWS, 4, false, true> p; p.a = a; run_midfft(p); }
+  else if (nx == 2048) { midfft::Prog<2048, 16, 16, ADV_ROWS, 2, false, true> p; p.a = a; run_midfft(p); }
+  else return 1;
+  return 0;
+}
+
 // v df/dx with the charge density fused into the store phase (Prog<..., DENS = true>); the sum over the column tiles
 // (fast::dens_reduce_kernel on the device) is done here on the host, in tile order
 extern "C" int emul_midfft_cols_density(const double* f_in, long ld_in, double* f_out, long ld_out, const double* kvec,

@@ -341,6 +341,23 @@ def test_midfft_programs(n, monkeypatch):
                 assert rel_err(dens[s], (ref * w).sum(axis=1)) < TOL
 
 
+@pytest.mark.parametrize("nx", [256, 512, 1024, 2048])
+def test_poisson_mid_size_program(nx):
+    """midfft.cuh in Poisson mode (two density rows packed per sequence, multiplier i one_over_kx, driver added by the
+    store) against the oracle's vlapy/core/field.py:39-88: odd and even numbers of rows, per-row wavenumber grids (an
+    ensemble), with and without driver rows"""
+    rng = np.random.default_rng(nx)
+    for batch in (1, 2, 5):
+        k0s = 0.25 + 0.05 * np.arange(batch)
+        grids = [O.spatial_grid(0.0, 2 * np.pi / k, nx) for k in k0s]
+        ook = np.stack([g[3] for g in grids])
+        n = 1.0 + 0.1 * rng.standard_normal((batch, nx))
+        drv = np.stack([0.02 * np.sin(k * g[1]) for k, g in zip(k0s, grids)])
+        ref = np.stack([O.solve_for_field(n[i], ook[i]) for i in range(batch)])
+        assert np.max(np.abs(E.midfft_poisson(n, ook) - ref)) < TOL * np.abs(ref).max()
+        assert np.max(np.abs(E.midfft_poisson(n, ook, drv) - (ref + drv))) < TOL * np.abs(ref).max()
+
+
 @pytest.mark.parametrize("nx", [4096, 8192, 16384])
 def test_poisson_single_launch_program(nx):
     """rowfft.cuh in Poisson mode (one CTA per density row: load 1 - n, multiplier i one_over_kx, add the driver)

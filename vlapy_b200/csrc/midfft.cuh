@@ -40,6 +40,9 @@ struct Args {
   // (trapezoid, vlapy/core/field.py:27-36) over the 2 CB columns of the tile; summed over the tiles by
   // fast::dens_reduce_kernel.  edge_flags: bit 0 / 1 = the first / last column is an end of the global v axis.
   double* dens_partial; double dv; int edge_flags;
+  // Poisson mode (Prog<..., POISSON = true>, ROWS): fin = n [nrows][L], fout = e, kvec = one_over_kx [nrows][L],
+  // addv = driver field [nrows][L] or null
+  const double* addv;
 };
 
 // asynchronous copies global -> shared (host emulation: plain copies)
@@ -63,10 +66,15 @@ VPFP_HD void cp_async_wait() {
 #endif
 }
 
-template <int L_, int R1_, int R2_, int MODE_, int CB_, bool DENS_ = false>
+// POISSON_: the spectral field solve of vlapy/core/field.py:39-88 for nx = L in one launch -- two density rows (two
+// simulations of an ensemble) packed as one complex sequence, loads 1 - n, the pointwise step multiplies by
+// i (one_over_kx[k] - one_over_kx[L-k]) / 2 (the Hermitian part of the reference's multiplier: what survives its np.real)
+// instead of a phase, the store adds the driver row.  Before: the generic shared-memory program, 16 us at nx = 256.
+template <int L_, int R1_, int R2_, int MODE_, int CB_, bool DENS_ = false, bool POISSON_ = false>
 struct Prog {
   static constexpr int L = L_, R1 = R1_, R2 = R2_, MODE = MODE_, CB = CB_;
-  static constexpr bool DENS = DENS_;
+  static constexpr bool DENS = DENS_, POISSON = POISSON_;
+  static_assert(!POISSON_ || (MODE_ == ADV_ROWS && !DENS_), "Poisson mode packs density rows");
   static_assert(!DENS_ || MODE_ == ADV_COLS, "the fused density belongs to v df/dx");
   static_assert(R1 * R2 * 8 == L, "L = R1 * R2 * 8");
   static constexpr int S = L / 8;              // stage-C sub-transforms
@@ -152,6 +160,7 @@ struct Prog {
 #endif
     }
     const long ra = 2 * (long)seq, rb = ra + 1;
+    if (POISSON) return cmake(1.0 - a.fin[ra * a.ld_in + n], (rb < a.nrows) ? 1.0 - a.fin[rb * a.ld_in + n] : 0.0);
     return cmake(a.fin[ra * a.ld_in + n], (rb < a.nrows) ? a.fin[rb * a.ld_in + n] : 0.0);
   }
   VPFP_HD void gstore(const Tile& t, int seq, int n, cplx v) const {
@@ -166,6 +175,10 @@ struct Prog {
       return;
     }
     const long ra = 2 * (long)seq, rb = ra + 1;
+    if (POISSON && a.addv != nullptr) {            // total field = self-consistent field + driver (field.py:66-88)
+      v.x += a.addv[ra * a.ld_out + n];
+      if (rb < a.nrows) v.y += a.addv[rb * a.ld_out + n];
+    }
     a.fout[ra * a.ld_out + n] = v.x;
     if (rb < a.nrows) a.fout[rb * a.ld_out + n] = v.y;
   }
@@ -227,6 +240,26 @@ struct Prog {
     for (int j = 0; j < 8; ++j) D[j * DP + tid] = wa * x[j0 + j].x + wb * x[j0 + j].y;
   }
 
+  // Poisson mode: the pair (k, L-k) of the two packed density rows ra, ra + 1 times i m(k) / (2L), m(k) = (ook[k] - ook[L-k]) / 2
+  VPFP_HD void pair_poisson(cplx& Zr, cplx& Zpr, const int kbin, const bool selfpair, const int seq) const {
+    const bool neg = (2 * kbin > L);
+    const int j = neg ? L - kbin : kbin;                 // |signed frequency index|, 0 .. L/2
+    const long ra = 2 * (long)seq, rb = ra + 1;
+    double ma = 0.0, mb = 0.0;
+    if (seq < a.nseq) {
+      const double* ka = a.kvec + ra * L;
+      ma = 0.5 * (ka[j] - ka[(L - j) % L]);
+      if (rb < a.nrows) mb = 0.5 * (ka[L + j] - ka[L + (L - j) % L]);
+    }
+    const double sc = (neg ? -0.5 : 0.5) / (double)L;
+    const cplx Pa = cmake(0.0, ma * sc), Pb = cmake(0.0, mb * sc);
+    const cplx Z = Zr, Zp = Zpr;
+    const cplx U = cadd(Z, cconj(Zp)), V = csub(Z, cconj(Zp));
+    const cplx X1 = cmul(Pa, U), X2 = cmul(Pb, V);
+    Zr = cadd(X1, X2);
+    if (!selfpair) Zpr = cconj(csub(X1, X2));
+  }
+
   // prefetched: this tile was brought into the thread's own slots by prefetch_own; nexttile: the tile this CTA handles
   // after this one (< 0: none)
   VPFP_HD void phase(int ph, long tile, long nexttile, bool prefetched, int tid, Regs& r, unsigned char* smem) const {
@@ -242,11 +275,11 @@ struct Prog {
       case 0: {
         // ---- phase tables of this tile: T0[j] = exp(-i phi j) / (2L), j < 16; T12[i] = exp(-i phi 16 i)
         const double* K = a.kvec + ((MODE == ADV_COLS) ? (long)t.sim * L : 0);
-        const double kdt = mul_rn(K[1], a.dt);
+        const double kdt = POISSON ? 0.0 : mul_rn(K[1], a.dt);
         cplx* T0 = t0(smem);
         cplx* T12 = t12(smem);
         constexpr int PER = 16 + NT12;
-        for (int w = tid; w < 2 * CB * PER; w += NT) {
+        for (int w = tid; w < (POISSON ? 0 : 2 * CB * PER); w += NT) {
           const int i = w % PER, cb_ = (w / PER) % CB, ch = w / (PER * CB);
           double ca, cbv;
           consts(t.seq0 + cb_, &ca, &cbv);
@@ -312,7 +345,19 @@ struct Prog {
         fft8<-1>(x + 8);
         const cplx* T0 = t0(smem);
         const cplx* T12 = t12(smem);
-        if (!special) {
+        if (POISSON) {
+          if (!special) {
+#pragma unroll
+            for (int pr = 0; pr < 8; ++pr) pair_poisson(x[pr], x[15 - pr], sA + S * pr, false, seq);
+          } else {
+            pair_poisson(x[0], x[0], 0, true, seq);                        // DC: multiplier 0
+            pair_poisson(x[4], x[4], S * 4, true, seq);                    // Nyquist: multiplier 0
+#pragma unroll
+            for (int pr = 1; pr < 4; ++pr) pair_poisson(x[pr], x[8 - pr], S * pr, false, seq);
+#pragma unroll
+            for (int pr = 0; pr < 4; ++pr) pair_poisson(x[8 + pr], x[15 - pr], S / 2 + S * pr, false, seq);
+          }
+        } else if (!special) {
           // A[k3] (bin sA + S k3) pairs with B[7 - k3]
 #pragma unroll
           for (int pr = 0; pr < 8; ++pr) pair_op(x[pr], x[15 - pr], sA + S * pr, false, b, T0, T12);

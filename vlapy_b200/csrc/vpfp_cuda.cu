@@ -1035,6 +1035,22 @@ int vpfp_poisson(const double* n, const double* one_over_kx, const double* drive
       default: return launch_rowfft<rowfft::Prog<8, 16, false, true>>(ra, st, "poisson");
     }
   }
+  if (nx == 256 || nx == 512 || nx == 1024 || nx == 2048) {
+    // mid-size single-pass kernel in Poisson mode (midfft.cuh): two density rows per sequence, one launch
+    midfft::Args ma;
+    memset(&ma, 0, sizeof(ma));
+    ma.nsim = 1; ma.nrows = batch; ma.nseq = (batch + 1) / 2;
+    ma.fin = n; ma.ld_in = nx; ma.fout = e; ma.ld_out = nx; ma.kvec = one_over_kx; ma.addv = driver;
+    int rc = get_twiddles(nx, &ma.tw);
+    if (rc) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    switch (nx) {
+      case 256: return launch_midfft<midfft::Prog<256, 8, 4, ADV_ROWS, 8, false, true>>(ma, st, "poisson");
+      case 512: return launch_midfft<midfft::Prog<512, 8, 8, ADV_ROWS, 4, false, true>>(ma, st, "poisson");
+      case 1024: return launch_midfft<midfft::Prog<1024, 16, 8, ADV_ROWS, 4, false, true>>(ma, st, "poisson");
+      default: return launch_midfft<midfft::Prog<2048, 16, 16, ADV_ROWS, 2, false, true>>(ma, st, "poisson");
+    }
+  }
   AdvectProg a;
   memset(&a, 0, sizeof(a));
   a.mode = ADV_ROWS; a.op = OP_POISSON; a.N = nx;
