@@ -12,7 +12,7 @@ CSRC = os.path.join(os.path.dirname(os.path.dirname(HERE)), "vlapy_b200", "csrc"
 
 
 def build(force=False):
-    deps = [SRC] + [os.path.join(CSRC, n) for n in ("advect.h", "rowops.h", "tridiag.h", "spline.h", "midfft.cuh", "advect_fast.cuh", "vpfp_common.h", "butterflies.h", "rowfft.cuh")]
+    deps = [SRC] + [os.path.join(CSRC, n) for n in ("advect.h", "rowops.h", "tridiag.h", "spline.h", "midfft.cuh", "tinyfft.cuh", "advect_fast.cuh", "vpfp_common.h", "butterflies.h", "rowfft.cuh")]
     if force or not os.path.exists(SO) or any(os.path.getmtime(d) > os.path.getmtime(SO) for d in deps):
         subprocess.check_call(["g++", "-O2", "-ffp-contract=off", "-std=c++17", "-shared", "-fPIC",
                                "-o", SO, SRC])
@@ -192,6 +192,27 @@ def midfft_cols(f, kx, v, dt, batch=1):
                            _p(np.ascontiguousarray(v)), c_double(dt), c_int(batch), c_int(nx), c_int(ncols))
     assert rc == 0
     return out
+
+
+def tiny_cols(f, kx, v, dt, batch=1):
+    """v df/dx for nx = 16 / 32 with the transform in the registers of one thread (tinyfft.cuh); f (batch, nx, ncols)"""
+    f = np.ascontiguousarray(f); out = np.empty_like(f)
+    nx, ncols = f.shape[-2], f.shape[-1]
+    rc = lib().emul_tiny_cols(_p(f), c_long(ncols), _p(out), c_long(ncols), _p(np.ascontiguousarray(kx)),
+                              _p(np.ascontiguousarray(v)), c_double(dt), c_int(batch), c_int(nx), c_int(ncols))
+    assert rc == 0
+    return out
+
+
+def tiny_poisson(n, ook, driver=None):
+    """spectral Poisson solve for nx = 16 / 32 (tinyfft.cuh); n, ook (batch, nx), driver (batch, nx) or None"""
+    n = np.ascontiguousarray(np.atleast_2d(n)); ook = np.ascontiguousarray(np.atleast_2d(ook))
+    batch, nx = n.shape
+    e = np.empty_like(n)
+    d = np.ascontiguousarray(np.atleast_2d(driver)) if driver is not None else None
+    rc = lib().emul_tiny_poisson(_p(n), _p(ook), _p(d) if d is not None else None, _p(e), c_int(batch), c_int(nx))
+    assert rc == 0
+    return e
 
 
 def midfft_poisson(n, ook, driver=None):

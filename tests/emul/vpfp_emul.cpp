@@ -334,6 +334,36 @@ extern "C" int emul_midfft(int mode, const double* f_in, long ld_in, double* f_o
   return 0;
 }
 
+// ---- nx = 16 / 32: whole transform in the registers of one thread (vlapy_b200/csrc/tinyfft.cuh)
+#include "../../vlapy_b200/csrc/tinyfft.cuh"
+extern "C" int emul_tiny_cols(const double* f_in, long ld_in, double* f_out, long ld_out, const double* kvec, const double* cvec,
+                              double dt, int nsim, int nx, int ncols) {
+  const long work = (long)nsim * (ncols / 2);
+  if (nx == 32) {
+    tiny::ColsProg<32> p;
+    p.nsim = nsim; p.nseq = ncols / 2; p.fin = f_in; p.ld_in = ld_in; p.fout = f_out; p.ld_out = ld_out; p.kvec = kvec; p.cvec = cvec; p.dt = dt;
+    run_prog(p, (work + 127) / 128, 128, 0, 1);
+  } else if (nx == 16) {
+    tiny::ColsProg<16> p;
+    p.nsim = nsim; p.nseq = ncols / 2; p.fin = f_in; p.ld_in = ld_in; p.fout = f_out; p.ld_out = ld_out; p.kvec = kvec; p.cvec = cvec; p.dt = dt;
+    run_prog(p, (work + 127) / 128, 128, 0, 1);
+  } else return 1;
+  return 0;
+}
+extern "C" int emul_tiny_poisson(const double* n, const double* ook, const double* driver, double* e, int batch, int nx) {
+  const long work = (batch + 1) / 2;
+  if (nx == 32) {
+    tiny::PoissonProg<32> p;
+    p.nrows = batch; p.n = n; p.ook = ook; p.driver = driver; p.e = e;
+    run_prog(p, (work + 127) / 128, 128, 0, 1);
+  } else if (nx == 16) {
+    tiny::PoissonProg<16> p;
+    p.nrows = batch; p.n = n; p.ook = ook; p.driver = driver; p.e = e;
+    run_prog(p, (work + 127) / 128, 128, 0, 1);
+  } else return 1;
+  return 0;
+}
+
 // spectral Poisson solve through the mid-size kernel in Poisson mode (two density rows per packed sequence)
 extern "C" int emul_midfft_poisson(const double* n, const double* ook, const double* driver, double* e, int batch, int nx) {
   midfft::Args a;

@@ -341,6 +341,32 @@ def test_midfft_programs(n, monkeypatch):
                 assert rel_err(dens[s], (ref * w).sum(axis=1)) < TOL
 
 
+@pytest.mark.parametrize("nx", [16, 32])
+def test_tiny_transform_programs(nx):
+    """tinyfft.cuh (nx = 16 / 32, the reference's Landau grid: whole transform in the registers of one thread) against the
+    oracle: v df/dx of a batch with per-simulation wavenumbers, both signs of dt, a ragged last CTA; the field solve for
+    odd and even numbers of rows with and without a driver"""
+    rng = np.random.default_rng(nx)
+    ncols = 2 * 131
+    vv = np.linspace(-6.4, 6.4, ncols)
+    k0s = (0.3, 0.41)
+    kx = np.stack([O.spatial_grid(0.0, 2 * np.pi / k, nx)[2] for k in k0s])
+    g = rng.standard_normal((2, nx, ncols))
+    for dt in (0.16, -0.05, 0.5):
+        out = E.tiny_cols(g, kx, vv, dt, batch=2)
+        for s in range(2):
+            assert rel_err(out[s], O.vdfdx_exponential(g[s], dt, kx[s], vv)) < TOL
+    for batch in (1, 2, 5):
+        k0b = 0.25 + 0.05 * np.arange(batch)
+        grids = [O.spatial_grid(0.0, 2 * np.pi / k, nx) for k in k0b]
+        ook = np.stack([gr[3] for gr in grids])
+        n = 1.0 + 0.1 * rng.standard_normal((batch, nx))
+        drv = np.stack([0.02 * np.sin(k * gr[1]) for k, gr in zip(k0b, grids)])
+        ref = np.stack([O.solve_for_field(n[i], ook[i]) for i in range(batch)])
+        assert np.max(np.abs(E.tiny_poisson(n, ook) - ref)) < TOL * np.abs(ref).max()
+        assert np.max(np.abs(E.tiny_poisson(n, ook, drv) - (ref + drv))) < TOL * np.abs(ref).max()
+
+
 @pytest.mark.parametrize("nx", [256, 512, 1024, 2048])
 def test_poisson_mid_size_program(nx):
     """midfft.cuh in Poisson mode (two density rows packed per sequence, multiplier i one_over_kx, driver added by the

@@ -11,7 +11,7 @@ ROOT = os.path.dirname(PKG)
 # VPFP_B200_LIB: another build of the same CUDA library (A/B timing of two revisions in one GPU session)
 SO = os.environ.get("VPFP_B200_LIB") or os.path.join(PKG, "lib", "libvpfp_b200.so")
 SRC = os.path.join(PKG, "csrc", "vpfp_cuda.cu")
-HEADERS = [os.path.join(PKG, "csrc", n) for n in ("vpfp_common.h", "advect.h", "rowops.h", "butterflies.h", "rowfft.cuh", "midfft.cuh", "tridiag.h", "spline.h",
+HEADERS = [os.path.join(PKG, "csrc", n) for n in ("vpfp_common.h", "advect.h", "rowops.h", "butterflies.h", "rowfft.cuh", "midfft.cuh", "tinyfft.cuh", "tridiag.h", "spline.h",
                                                     "advect_fast.cuh", "fp_fast.cuh", "fp_reg.cuh")] + [
     os.path.join(ROOT, "include", "vpfp_b200.h")]
 

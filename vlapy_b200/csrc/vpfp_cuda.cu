@@ -19,6 +19,7 @@
 #include "advect_fast.cuh"
 #include "fp_fast.cuh"
 #include "midfft.cuh"
+#include "tinyfft.cuh"
 #include "fp_reg.cuh"
 #include "rowfft.cuh"
 #include "rowops.h"
@@ -439,6 +440,28 @@ static int run_advect(AdvectProg a, cudaStream_t st, int flags = VPFP_PHASE_EXAC
   const bool small = cells < (1L << 22) && a.N <= 2048;
   const AdvectPlan pl = ((flags & VPFP_FORCE_GENERIC) || small) ? make_advect_plan(a.mode, a.N, 2048, 2048)
                                                                 : make_advect_plan(a.mode, a.N, 128, 128);
+  if (!(scat && scat->mode) && a.op == OP_PHASE && a.mode == ADV_COLS && (a.N == 16 || a.N == 32) &&
+      (flags & VPFP_PHASE_TABLE) && !(flags & (VPFP_FORCE_GENERIC | VPFP_FORCE_THREE_PASS)) && !(a.ld_in & 1) && !(a.ld_out & 1) &&
+      !(((uintptr_t)a.fin | (uintptr_t)a.fout) & 15)) {
+    // nx = 16 / 32 (the reference's Landau grid): the whole x transform in the registers of one thread (tinyfft.cuh);
+    // density: the caller's fallback
+    const long work = (long)a.nsim * a.nseq;
+    const unsigned grid = (unsigned)((work + 127) / 128);
+    ProfScope ps("vdfdx.tiny", st);
+    if (a.N == 32) {
+      tiny::ColsProg<32> p;
+      p.nsim = a.nsim; p.nseq = a.nseq; p.fin = a.fin; p.ld_in = a.ld_in; p.fout = a.fout; p.ld_out = a.ld_out;
+      p.kvec = a.kvec; p.cvec = a.cvec; p.dt = a.dt;
+      prog128_kernel<tiny::ColsProg<32>><<<grid, 128, 0, st>>>(p);
+    } else {
+      tiny::ColsProg<16> p;
+      p.nsim = a.nsim; p.nseq = a.nseq; p.fin = a.fin; p.ld_in = a.ld_in; p.fout = a.fout; p.ld_out = a.ld_out;
+      p.kvec = a.kvec; p.cvec = a.cvec; p.dt = a.dt;
+      prog128_kernel<tiny::ColsProg<16>><<<grid, 128, 0, st>>>(p);
+    }
+    CUDA_TRY(cudaGetLastError());
+    return VPFP_OK;
+  }
   if (!(scat && scat->mode) && midfft_eligible(a, flags))     // density at N = 2048: the caller's fallback
     return run_midfft(a, st, (dens && dens->out) ? dens : nullptr, dens_done);
   int rc = get_twiddles(a.N, &a.tw);
@@ -1034,6 +1057,23 @@ int vpfp_poisson(const double* n, const double* one_over_kx, const double* drive
       case 8192: return launch_rowfft<rowfft::Prog<16, 16, false, true>>(ra, st, "poisson");
       default: return launch_rowfft<rowfft::Prog<8, 16, false, true>>(ra, st, "poisson");
     }
+  }
+  if (nx == 16 || nx == 32) {
+    // the reference's Landau grid: two density rows in the registers of one thread (tinyfft.cuh)
+    cudaStream_t st = (cudaStream_t)stream;
+    const unsigned grid = (unsigned)(((batch + 1) / 2 + 127) / 128);
+    ProfScope ps("poisson", st);
+    if (nx == 32) {
+      tiny::PoissonProg<32> p;
+      p.nrows = batch; p.n = n; p.ook = one_over_kx; p.driver = driver; p.e = e;
+      prog128_kernel<tiny::PoissonProg<32>><<<grid, 128, 0, st>>>(p);
+    } else {
+      tiny::PoissonProg<16> p;
+      p.nrows = batch; p.n = n; p.ook = one_over_kx; p.driver = driver; p.e = e;
+      prog128_kernel<tiny::PoissonProg<16>><<<grid, 128, 0, st>>>(p);
+    }
+    CUDA_TRY(cudaGetLastError());
+    return VPFP_OK;
   }
   if (nx == 256 || nx == 512 || nx == 1024 || nx == 2048) {
     // mid-size single-pass kernel in Poisson mode (midfft.cuh): two density rows per sequence, one launch
