@@ -226,7 +226,12 @@ int emul_xmodes(const double* f, long ld, double* out, int nmodes, int batch, in
   p.x_offset = 0; p.nx_total = nx;
   const int threads = 128;
   p.cblocks = (ncols + threads - 1) / threads;
-  int xch = nx / 128;
+  int rows_per_chunk = 128;                        // the chunk rule of vpfp_xmodes_partial
+  {
+    const long col_ctas = (long)batch * ((ncols / 2 + threads - 1) / threads);
+    while (rows_per_chunk > 8 && col_ctas * ((nx + rows_per_chunk - 1) / rows_per_chunk) < 148) rows_per_chunk >>= 1;
+  }
+  int xch = nx / rows_per_chunk;
   if (xch < 1) xch = 1;
   if (xch > 32) xch = 32;
   p.xchunks = xch;
