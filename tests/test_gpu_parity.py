@@ -236,6 +236,25 @@ def test_field_solver_unit_cases(dev):
         assert err < TOL * max(np.abs(ref).max(), 1e-3), (nx, err)     # nx = 2 has only DC + Nyquist: E = 0
 
 
+@pytest.mark.parametrize("nx", [16, 32, 64, 256, 512, 1024, 2048, 4096, 16384])
+def test_field_solve_of_an_ensemble_every_kernel(dev, nx):
+    """the spectral field solve for batches of density rows with their own wavenumber grids and driver rows: in-register
+    transforms (nx = 16, 32), generic program (64), mid-size kernel in Poisson mode (256 .. 2048, two rows per packed
+    sequence: odd and even batch sizes), row-FFT kernel in Poisson mode (4096, 16384)"""
+    from vlapy_b200 import ops
+    rng = np.random.default_rng(nx)
+    for batch in (1, 2, 5):
+        k0s = 0.25 + 0.05 * np.arange(batch)
+        grids = [O.spatial_grid(0.0, 2 * np.pi / k, nx) for k in k0s]
+        ook = np.stack([g[3] for g in grids])
+        n = 1.0 + 0.1 * rng.standard_normal((batch, nx))
+        drv = np.stack([0.02 * np.sin(k * g[1]) for k, g in zip(k0s, grids)])
+        ref = np.stack([O.solve_for_field(n[i], ook[i]) for i in range(batch)])
+        nd, od, dd = (torch.from_numpy(a).to(dev) for a in (n, ook, drv))
+        assert np.max(np.abs(ops.poisson(nd, od).cpu().numpy() - ref)) < TOL * np.abs(ref).max()
+        assert np.max(np.abs(ops.poisson(nd, od, dd).cpu().numpy() - (ref + drv))) < TOL * np.abs(ref).max()
+
+
 def test_collision_unit_cases(dev):
     """tests/test_collisions.py of the reference: 16 steps at nx=2, nv=1024, nu=1e-2, dt=0.1."""
     from vlapy_b200.core import step
