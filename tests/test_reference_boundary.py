@@ -167,3 +167,43 @@ def test_initial_storage_dictionary_matches_the_reference(ref, b200_on_cpu):
             assert np.asarray(a[k]).shape == np.asarray(b[k]).shape, k
             assert np.asarray(a[k]).dtype == np.asarray(b[k]).dtype, k
             np.testing.assert_array_equal(np.asarray(a[k]), np.asarray(b[k]))
+
+
+def test_restart_from_a_stored_state_on_the_host_logic(ref, b200_on_cpu):
+    """SURVEY 8f N3 (restart, the reference's TODO at vlapy/manager.py:118-119): a fresh inner loop that resumes from the
+    host copy of the state after loop 1 reproduces loop 2 of an uninterrupted run -- and loop 2 of the reference's own
+    numpy inner loop on the same setup"""
+    bo, _ = b200_on_cpu
+    ol = ref.outer_loop
+    k0, steps, loops = 0.35, 6, 2
+    p = _params(ref, k0, 16, 128, 1000, 4000, -2)
+    pulse = {"first pulse": {"start_time": 0, "t_L": 6, "t_wL": 2.5, "t_R": 25, "t_wR": 2.5, "w0": p["w_epw"],
+                             "a0": 4e-2, "k0": k0}}
+    stuff, want = _run(ol, copy.deepcopy(p), pulse, steps, loops)
+    pb = copy.deepcopy(p)
+    pb["backend"]["core"] = "b200"
+    pb["backend"]["cuda_graph"] = False
+    stuff["pulse_dictionary"] = pulse
+
+    def one_loop(cfg, inner, li):
+        idx = np.arange(li * steps, (li + 1) * steps)
+        return inner(temp_storage=cfg, driver_array=np.array(stuff["driver"][idx]), time_array=np.array(stuff["t"][idx]))
+
+    cfg, inner = bo.get_sim_config_and_inner_loop_step(pb, stuff, steps, Rules.rules_to_store_f)
+    cfg = one_loop(cfg, inner, 0)
+    f1, e1, cum1 = np.array(cfg["f"]), np.array(cfg["e"]), float(cfg["series"]["mean_cum_de2"][-1])
+    cfg = one_loop(cfg, inner, 1)
+    straight = {"f": np.array(cfg["f"]), "e": np.array(cfg["e"]),
+                "series": {k: np.array(v) for k, v in cfg["series"].items()}}
+    # restart: a FRESH configuration and inner loop, fed with the stored state
+    cfg2, inner2 = bo.get_sim_config_and_inner_loop_step(pb, stuff, steps, Rules.rules_to_store_f)
+    cfg2 = bo.resume_from(cfg2, f1, e1, mean_cum_de2_previous=cum1)
+    cfg2 = one_loop(cfg2, inner2, 1)
+    np.testing.assert_array_equal(np.asarray(cfg2["f"]), straight["f"])
+    np.testing.assert_array_equal(np.asarray(cfg2["e"]), straight["e"])
+    for k in ("mean_n", "mean_T", "mean_e2", "mean_cum_de2"):
+        np.testing.assert_allclose(np.asarray(cfg2["series"][k]), straight["series"][k], rtol=1e-14, atol=0)
+        np.testing.assert_allclose(np.asarray(cfg2["series"][k]), want[1]["series"][k], rtol=1e-9, atol=1e-15)
+    assert np.max(np.abs(np.asarray(cfg2["f"]) - want[1]["f"])) < 1e-11 * np.max(np.abs(want[1]["f"]))
+    with pytest.raises(ValueError):
+        bo.resume_from(cfg2, f1[0], e1)
