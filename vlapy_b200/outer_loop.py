@@ -108,20 +108,26 @@ class _GraphStep:
     is ~25 kernels of a few microseconds, so the Python/launch overhead dominates.  The captured
     step reads its time and driver row from a small device input buffer and writes everything the
     storage step records into one staging row, so a replay costs three launches from Python
-    (input copy, graph, staging copy).  Needs the device-side driver (``pulse_dictionary``)."""
+    (input copy, graph, staging copy).  The state ``e`` and the moment rows ARE slices of the staging row and the x-mode
+    kernel writes its slice directly: no copies between them inside the graph (each was a launch of its own, 2-3 us of a
+    60-90 us step); the driver rows are not staged at all, the caller has them.  Needs the device-side driver
+    (``pulse_dictionary``)."""
 
     def __init__(self, all_params, stuff, nx, nv, nmodes_shape, modes_complex, dev):
         self.vp_step, self.fp_step, self.fused, self.store_f = step.get_step_parts(all_params, stuff)
         self.v_d, self.dv = const(stuff["v"]), float(stuff["dv"])
         self.nx, self.nv = nx, nv
         self.inp = torch.zeros(1 + nx, dtype=torch.float64, device=dev)            # [t, driver row]
-        self.e = torch.zeros(nx, dtype=torch.float64, device=dev)
         self.f = torch.zeros((nx, nv), dtype=torch.float64, device=dev)
-        self.mom = torch.zeros((8, nx), dtype=torch.float64, device=dev)
         self.n_modes = int(np.prod(nmodes_shape))
         self.modes_complex = bool(modes_complex)
-        nstage = 8 * nx + 7 + (2 * self.n_modes if self.modes_complex else self.n_modes)
+        # staging row: [e (nx) | eight moment rows (8 nx) | seven series entries + 1 pad | stored modes]
+        nstage = 9 * nx + 8 + (2 * self.n_modes if self.modes_complex else self.n_modes)
         self.stage = torch.zeros(nstage, dtype=torch.float64, device=dev)
+        self.e = self.stage[0:nx]
+        self.mom = self.stage[nx:9 * nx].view(8, nx)
+        rule = stuff["rules_to_store_f"]
+        self.xmodes_direct = self.modes_complex and rule["space"][0] == "k0" and self.n_modes % nv == 0
         self.graph = None
 
     def _body(self):
@@ -135,14 +141,14 @@ class _GraphStep:
             f = self.fp_step(f=f)
             ops.moments(f, self.v_d, self.dv, nmom=8, out=self.mom)
         st = self.stage
-        st[0:nx] = e
-        st[nx:2 * nx] = de
-        st[2 * nx:8 * nx] = self.mom[:6].reshape(-1)
-        ops.series(self.mom, e, de, out=st[8 * nx:8 * nx + 7])
-        m = self.store_f(f)
-        tail = st[8 * nx + 7:]
-        tail.copy_(torch.view_as_real(m).reshape(-1) if self.modes_complex else m.reshape(-1))
-        self.e.copy_(e)
+        ops.series(self.mom, e, de, out=st[9 * nx:9 * nx + 7])
+        tail = st[9 * nx + 8:]
+        if self.xmodes_direct:
+            ops.xmodes(f, self.n_modes // self.nv, out=tail.view(1, self.n_modes // self.nv, self.nv, 2))
+        else:
+            m = self.store_f(f)
+            tail.copy_(torch.view_as_real(m).reshape(-1) if self.modes_complex else m.reshape(-1))
+        self.e.copy_(e)                                  # = the e slice of the staging row
         self.f.copy_(f)
 
     def capture(self):
@@ -208,9 +214,11 @@ def get_inner_loop_stepper(all_params, stuff_for_time_loop, steps_in_loop):
             gs.graph.replay()
             rows[it].copy_(gs.stage)
         d["e"], d["f"] = gs.e.clone(), gs.f.clone()
-        d["fields"].copy_(rows[:, :8 * nx].reshape(nt, 8, nx).permute(1, 0, 2))
-        d["series_rows"].copy_(rows[:, 8 * nx:8 * nx + 7])
-        tail = rows[:, 8 * nx + 7:]
+        d["fields"][0].copy_(rows[:, :nx])                                                  # FIELD_KEYS: e, driver, six moments
+        d["fields"][1].copy_(drv)
+        d["fields"][2:8].copy_(rows[:, nx:7 * nx].reshape(nt, 6, nx).permute(1, 0, 2))
+        d["series_rows"].copy_(rows[:, 9 * nx:9 * nx + 7])
+        tail = rows[:, 9 * nx + 8:]
         if gs.modes_complex:
             d["stored_f"].copy_(torch.view_as_complex(tail.reshape(nt, -1, 2).contiguous()).reshape(d["stored_f"].shape))
         else:
