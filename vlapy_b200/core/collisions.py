@@ -18,8 +18,8 @@ def get_collision_operator(vax, nv, nx, nu, dt, dv, operator="lb"):
     v_d = const(vax)
     vgrid = ops.linspace_params(vax)      # np.linspace grids get the specialised kernel
 
-    def collide(f_xv, moments_out=None):
-        return ops.fp_step(f_xv, v_d, nu, dt, dv, operator, moments_out=moments_out, vgrid=vgrid)
+    def collide(f_xv, moments_out=None, out=None):
+        return ops.fp_step(f_xv, v_d, nu, dt, dv, operator, out=out, moments_out=moments_out, vgrid=vgrid)
 
     return collide
 

@@ -71,9 +71,11 @@ def get_collision_step(stuff_for_time_loop, all_params):
             nu=stuff_for_time_loop["nu"], dt=stuff_for_time_loop["dt"], dv=stuff_for_time_loop["dv"],
             operator=all_params["fokker-planck"]["type"])
 
-        def take_collision_step(f, moments_out=None):
+        def take_collision_step(f, moments_out=None, out=None):
+            # moments_out / out (device tensors): b200 extensions for callers that own their buffers (storage step,
+            # captured step); the reference's signature is take_collision_step(f)
             f_d, host = to_dev(f)
-            return back(collide(f_d.contiguous(), moments_out=moments_out), host)
+            return back(collide(f_d.contiguous(), moments_out=moments_out, out=out), host)
 
         take_collision_step.fuses_moments = True
     else:

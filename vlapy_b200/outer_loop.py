@@ -136,7 +136,7 @@ class _GraphStep:
         de = self.inp[1:]
         e, f = self.vp_step(e=self.e, f=self.f, t=t)
         if self.fused:
-            f = self.fp_step(f, moments_out=self.mom)
+            f = self.fp_step(f, moments_out=self.mom, out=self.f)      # straight into the state buffer (f is a new tensor)
         else:
             f = self.fp_step(f=f)
             ops.moments(f, self.v_d, self.dv, nmom=8, out=self.mom)
@@ -149,7 +149,8 @@ class _GraphStep:
             m = self.store_f(f)
             tail.copy_(torch.view_as_real(m).reshape(-1) if self.modes_complex else m.reshape(-1))
         self.e.copy_(e)                                  # = the e slice of the staging row
-        self.f.copy_(f)
+        if f.data_ptr() != self.f.data_ptr():
+            self.f.copy_(f)
 
     def capture(self):
         side = torch.cuda.Stream()
